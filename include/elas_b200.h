@@ -1,0 +1,179 @@
+/* elas_b200.h -- C-ABI of the B200-native ELAS stereo hot path (libelas_b200.so).
+ *
+ * Plain pointers and sizes only; no C++ or framework types cross this boundary.
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * repository root).  The reference's own exported C symbols (generatePointCloud / clean /
+ * getColor, src/parallel_includes/main/stereo_vision.cu:113-127,574-637) are declared in
+ * include/stereo_vision_c.h and live in the same shared library.
+ *
+ * Error convention: functions returning int return 0 on success and a negative svb_status on
+ * failure; svb_last_error() gives the message.  There is NO CPU fallback: without a CUDA device
+ * svb_create() fails with SVB_ERR_NO_DEVICE.
+ */
+#ifndef ELAS_B200_H
+#define ELAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* POD mirror of Elas::parameters (src/parallel_includes/elas/elas.h:58-83): same field order,
+ * bools widened to int32 so that every field is 4 bytes. */
+typedef struct svb_params {
+    int32_t disp_min;
+    int32_t disp_max;
+    float support_threshold;
+    int32_t support_texture;
+    int32_t candidate_stepsize;
+    int32_t incon_window_size;
+    int32_t incon_threshold;
+    int32_t incon_min_support;
+    int32_t add_corners;
+    int32_t grid_size;
+    float beta;
+    float gamma;
+    float sigma;
+    float sradius;
+    int32_t match_texture;
+    int32_t lr_threshold;
+    float speckle_sim_threshold;
+    int32_t speckle_size;
+    int32_t ipol_gap_width;
+    int32_t filter_median;
+    int32_t filter_adaptive_mean;
+    int32_t postprocess_only_left;
+    int32_t subsampling;
+} svb_params;
+
+enum svb_setting { SVB_ROBOTICS = 0, SVB_MIDDLEBURY = 1, SVB_PIPELINE = 2 };
+
+enum svb_status {
+    SVB_OK = 0,
+    SVB_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the library never computes on the CPU */
+    SVB_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+    SVB_ERR_ARG = -3,         /* invalid argument */
+    SVB_ERR_UNSUPPORTED = -4, /* parameter combination not implemented (e.g. subsampling) */
+    SVB_ERR_FEW_SUPPORT = -5  /* < 3 support points: outputs left untouched, like elas.cpp:64-69 */
+};
+
+/* adaptive-mean weight form (SURVEY.md finding 3) */
+enum svb_mean_mode {
+    SVB_MEAN_SERIAL_QUANTISED = 0, /* serial reference: bit-mask "abs" (elas.cpp:1329) -> weights {4,2,0} */
+    SVB_MEAN_TRUE_ABS = 1          /* parallel reference: max(-x,x) (src/parallel_includes/elas/elas.cpp:1552) */
+};
+
+typedef struct svb_context svb_context;
+
+const char *svb_last_error(void);
+const char *svb_version(void);
+int svb_device_count(void);
+
+/* Elas::parameters(setting) (src/parallel_includes/elas/elas.h:86-142).  SVB_PIPELINE is the preset
+ * generateDisparityMap() builds (src/parallel_includes/main/stereo_vision.cu:315-319):
+ * MIDDLEBURY + postprocess_only_left + filter_adaptive_mean. */
+int svb_default_params(int setting, svb_params *out);
+
+/* Replaces `ElasGPU elas(param)` (src/parallel_includes/elas/elas_gpu.h:26-33) plus the lazy
+ * ElasGPU::memInit (elas_gpu.cu:289-306): all device arenas, pinned staging buffers, streams and
+ * the host Delaunay worker pool are created once, sized for `chunk` frames of width x height in
+ * flight per lane.  device < 0 picks the current device. */
+svb_context *svb_create(const svb_params *params, int width, int height, int chunk, int device);
+void svb_destroy(svb_context *ctx);
+int svb_set_mean_mode(svb_context *ctx, int mode);
+int svb_set_delaunay_threads(svb_context *ctx, int n_threads);
+
+/* Elas::process (src/parallel_includes/elas/elas.h:151-160, serial semantics of
+ * src/serial_includes/elas/elas.cpp:31-150).  Host buffers; I1/I2 are u8 with `stride` bytes per
+ * line; D1/D2 are caller-allocated width*height floats. */
+int svb_process(svb_context *ctx, const uint8_t *I1, const uint8_t *I2, int stride, float *D1, float *D2);
+
+/* ---- stage taps of the most recent svb_process() call (parity harness) ---------------------
+ * With tap mode on, svb_process() snapshots every intermediate; svb_tap copies one to the host.
+ * names: desc1 desc2 dcan_raw dcan support tri1 tri2 planes1 planes2 grid1 grid2 owner1 owner2
+ *        D1raw D2raw D1lr D2lr D1seg D1gap D1mean D1med (and the D2* counterparts)
+ * Returns the number of bytes written, or a negative svb_status. */
+int svb_set_tap_mode(svb_context *ctx, int on);
+int64_t svb_tap(svb_context *ctx, const char *name, void *dst, int64_t capacity_bytes);
+
+/* Use a caller-supplied triangle list (n x {c1,c2,c3}) for side 0 (left) / 1 (right) in the next
+ * svb_process() calls instead of the host Delaunay stage; n < 0 restores the built-in stage.
+ * Replaces the output of Elas::computeDelaunayTriangulation (elas.cpp:442-501) for
+ * stage-isolated parity (SURVEY.md finding 7). */
+int svb_inject_triangles(svb_context *ctx, int side, const int32_t *tri, int n);
+
+/* ---- stage-isolated entry points (host in / host out, one frame) ---------------------------- */
+/* Descriptor::Descriptor (src/common_includes/elas/descriptor.cpp:30-39): out = 16*W*H bytes */
+int svb_stage_descriptor(svb_context *ctx, const uint8_t *I, int stride, uint8_t *desc_out);
+/* Elas::computeSupportMatches (elas.cpp:373-440): dcan_raw/dcan are ch*cw int16 (may be NULL),
+ * support is cap x {u,v,d}; returns the number of support points via *n_out. */
+int svb_stage_support(svb_context *ctx, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int16_t *dcan,
+                      int32_t *support, int cap, int *n_out);
+/* Elas::computeDelaunayTriangulation (elas.cpp:442-501) -- the host stage on its own */
+int svb_stage_delaunay(const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out);
+/* Elas::computeDisparityPlanes (elas.cpp:503-575): planes = m x {t1a,t1b,t1c,t2a,t2b,t2c} */
+int svb_stage_planes(svb_context *ctx, const int32_t *support, int n, const int32_t *tri, int m, float *planes);
+/* Elas::createGrid (elas.cpp:577-653): grid = gh*gw*(disp_max+2) int32, reference layout */
+int svb_stage_grid(svb_context *ctx, const int32_t *support, int n, int right_image, int32_t *grid);
+/* Elas::computeDisparity + findMatch (elas.cpp:688-944) */
+int svb_stage_disparity(svb_context *ctx, const int32_t *support, int n, const int32_t *tri, int m, const uint8_t *desc1,
+                        const uint8_t *desc2, int right_image, float *D);
+/* Elas::leftRightConsistencyCheck (elas.cpp:946-1011), in place on both */
+int svb_stage_lr_check(svb_context *ctx, float *D1, float *D2);
+/* Elas::removeSmallSegments / gapInterpolation / adaptiveMean / median (elas.cpp:1013,1126,1297,1496) */
+int svb_stage_remove_small_segments(svb_context *ctx, float *D);
+int svb_stage_gap_interpolation(svb_context *ctx, float *D);
+int svb_stage_adaptive_mean(svb_context *ctx, float *D);
+int svb_stage_median(svb_context *ctx, float *D);
+/* generateDisparityMap tail + projectParallel (stereo_vision.cu:324,188-212):
+ * dmap = saturate_u8(rint(4*D)); points = XR * (Q*[x y d 1]^T)_{xyz/w} + XT.  dmap_out may be NULL. */
+int svb_stage_reproject(svb_context *ctx, const float *D, const double *Q16, const double *XR9, const double *XT3,
+                        uint8_t *dmap_out, double *points_out);
+
+/* ---- frame-batch pipeline (BASELINE.json configs[1]: 1242x375 x 1024 frames) ------------------
+ * Frames are independent: a batch is cut into chunks that flow through
+ * descriptor+support (GPU) -> Delaunay (host worker pool) -> planes..reproject (GPU), with the
+ * lanes overlapping one another.  Replaces the per-frame loop imageLoop()/generatePointCloud()
+ * (stereo_vision.cu:645-697,574-632). */
+int svb_set_calibration(svb_context *ctx, const double *Q16, const double *XR9, const double *XT3);
+/* copy n frames (tight W*H u8 each) into the device-resident input store */
+int svb_batch_upload(svb_context *ctx, const uint8_t *left, const uint8_t *right, int n_frames);
+/* run the whole path on the resident inputs; results stay resident.  flags: SVB_OUT_* */
+enum svb_out_flags { SVB_OUT_DISPARITY = 1, SVB_OUT_POINTS = 2 };
+int svb_batch_run(svb_context *ctx, int n_frames, int flags);
+int svb_batch_download_disparity(svb_context *ctx, int frame, float *D1_out);
+int svb_batch_download_points(svb_context *ctx, int frame, double *points_out);
+/* end to end from pinned or pageable HOST buffers: H2D inputs, run, D2H outputs, all inside */
+int svb_batch_run_host(svb_context *ctx, const uint8_t *left, const uint8_t *right, int n_frames, int flags, float *D1_out,
+                       double *points_out);
+
+/* timing / accounting of the most recent batch or process call */
+typedef struct svb_stats {
+    double gpu_ms_total;       /* CUDA-event time from first to last kernel of the call */
+    double delaunay_ms_total;  /* summed host time inside the Delaunay stage (all workers) */
+    double delaunay_ms_wall;   /* wall time the pipeline waited on the host stage */
+    int64_t kernel_launches;   /* kernels launched by this library during the call */
+    int64_t support_points;    /* summed over frames */
+    int64_t triangles;         /* summed over frames, both sides */
+    int64_t frames;
+    int64_t frames_failed;     /* frames with < 3 support points */
+    double stage_ms[24];       /* per-stage CUDA-event time, index = svb_stage_id */
+} svb_stats;
+int svb_get_stats(svb_context *ctx, svb_stats *out);
+const char *svb_stage_name(int stage_id);
+int svb_set_stage_timing(svb_context *ctx, int on);
+
+/* Deterministic synthetic rectified stereo pair of known disparity (bench / parity INPUT generator, host only;
+ * SURVEY.md 8d).  left/right: W*H u8 each.  slanted = 0: bands of disparity 8/24/48; 1: d = 10 + 0.03 u. */
+int svb_synth_pair(int frame_index, int width, int height, int slanted, uint8_t *left, uint8_t *right);
+
+/* pinned host memory helpers for callers that want the e2e path at full PCIe rate */
+void *svb_host_alloc(size_t bytes);
+void svb_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,6 @@
+"""B200-native ELAS stereo hot path: CUDA kernels + C-ABI in csrc/, ctypes host mirror in binding.py.
+
+The directory name is fixed by the build contract and is not a Python identifier; load it by path
+(tests/conftest.py: load_binding()) under the module name `elas_b200`.
+"""
+from . import binding  # noqa: F401

@@ -1,0 +1,24 @@
+// Host stage: Delaunay triangulation of the support points (the one inherently sequential stage of the path).
+//
+// Replaces Elas::computeDelaunayTriangulation -> triangulate("zQB")
+// (src/serial_includes/elas/elas.cpp:442-501, src/common_includes/elas/triangle.cpp:8116).
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace svb {
+
+// Reusable scratch memory so that the per-frame stage performs no heap allocation in steady state.
+struct DelaunayScratch {
+    std::vector<int32_t> storage;  // coordinates (with a sentinel in front), triangle records, sort arrays
+};
+
+// support: n x {u,v,d}.  Left image (right_image = 0) triangulates (u,v), right image (u-d,v).
+// tri_out receives up to `cap` triangles as {c1,c2,c3} = indices into `support`, in the exact order and corner
+// rotation the reference emits.  Returns the number of triangles (which may exceed cap; only cap are stored).
+int delaunay_support(const int32_t *support, int n, int right_image, int32_t *tri_out, int cap, DelaunayScratch &scratch);
+
+// Same on explicit integer coordinates.
+int delaunay_xy(const int32_t *x, const int32_t *y, int n, int32_t *tri_out, int cap, DelaunayScratch &scratch);
+
+}  // namespace svb

@@ -1,0 +1,127 @@
+// removeSmallSegments as GPU connected components.
+//
+// Replaces Elas::removeSmallSegments (src/serial_includes/elas/elas.cpp:1013-1124): 4-connected components over
+// the relation "both pixels valid (>= 0) and |D(p) - D(q)| <= speckle_sim_threshold"; every component with fewer
+// than speckle_size pixels is set to -10.  The reference grows segments breadth-first from scan-order seeds, but
+// the relation is symmetric, so the partition (and therefore the result) does not depend on the order.
+// (Invalid pixels are -10 after the L/R check, |(-10) - d| >= 10 > threshold, so they never join a segment.)
+//
+// Algorithm: lock-free union-find over pixel indices (roots are the minimum index of a component).
+//   1. init   : every pixel links to the leftmost pixel of its horizontal run (warp ballot, no atomics);
+//   2. merge  : vertical edges and run boundaries are united with atomicMin hooks;
+//   3. count  : each pixel finds its root and adds 1 to the root's counter;
+//   4. prune  : pixels whose root counts < speckle_size become -10.
+#include "svb_internal.h"
+
+namespace svb {
+
+namespace {
+
+__device__ __forceinline__ bool similar(float a, float b, float thr) { return a >= 0.f && b >= 0.f && fabsf(__fsub_rn(a, b)) <= thr; }
+
+__device__ __forceinline__ int find_root(const int32_t *labels, int i) {
+    int p = labels[i];
+    while (p != i) {
+        i = p;
+        p = labels[i];
+    }
+    return i;
+}
+
+__device__ void unite(int32_t *labels, int a, int b) {
+    while (true) {
+        a = find_root(labels, a);
+        b = find_root(labels, b);
+        if (a == b) return;
+        if (a > b) {
+            int t = a;
+            a = b;
+            b = t;
+        }
+        // hook the larger root under the smaller one
+        const int old = atomicMin(labels + b, a);
+        if (old == b) return;
+        b = old;
+    }
+}
+
+// grid: (ceil(W/128), H, nimg)   labels are indices local to the image
+__global__ void __launch_bounds__(128) k_ccl_init(const float *__restrict__ D_all, int32_t *__restrict__ labels_all, int32_t *__restrict__ sizes_all,
+                                                 int W, int H, float thr) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    const size_t img = (size_t)blockIdx.z * W * H;
+    const int lane = threadIdx.x & 31;
+    const bool in = u < W;
+    const int idx = v * W + u;
+    const float d = in ? D_all[img + idx] : -10.f;
+    const float dl = (in && u > 0) ? D_all[img + idx - 1] : -10.f;
+    // linked to the left neighbour?
+    const bool link = in && similar(d, dl, thr);
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, link);
+    if (!in) return;
+    // run start inside this warp: the nearest lane at or below `lane` whose link bit is clear
+    const unsigned clear_below = ~bal & ((2u << lane) - 1u);  // lanes <= lane with no left link (lane 31: all bits)
+    const unsigned mask = (lane == 31) ? ~bal : clear_below;
+    int start_lane = mask ? (31 - __clz(mask)) : -1;
+    int label;
+    if (start_lane >= 0) {
+        label = idx - (lane - start_lane);
+    } else {
+        // the run continues into the previous warp: link to the pixel just left of this warp's first lane
+        label = idx - lane - 1;
+    }
+    labels_all[img + idx] = label;
+    sizes_all[img + idx] = 0;
+}
+
+__global__ void __launch_bounds__(128) k_ccl_merge(const float *__restrict__ D_all, int32_t *__restrict__ labels_all, int W, int H, float thr) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (u >= W || v == 0) return;
+    const size_t img = (size_t)blockIdx.z * W * H;
+    const int idx = v * W + u;
+    const float d = D_all[img + idx];
+    const float du = D_all[img + idx - W];
+    if (similar(d, du, thr)) unite(labels_all + img, idx, idx - W);
+}
+
+__global__ void __launch_bounds__(128) k_ccl_count(int32_t *__restrict__ labels_all, int32_t *__restrict__ sizes_all, int W, int H) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (u >= W) return;
+    const size_t img = (size_t)blockIdx.z * W * H;
+    const int idx = v * W + u;
+    const int r = find_root(labels_all + img, idx);
+    labels_all[img + idx] = r;  // path compression to the root (roots are fixed once merging has finished)
+    atomicAdd(sizes_all + img + r, 1);
+}
+
+__global__ void __launch_bounds__(128) k_ccl_prune(float *__restrict__ D_all, const int32_t *__restrict__ labels_all,
+                                                  const int32_t *__restrict__ sizes_all, int W, int H, int min_size) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (u >= W) return;
+    const size_t img = (size_t)blockIdx.z * W * H;
+    const int idx = v * W + u;
+    const int r = labels_all[img + idx];
+    if (sizes_all[img + r] < min_size) D_all[img + idx] = -10.f;
+}
+
+}  // namespace
+
+int launch_remove_small_segments(const Dims &d, const svb_params &p, float *D, int32_t *labels, int32_t *sizes, int nimg, cudaStream_t s) {
+    if (nimg <= 0) return SVB_OK;
+    dim3 grid((d.W + 127) / 128, d.H, nimg);
+    k_ccl_init<<<grid, 128, 0, s>>>(D, labels, sizes, d.W, d.H, p.speckle_sim_threshold);
+    SVB_LAUNCH_CHECK();
+    k_ccl_merge<<<grid, 128, 0, s>>>(D, labels, d.W, d.H, p.speckle_sim_threshold);
+    SVB_LAUNCH_CHECK();
+    k_ccl_count<<<grid, 128, 0, s>>>(labels, sizes, d.W, d.H);
+    SVB_LAUNCH_CHECK();
+    k_ccl_prune<<<grid, 128, 0, s>>>(D, labels, sizes, d.W, d.H, p.speckle_size);
+    SVB_LAUNCH_CHECK();
+    return SVB_OK;
+}
+
+}  // namespace svb

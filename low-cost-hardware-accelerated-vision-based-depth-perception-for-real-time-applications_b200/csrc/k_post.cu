@@ -1,0 +1,318 @@
+// Left/right consistency check, gap interpolation, adaptive mean and median filters.
+//
+// Replaces Elas::leftRightConsistencyCheck, gapInterpolation, adaptiveMean (full-resolution branch) and median
+// (src/serial_includes/elas/elas.cpp:946-1011, 1126-1295, 1297-1494, 1496-1559).  All of these are a few bytes
+// of HBM traffic per pixel; the kernels are laid out so that every global access is coalesced along image rows.
+#include "svb_internal.h"
+
+namespace svb {
+
+namespace {
+
+// ---- L/R check ------------------------------------------------------------------------------------
+// grid: (ceil(W/256), H, nf).  Out of place: the reference works on copies of both maps (elas.cpp:956-959).
+__global__ void __launch_bounds__(256) k_lr_check(const float *__restrict__ D1in, const float *__restrict__ D2in, float *__restrict__ D1out,
+                                                 float *__restrict__ D2out, int W, int H, float lr_threshold) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= W) return;
+    const size_t base = ((size_t)blockIdx.z * H + blockIdx.y) * W;
+    const float d1 = D1in[base + u];
+    const float d2 = D2in[base + u];
+    const float fw = (float)W;
+    float o1 = -10.f, o2 = -10.f;
+    const float uw1 = __fsub_rn((float)u, d1);
+    if (d1 >= 0.f && uw1 >= 0.f && uw1 < fw) {
+        const float other = D2in[base + (int)uw1];
+        o1 = (fabsf(__fsub_rn(other, d1)) > lr_threshold) ? -10.f : d1;
+    }
+    const float uw2 = __fadd_rn((float)u, d2);
+    if (d2 >= 0.f && uw2 >= 0.f && uw2 < fw) {
+        const float other = D1in[base + (int)uw2];
+        o2 = (fabsf(__fsub_rn(other, d2)) > lr_threshold) ? -10.f : d2;
+    }
+    D1out[base + u] = o1;
+    if (D2out) D2out[base + u] = o2;
+}
+
+// ---- gap interpolation, row pass --------------------------------------------------------------------
+// For an invalid pixel only the nearest valid pixel on each side matters: with p = previous valid column and
+// n = next valid column (values dp, dn, untouched by the pass),
+//   p and n exist, n-p-1 <= gap : fill with (dp+dn)/2 if |dp-dn| < 3 else min(dp,dn)       (elas.cpp:1156-1176)
+//   only n exists (n = first valid), add_corners, n-u <= gap : fill with dn                 (elas.cpp:1191-1201)
+//   only p exists (p = last valid),  add_corners, u-p <= gap : fill with dp                 (elas.cpp:1204-1214)
+// One warp owns one row: a forward sweep records p per column in shared memory, a backward sweep carries n.
+constexpr int GAP_WARPS = 4;
+
+__device__ __forceinline__ float gap_fill_value(float d1, float d2) {
+    if (fabsf(__fsub_rn(d1, d2)) < 3.0f) return __fdiv_rn(__fadd_rn(d1, d2), 2.0f);
+    return d2 < d1 ? d2 : d1;  // std::min(d1, d2)
+}
+
+// grid: (ceil(H/GAP_WARPS), nimg); dynamic smem: GAP_WARPS * Wpad int32
+__global__ void __launch_bounds__(GAP_WARPS * 32) k_gap_rows(float *__restrict__ D_all, int W, int H, int gap_width, int add_corners, int Wpad) {
+    extern __shared__ int s_prev[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int v = blockIdx.x * GAP_WARPS + wid;
+    if (v >= H) return;
+    float *row = D_all + ((size_t)blockIdx.y * H + v) * W;
+    int *prev = s_prev + wid * Wpad;
+
+    int carry = -1;
+    const int chunks = (W + 31) / 32;
+    for (int k = 0; k < chunks; k++) {
+        const int u = k * 32 + lane;
+        const bool valid = (u < W) && (row[u] >= 0.f);
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid);
+        const unsigned below = bal & ((1u << lane) - 1u);
+        if (u < W) prev[u] = below ? (k * 32 + 31 - __clz(below)) : carry;
+        if (bal) carry = k * 32 + 31 - __clz(bal);
+    }
+    __syncwarp();
+    int ncarry = -1;  // next valid column to the right of the current chunk
+    for (int k = chunks - 1; k >= 0; k--) {
+        const int u = k * 32 + lane;
+        const float val = (u < W) ? row[u] : -1.f;
+        const bool valid = (u < W) && (val >= 0.f);
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid);
+        const unsigned above = (lane == 31) ? 0u : (bal & ~((2u << lane) - 1u));
+        const int n = above ? (k * 32 + __ffs(above) - 1) : ncarry;
+        if (u < W && !valid) {
+            const int p = prev[u];
+            float fill = 0.f;
+            bool do_fill = false;
+            if (p >= 0 && n >= 0) {
+                if (n - p - 1 <= gap_width) {
+                    fill = gap_fill_value(row[p], row[n]);
+                    do_fill = true;
+                }
+            } else if (add_corners && p < 0 && n >= 0) {
+                if (n - u <= gap_width) {
+                    fill = row[n];
+                    do_fill = true;
+                }
+            } else if (add_corners && p >= 0 && n < 0) {
+                if (u - p <= gap_width) {
+                    fill = row[p];
+                    do_fill = true;
+                }
+            }
+            // values at p and n are valid pixels, which this pass never modifies: reading them while other
+            // lanes write invalid positions is race free
+            if (do_fill) row[u] = fill;
+        }
+        if (bal) ncarry = k * 32 + __ffs(bal) - 1;
+    }
+}
+
+// ---- gap interpolation, column pass -------------------------------------------------------------------
+// One thread walks one column top to bottom exactly like elas.cpp:1220-1293; neighbouring threads own
+// neighbouring columns, so every step of the walk is a coalesced row access.
+__global__ void __launch_bounds__(128) k_gap_cols(float *__restrict__ D_all, int W, int H, int gap_width, int add_corners) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= W) return;
+    float *D = D_all + (size_t)blockIdx.y * W * H + u;
+    int count = 0;
+    int first_valid = -1, last_valid = -1;
+    for (int v = 0; v < H; v++) {
+        const float val = D[(size_t)v * W];
+        if (val >= 0.f) {
+            if (count >= 1 && count <= gap_width) {
+                const int v_first = v - count, v_last = v - 1;
+                if (v_first > 0 && v_last < H - 1) {
+                    const float d1 = D[(size_t)(v_first - 1) * W];
+                    const float fill = gap_fill_value(d1, val);
+                    for (int vc = v_first; vc <= v_last; vc++) D[(size_t)vc * W] = fill;
+                }
+            }
+            count = 0;
+            if (first_valid < 0) first_valid = v;
+            last_valid = v;
+        } else {
+            count++;
+        }
+    }
+    if (add_corners && first_valid >= 0) {
+        // the first / last valid pixel of the column is the same before and after the interior fill
+        const float top = D[(size_t)first_valid * W];
+        for (int v2 = max(first_valid - gap_width, 0); v2 < first_valid; v2++) D[(size_t)v2 * W] = top;
+        const float bot = D[(size_t)last_valid * W];
+        for (int v2 = last_valid + 1; v2 <= min(last_valid + gap_width, H - 1); v2++) D[(size_t)v2 * W] = bot;
+    }
+}
+
+// ---- adaptive mean ----------------------------------------------------------------------------------
+// 8-tap horizontal then 8-tap vertical weighted mean (elas.cpp:1401-1485).  Tap coordinates of a centre c are
+// c-4 .. c+3.  The reference keeps the window in a ring buffer indexed by (coordinate mod 8) and sums the SSE
+// lanes as ((s0+s1)+s2)+s3 with s_k = term(slot k) + term(slot k+4); the same association is used here.
+// mode 0: weight = max(0, 4 - float_and(x - xc, 0x4F000000))   (the serial reference's bit-mask "abs")
+// mode 1: weight = max(0, 4 - |x - xc|)                         (the parallel reference)
+__device__ __forceinline__ float mean_weight(float x, float xc, int mode) {
+    const float diff = __fsub_rn(x, xc);
+    const float m = mode ? fabsf(diff) : __int_as_float(__float_as_int(diff) & 0x4F000000);
+    return fmaxf(0.f, __fsub_rn(4.f, m));
+}
+
+// window[k] = value at coordinate base+k, k = 0..7 (base = centre-4).  Returns true and *out if the pixel is written.
+__device__ __forceinline__ bool mean8(const float window[8], int base, int mode, float *out) {
+    const float xc = window[4];
+    float wsum[4], fsum[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        // slot s holds the coordinate congruent to s (mod 8), slot s+4 the one 4 further
+        const int k0 = (s - base) & 7;
+        const int k1 = (k0 + 4) & 7;
+        const float x0 = window[k0], x1 = window[k1];
+        const float w0 = mean_weight(x0, xc, mode), w1 = mean_weight(x1, xc, mode);
+        wsum[s] = __fadd_rn(w0, w1);
+        fsum[s] = __fadd_rn(__fmul_rn(x0, w0), __fmul_rn(x1, w1));
+    }
+    const float weight_sum = __fadd_rn(__fadd_rn(__fadd_rn(wsum[0], wsum[1]), wsum[2]), wsum[3]);
+    const float factor_sum = __fadd_rn(__fadd_rn(__fadd_rn(fsum[0], fsum[1]), fsum[2]), fsum[3]);
+    if (weight_sum > 0.f) {
+        const float d = __fdiv_rn(factor_sum, weight_sum);
+        if (d >= 0.f) {
+            *out = d;
+            return true;
+        }
+    }
+    return false;
+}
+
+// Horizontal pass: tmp = (D < 0 ? -10 : 0) overwritten by the filtered value where the reference writes D_tmp.
+// (D_tmp is malloc'ed and only partly written in the reference; unwritten valid pixels are DEFINED as 0,
+// SURVEY.md finding 5.)  grid: (ceil(W/256), H, nimg)
+__global__ void __launch_bounds__(256) k_mean_h(const float *__restrict__ D_all, float *__restrict__ tmp_all, int W, int H, int mode) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= W) return;
+    const int v = blockIdx.y;
+    const size_t base = ((size_t)blockIdx.z * H + v) * W;
+    const float *row = D_all + base;
+    const float own = row[c];
+    float out = own < 0.f ? -10.f : 0.f;
+    if (v >= 3 && v < H - 3 && c >= 4 && c <= W - 4) {
+        float win[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float x = row[c - 4 + k];
+            win[k] = x < 0.f ? -10.f : x;  // D_copy (elas.cpp:1313-1316)
+        }
+        float r;
+        if (mean8(win, c - 4, mode, &r)) out = r;
+    }
+    tmp_all[base + c] = out;
+}
+
+// Vertical pass on tmp, writing D in place.  grid: (ceil(W/256), H, nimg)
+__global__ void __launch_bounds__(256) k_mean_v(const float *__restrict__ tmp_all, float *__restrict__ D_all, int W, int H, int mode) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= W) return;
+    const int c = blockIdx.y;  // centre row
+    if (!(u >= 3 && u < W - 3 && c >= 4 && c <= H - 4)) return;
+    const size_t img = (size_t)blockIdx.z * H * W;
+    float win[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) win[k] = tmp_all[img + (size_t)(c - 4 + k) * W + u];
+    float r;
+    if (mean8(win, c - 4, mode, &r)) D_all[img + (size_t)c * W + u] = r;
+}
+
+// ---- median -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float median7(float a[7]) {
+    // insertion sort exactly as elas.cpp:1519-1528 (selection only, so any correct sort gives the same value)
+#pragma unroll
+    for (int j = 1; j < 7; j++) {
+        const float t = a[j];
+        int i = j - 1;
+        while (i >= 0 && a[i] > t) {
+            a[i + 1] = a[i];
+            i--;
+        }
+        a[i + 1] = t;
+    }
+    return a[3];
+}
+
+// D_temp is calloc'ed (elas.cpp:1506): 0 outside [3,W-3)x[3,H-3).  grid: (ceil(W/256), H, nimg)
+__global__ void __launch_bounds__(256) k_median_h(const float *__restrict__ D_all, float *__restrict__ tmp_all, int W, int H) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= W) return;
+    const int v = blockIdx.y;
+    const size_t base = ((size_t)blockIdx.z * H + v) * W;
+    float out = 0.f;
+    if (u >= 3 && u < W - 3 && v >= 3 && v < H - 3) {
+        const float own = D_all[base + u];
+        if (own >= 0.f) {
+            float a[7];
+#pragma unroll
+            for (int k = 0; k < 7; k++) a[k] = D_all[base + u - 3 + k];
+            out = median7(a);
+        } else {
+            out = own;
+        }
+    }
+    tmp_all[base + u] = out;
+}
+
+__global__ void __launch_bounds__(256) k_median_v(const float *__restrict__ tmp_all, float *__restrict__ D_all, int W, int H) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= W) return;
+    const int v = blockIdx.y;
+    if (!(u >= 3 && u < W - 3 && v >= 3 && v < H - 3)) return;
+    const size_t img = (size_t)blockIdx.z * H * W;
+    const size_t idx = img + (size_t)v * W + u;
+    if (D_all[idx] >= 0.f) {
+        float a[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) a[k] = tmp_all[img + (size_t)(v - 3 + k) * W + u];
+        D_all[idx] = median7(a);
+    }
+}
+
+}  // namespace
+
+int launch_lr_check(const Dims &d, const svb_params &p, const float *D1in, const float *D2in, float *D1out, float *D2out, int nf,
+                    cudaStream_t s) {
+    if (nf <= 0) return SVB_OK;
+    dim3 grid((d.W + 255) / 256, d.H, nf);
+    k_lr_check<<<grid, 256, 0, s>>>(D1in, D2in, D1out, D2out, d.W, d.H, (float)p.lr_threshold);
+    SVB_LAUNCH_CHECK();
+    return SVB_OK;
+}
+
+int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s) {
+    if (nimg <= 0) return SVB_OK;
+    const int Wpad = (d.W + 31) & ~31;
+    {
+        dim3 grid((d.H + GAP_WARPS - 1) / GAP_WARPS, nimg);
+        k_gap_rows<<<grid, GAP_WARPS * 32, (size_t)GAP_WARPS * Wpad * sizeof(int), s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners, Wpad);
+        SVB_LAUNCH_CHECK();
+    }
+    {
+        dim3 grid((d.W + 127) / 128, nimg);
+        k_gap_cols<<<grid, 128, 0, s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners);
+        SVB_LAUNCH_CHECK();
+    }
+    return SVB_OK;
+}
+
+int launch_adaptive_mean(const Dims &d, int mean_mode, float *D, float *tmp, int nimg, cudaStream_t s) {
+    if (nimg <= 0) return SVB_OK;
+    dim3 grid((d.W + 255) / 256, d.H, nimg);
+    k_mean_h<<<grid, 256, 0, s>>>(D, tmp, d.W, d.H, mean_mode);
+    SVB_LAUNCH_CHECK();
+    k_mean_v<<<grid, 256, 0, s>>>(tmp, D, d.W, d.H, mean_mode);
+    SVB_LAUNCH_CHECK();
+    return SVB_OK;
+}
+
+int launch_median(const Dims &d, float *D, float *tmp, int nimg, cudaStream_t s) {
+    if (nimg <= 0) return SVB_OK;
+    dim3 grid((d.W + 255) / 256, d.H, nimg);
+    k_median_h<<<grid, 256, 0, s>>>(D, tmp, d.W, d.H);
+    SVB_LAUNCH_CHECK();
+    k_median_v<<<grid, 256, 0, s>>>(tmp, D, d.W, d.H);
+    SVB_LAUNCH_CHECK();
+    return SVB_OK;
+}
+
+}  // namespace svb

@@ -1,0 +1,1015 @@
+// Context, device arenas, the frame-batch pipeline and every svb_* entry point of include/elas_b200.h.
+//
+// One svb_context owns LANES independent lanes; a lane holds the device arenas for `chunk` frames, one CUDA
+// stream and pinned staging buffers.  A batch is cut into chunks that go round-robin over the lanes:
+//     stage A (GPU)  descriptor -> support matching -> lattice filters/compaction -> D2H support list
+//     host stage     Delaunay triangulation (worker pool, one job per frame and side)
+//     stage B (GPU)  H2D triangles -> planes -> grid -> raster -> dense matching -> L/R check -> speckle removal
+//                    -> gap interpolation -> adaptive mean -> median -> u8 conversion + reprojection
+// While the host triangulates chunk k, the GPU runs stage B of chunk k-1 and stage A of chunk k+1.
+// Frames never interact, so there is no collective anywhere.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <chrono>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "host_delaunay.h"
+#include "svb_internal.h"
+#include "thread_pool.h"
+
+namespace svb {
+
+static thread_local char g_err[1024] = "";
+thread_local long long g_launch_counter = 0;
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int make_dims(const svb_params &p, int W, int H, Dims *out) {
+    Dims d;
+    memset(&d, 0, sizeof(d));
+    if (W < 16 || H < 16 || W > 16384 || H > 16384) {
+        set_error("unsupported image size %dx%d", W, H);
+        return SVB_ERR_ARG;
+    }
+    if (p.subsampling) {
+        set_error("subsampling=1 is not implemented yet (SURVEY.md 8f rank 3)");
+        return SVB_ERR_UNSUPPORTED;
+    }
+    if (p.disp_max < 0 || p.disp_max > 4095 || p.grid_size < 1 || p.candidate_stepsize < 1) {
+        set_error("invalid parameters (disp_max=%d grid_size=%d candidate_stepsize=%d)", p.disp_max, p.grid_size, p.candidate_stepsize);
+        return SVB_ERR_ARG;
+    }
+    if (!(p.speckle_sim_threshold < 10.0f)) {
+        set_error("speckle_sim_threshold >= 10 would connect invalid (-10) pixels in the reference; unsupported");
+        return SVB_ERR_UNSUPPORTED;
+    }
+    d.W = W;
+    d.H = H;
+    d.N = W * H;
+    d.step = p.candidate_stepsize;
+    d.cw = (W + d.step - 1) / d.step;  // elas.cpp:383-386
+    d.ch = (H + d.step - 1) / d.step;
+    d.gw = (int)ceil((float)W / (float)p.grid_size);  // elas.cpp:88-89
+    d.gh = (int)ceil((float)H / (float)p.grid_size);
+    d.gwords = (p.disp_max + 1 + 31) / 32;
+    d.maxS = (d.cw - 1) * (d.ch - 1) + 6;
+    d.maxT = 2 * d.maxS;
+    // elas.cpp:828-832
+    const float two_sigma_squared = 2 * p.sigma * p.sigma;
+    d.plane_radius = (int32_t)fmaxf((float)ceil(p.sigma * p.sradius), (float)2.0);
+    if (d.plane_radius > 7) {
+        set_error("plane radius %d > 7 unsupported", d.plane_radius);
+        return SVB_ERR_UNSUPPORTED;
+    }
+    for (int delta = 0; delta < 8; delta++)
+        d.P[delta] = (int32_t)((-log(p.gamma + exp(-delta * delta / two_sigma_squared)) + log(p.gamma)) / p.beta);
+    *out = d;
+    return SVB_OK;
+}
+
+static const char *kStageNames[ST_COUNT] = {"descriptor", "support_match", "support_filter", "d2h_support", "h2d_triangles",
+                                            "planes",     "grid",          "raster",         "dense_match", "lr_check",
+                                            "remove_small_segments", "gap_interpolation", "adaptive_mean", "median", "reproject"};
+
+constexpr int LANES = 3;
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_done = nullptr, ev_a_end = nullptr;
+    cudaEvent_t ev_stage[ST_COUNT + 1] = {};
+    bool stage_events_valid = false;
+    // device
+    uint8_t *img[2] = {nullptr, nullptr};
+    uint8_t *desc[2] = {nullptr, nullptr};
+    int16_t *dcan_raw = nullptr, *dcan = nullptr;
+    uint8_t *removed = nullptr;
+    int32_t *support = nullptr, *nsupport = nullptr;
+    int32_t *tri[2] = {nullptr, nullptr};
+    int32_t *ntri = nullptr;
+    PlaneRec *rec[2] = {nullptr, nullptr};
+    uint32_t *grid_tmp = nullptr, *grid[2] = {nullptr, nullptr};
+    int32_t *owner[2] = {nullptr, nullptr};
+    float *Draw = nullptr;  // [2][chunk][N]
+    float *Dlr = nullptr;   // [2][chunk][N]
+    float *Dtmp = nullptr;  // [2][chunk][N]
+    int32_t *labels = nullptr, *sizes = nullptr;  // [2][chunk][N]
+    uint8_t *dmap = nullptr;
+    // pinned host
+    int32_t *h_support = nullptr, *h_nsupport = nullptr, *h_tri[2] = {nullptr, nullptr}, *h_ntri = nullptr;
+};
+
+struct Tap {
+    std::string name;
+    void *dev = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace svb
+
+using namespace svb;
+
+struct svb_context {
+    svb_params p;
+    Dims d;
+    int chunk = 1;
+    int device = 0;
+    int mean_mode = SVB_MEAN_SERIAL_QUANTISED;
+    Lane lanes[LANES];
+    std::unique_ptr<ThreadPool> pool;
+    std::vector<DelaunayScratch> scratch;
+    Calib calib;
+    bool have_calib = false;
+    // tap mode (single frame)
+    bool tap_mode = false;
+    std::vector<Tap> taps;
+    float *planes_ref[2] = {nullptr, nullptr};  // [maxT][6], tap mode only
+    std::vector<int32_t> inject_tri[2];
+    bool inject[2] = {false, false};
+    // resident batch stores
+    uint8_t *in_img[2] = {nullptr, nullptr};
+    size_t in_frames = 0;
+    float *out_D1 = nullptr;
+    size_t out_D1_frames = 0;
+    double *out_points = nullptr;
+    size_t out_points_frames = 0;
+    // stats
+    svb_stats stats;
+    bool stage_timing = false;
+    std::mutex mu;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(T **p, size_t count) {
+    *p = nullptr;
+    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T) + 256);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+        return SVB_ERR_CUDA;
+    }
+    return SVB_OK;
+}
+template <typename T>
+int host_alloc(T **p, size_t count) {
+    *p = nullptr;
+    cudaError_t e = cudaHostAlloc((void **)p, count * sizeof(T) + 64, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        set_error("cudaHostAlloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+        return SVB_ERR_CUDA;
+    }
+    return SVB_OK;
+}
+
+int lane_create(svb_context *c, Lane &L) {
+    const Dims &d = c->d;
+    const size_t C = (size_t)c->chunk, N = (size_t)d.N;
+    SVB_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    SVB_CUDA(cudaEventCreateWithFlags(&L.ev_a, cudaEventDisableTiming));
+    SVB_CUDA(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
+    for (int i = 0; i <= ST_COUNT; i++) SVB_CUDA(cudaEventCreate(&L.ev_stage[i]));
+    SVB_CUDA(cudaEventCreate(&L.ev_a_end));
+    for (int s = 0; s < 2; s++) {
+        SVB_TRY(dev_alloc(&L.img[s], C * N));
+        SVB_TRY(dev_alloc(&L.desc[s], C * N * 16));
+        SVB_TRY(dev_alloc(&L.tri[s], C * d.maxT * 3));
+        SVB_TRY(dev_alloc(&L.rec[s], C * d.maxT));
+        SVB_TRY(dev_alloc(&L.grid[s], C * d.gw * d.gh * d.gwords));
+        SVB_TRY(dev_alloc(&L.owner[s], C * N));
+        SVB_TRY(host_alloc(&L.h_tri[s], C * d.maxT * 3));
+    }
+    SVB_TRY(dev_alloc(&L.dcan_raw, C * d.cw * d.ch));
+    SVB_TRY(dev_alloc(&L.dcan, C * d.cw * d.ch));
+    SVB_TRY(dev_alloc(&L.removed, C * d.cw * d.ch));
+    SVB_TRY(dev_alloc(&L.support, C * d.maxS * 3));
+    SVB_TRY(dev_alloc(&L.nsupport, C));
+    SVB_TRY(dev_alloc(&L.ntri, C * 2));
+    SVB_TRY(dev_alloc(&L.grid_tmp, C * 2 * d.gw * d.gh * d.gwords));
+    SVB_TRY(dev_alloc(&L.Draw, 2 * C * N));
+    SVB_TRY(dev_alloc(&L.Dlr, 2 * C * N));
+    SVB_TRY(dev_alloc(&L.Dtmp, 2 * C * N));
+    SVB_TRY(dev_alloc(&L.labels, 2 * C * N));
+    SVB_TRY(dev_alloc(&L.sizes, 2 * C * N));
+    SVB_TRY(dev_alloc(&L.dmap, C * N));
+    SVB_TRY(host_alloc(&L.h_support, C * d.maxS * 3));
+    SVB_TRY(host_alloc(&L.h_nsupport, C));
+    SVB_TRY(host_alloc(&L.h_ntri, C * 2));
+    return SVB_OK;
+}
+
+void lane_destroy(Lane &L) {
+    for (int s = 0; s < 2; s++) {
+        cudaFree(L.img[s]);
+        cudaFree(L.desc[s]);
+        cudaFree(L.tri[s]);
+        cudaFree(L.rec[s]);
+        cudaFree(L.grid[s]);
+        cudaFree(L.owner[s]);
+        cudaFreeHost(L.h_tri[s]);
+    }
+    cudaFree(L.dcan_raw);
+    cudaFree(L.dcan);
+    cudaFree(L.removed);
+    cudaFree(L.support);
+    cudaFree(L.nsupport);
+    cudaFree(L.ntri);
+    cudaFree(L.grid_tmp);
+    cudaFree(L.Draw);
+    cudaFree(L.Dlr);
+    cudaFree(L.Dtmp);
+    cudaFree(L.labels);
+    cudaFree(L.sizes);
+    cudaFree(L.dmap);
+    cudaFreeHost(L.h_support);
+    cudaFreeHost(L.h_nsupport);
+    cudaFreeHost(L.h_ntri);
+    for (int i = 0; i <= ST_COUNT; i++)
+        if (L.ev_stage[i]) cudaEventDestroy(L.ev_stage[i]);
+    if (L.ev_a) cudaEventDestroy(L.ev_a);
+    if (L.ev_a_end) cudaEventDestroy(L.ev_a_end);
+    if (L.ev_done) cudaEventDestroy(L.ev_done);
+    if (L.stream) cudaStreamDestroy(L.stream);
+    L = Lane();
+}
+
+struct StageTimer {
+    svb_context *c;
+    Lane &L;
+    bool on;
+    StageTimer(svb_context *c_, Lane &L_) : c(c_), L(L_), on(c_->stage_timing) {}
+    int mark(int idx) {
+        if (!on) return SVB_OK;
+        SVB_CUDA(cudaEventRecord(L.ev_stage[idx], L.stream));
+        return SVB_OK;
+    }
+};
+
+// collect per-stage times of a lane whose work has completed
+int lane_collect_times(svb_context *c, Lane &L, int first, int last) {
+    if (!c->stage_timing) return SVB_OK;
+    for (int i = first; i < last; i++) {
+        float ms = 0.f;
+        // the D2H of the support lists ends stage A; the host stage separates it from the next device stage
+        cudaError_t e = cudaEventElapsedTime(&ms, L.ev_stage[i], i == ST_D2H_SUPPORT ? L.ev_a_end : L.ev_stage[i + 1]);
+        if (e == cudaSuccess) c->stats.stage_ms[i] += ms;
+    }
+    return SVB_OK;
+}
+
+int tap_store(svb_context *c, const char *name, const void *dev_src, size_t bytes, cudaStream_t s) {
+    if (!c->tap_mode) return SVB_OK;
+    Tap *t = nullptr;
+    for (auto &x : c->taps)
+        if (x.name == name) t = &x;
+    if (!t) {
+        c->taps.push_back(Tap());
+        t = &c->taps.back();
+        t->name = name;
+    }
+    if (t->bytes < bytes || !t->dev) {
+        if (t->dev) cudaFree(t->dev);
+        SVB_CUDA(cudaMalloc(&t->dev, bytes + 256));
+    }
+    t->bytes = bytes;
+    SVB_CUDA(cudaMemcpyAsync(t->dev, dev_src, bytes, cudaMemcpyDeviceToDevice, s));
+    return SVB_OK;
+}
+
+// ---- stage A: images (device) -> support lists (device + pinned host) ------------------------------
+int stage_a(svb_context *c, Lane &L, const uint8_t *img1, const uint8_t *img2, int nf) {
+    const Dims &d = c->d;
+    StageTimer T(c, L);
+    SVB_TRY(T.mark(ST_DESCRIPTOR));
+    SVB_TRY(launch_descriptor(d, img1, L.desc[0], nf, L.stream));
+    SVB_TRY(launch_descriptor(d, img2, L.desc[1], nf, L.stream));
+    SVB_TRY(T.mark(ST_SUPPORT_MATCH));
+    SVB_TRY(launch_support_match(d, c->p, L.desc[0], L.desc[1], L.dcan_raw, nf, L.stream));
+    SVB_TRY(T.mark(ST_SUPPORT_FILTER));
+    SVB_TRY(launch_support_filter(d, c->p, L.dcan_raw, L.dcan, L.removed, L.support, L.nsupport, nf, L.stream));
+    SVB_TRY(T.mark(ST_D2H_SUPPORT));
+    SVB_CUDA(cudaMemcpyAsync(L.h_nsupport, L.nsupport, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(L.h_support, L.support, sizeof(int32_t) * 3 * (size_t)d.maxS * nf, cudaMemcpyDeviceToHost, L.stream));
+    if (T.on) SVB_CUDA(cudaEventRecord(L.ev_a_end, L.stream));
+    SVB_CUDA(cudaEventRecord(L.ev_a, L.stream));
+    return SVB_OK;
+}
+
+// ---- host stage ----------------------------------------------------------------------------------------
+int stage_host(svb_context *c, Lane &L, int nf) {
+    const Dims &d = c->d;
+    SVB_CUDA(cudaEventSynchronize(L.ev_a));
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<double> per_worker(c->pool->size(), 0.0);
+    c->pool->parallel_for(nf * 2, [&](int job, int worker) {
+        const auto w0 = std::chrono::steady_clock::now();
+        const int f = job >> 1, side = job & 1;
+        const int n = L.h_nsupport[f];
+        int32_t *out = L.h_tri[side] + (size_t)f * d.maxT * 3;
+        int m = 0;
+        if (c->inject[side]) {
+            m = (int)(c->inject_tri[side].size() / 3);
+            if (m > d.maxT) m = d.maxT;
+            memcpy(out, c->inject_tri[side].data(), sizeof(int32_t) * 3 * m);
+        } else if (n >= 3) {
+            m = delaunay_support(L.h_support + (size_t)f * d.maxS * 3, n, side, out, d.maxT, c->scratch[worker]);
+            if (m > d.maxT) m = d.maxT;
+        }
+        L.h_ntri[2 * f + side] = m;
+        per_worker[worker] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    });
+    const auto t1 = std::chrono::steady_clock::now();
+    c->stats.delaunay_ms_wall += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    for (double v : per_worker) c->stats.delaunay_ms_total += v;
+    for (int f = 0; f < nf; f++) {
+        c->stats.support_points += L.h_nsupport[f];
+        c->stats.triangles += L.h_ntri[2 * f] + L.h_ntri[2 * f + 1];
+        if (L.h_nsupport[f] < 3) c->stats.frames_failed++;
+    }
+    return SVB_OK;
+}
+
+// ---- stage B: triangles (pinned host) -> disparity / points -------------------------------------------
+// out_D1 / out_points may be null.  The final maps stay in L.Dlr ([0] = left, [1] = right).
+int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points) {
+    const Dims &d = c->d;
+    const svb_params &p = c->p;
+    const size_t N = (size_t)d.N, C = (size_t)c->chunk;
+    StageTimer T(c, L);
+    int max_tri = 0, max_support = 0;
+    for (int i = 0; i < 2 * nf; i++) max_tri = L.h_ntri[i] > max_tri ? L.h_ntri[i] : max_tri;
+    for (int i = 0; i < nf; i++) max_support = L.h_nsupport[i] > max_support ? L.h_nsupport[i] : max_support;
+    SVB_TRY(T.mark(ST_H2D_TRIANGLES));
+    SVB_CUDA(cudaMemcpyAsync(L.ntri, L.h_ntri, sizeof(int32_t) * 2 * nf, cudaMemcpyHostToDevice, L.stream));
+    for (int s = 0; s < 2; s++)
+        SVB_CUDA(cudaMemcpyAsync(L.tri[s], L.h_tri[s], sizeof(int32_t) * 3 * (size_t)d.maxT * nf, cudaMemcpyHostToDevice, L.stream));
+    SVB_TRY(T.mark(ST_PLANES));
+    float *pr1 = (c->tap_mode && nf == 1) ? c->planes_ref[0] : nullptr;
+    float *pr2 = (c->tap_mode && nf == 1) ? c->planes_ref[1] : nullptr;
+    SVB_TRY(launch_planes(d, L.support, L.tri[0], L.tri[1], L.ntri, pr1, pr2, L.rec[0], L.rec[1], nf, max_tri, L.stream));
+    SVB_TRY(T.mark(ST_GRID));
+    SVB_TRY(launch_grid(d, p, L.support, L.nsupport, L.grid_tmp, L.grid[0], L.grid[1], nf, max_support, L.stream));
+    SVB_TRY(T.mark(ST_RASTER));
+    SVB_TRY(launch_raster(d, L.support, L.tri[0], L.tri[1], L.ntri, L.owner[0], L.owner[1], nf, max_tri, L.stream));
+    SVB_TRY(T.mark(ST_DENSE));
+    float *D1raw = L.Draw, *D2raw = L.Draw + C * N;
+    float *D1 = L.Dlr, *D2 = L.Dlr + C * N;
+    SVB_TRY(launch_dense(d, p, L.desc[0], L.desc[1], L.owner[0], L.owner[1], L.rec[0], L.rec[1], L.grid[0], L.grid[1], D1raw, D2raw, nf,
+                         L.stream));
+    SVB_TRY(T.mark(ST_LR));
+    const bool both = !p.postprocess_only_left;
+    const bool need_d2 = both || c->tap_mode || (out_D1 == nullptr && out_points == nullptr);
+    SVB_TRY(launch_lr_check(d, p, D1raw, D2raw, D1, need_d2 ? D2 : nullptr, nf, L.stream));
+    if (c->tap_mode && nf == 1) {
+        SVB_TRY(tap_store(c, "D1raw", D1raw, N * 4, L.stream));
+        SVB_TRY(tap_store(c, "D2raw", D2raw, N * 4, L.stream));
+        SVB_TRY(tap_store(c, "D1lr", D1, N * 4, L.stream));
+        SVB_TRY(tap_store(c, "D2lr", D2, N * 4, L.stream));
+    }
+    // post-processing chain; when both maps are processed they are handled as 2*nf independent images, which
+    // needs the left and right blocks to be adjacent: true when nf == chunk, otherwise run the sides separately
+    const int passes = both ? 2 : 1;
+    SVB_TRY(T.mark(ST_SEGMENTS));
+    for (int s = 0; s < passes; s++) SVB_TRY(launch_remove_small_segments(d, p, s ? D2 : D1, L.labels, L.sizes, nf, L.stream));
+    if (c->tap_mode && nf == 1) {
+        SVB_TRY(tap_store(c, "D1seg", D1, N * 4, L.stream));
+        if (both) SVB_TRY(tap_store(c, "D2seg", D2, N * 4, L.stream));
+    }
+    SVB_TRY(T.mark(ST_GAP));
+    for (int s = 0; s < passes; s++) SVB_TRY(launch_gap(d, p, s ? D2 : D1, nf, L.stream));
+    if (c->tap_mode && nf == 1) {
+        SVB_TRY(tap_store(c, "D1gap", D1, N * 4, L.stream));
+        if (both) SVB_TRY(tap_store(c, "D2gap", D2, N * 4, L.stream));
+    }
+    SVB_TRY(T.mark(ST_MEAN));
+    if (p.filter_adaptive_mean) {
+        for (int s = 0; s < passes; s++) SVB_TRY(launch_adaptive_mean(d, c->mean_mode, s ? D2 : D1, L.Dtmp, nf, L.stream));
+        if (c->tap_mode && nf == 1) {
+            SVB_TRY(tap_store(c, "D1mean", D1, N * 4, L.stream));
+            if (both) SVB_TRY(tap_store(c, "D2mean", D2, N * 4, L.stream));
+        }
+    }
+    SVB_TRY(T.mark(ST_MEDIAN));
+    if (p.filter_median) {
+        for (int s = 0; s < passes; s++) SVB_TRY(launch_median(d, s ? D2 : D1, L.Dtmp, nf, L.stream));
+        if (c->tap_mode && nf == 1) {
+            SVB_TRY(tap_store(c, "D1med", D1, N * 4, L.stream));
+            if (both) SVB_TRY(tap_store(c, "D2med", D2, N * 4, L.stream));
+        }
+    }
+    SVB_TRY(T.mark(ST_REPROJECT));
+    if (out_D1) SVB_CUDA(cudaMemcpyAsync(out_D1, D1, N * 4 * nf, cudaMemcpyDeviceToDevice, L.stream));
+    if (out_points) SVB_TRY(launch_reproject(d, c->calib, D1, L.dmap, out_points, nf, L.stream));
+    SVB_TRY(T.mark(ST_COUNT));
+    SVB_CUDA(cudaEventRecord(L.ev_done, L.stream));
+    return SVB_OK;
+}
+
+int tap_after_a(svb_context *c, Lane &L) {
+    const Dims &d = c->d;
+    const size_t N = (size_t)d.N;
+    SVB_TRY(tap_store(c, "desc1", L.desc[0], N * 16, L.stream));
+    SVB_TRY(tap_store(c, "desc2", L.desc[1], N * 16, L.stream));
+    SVB_TRY(tap_store(c, "dcan_raw", L.dcan_raw, (size_t)d.cw * d.ch * 2, L.stream));
+    SVB_TRY(tap_store(c, "dcan", L.dcan, (size_t)d.cw * d.ch * 2, L.stream));
+    return SVB_OK;
+}
+
+int ensure_calib(svb_context *c) {
+    if (c->have_calib) return SVB_OK;
+    // identity-like default: Q = I, XR = I, XT = 0 (callers set the real one with svb_set_calibration)
+    memset(&c->calib, 0, sizeof(c->calib));
+    for (int i = 0; i < 4; i++) c->calib.Q[5 * i] = 1.0;
+    for (int i = 0; i < 3; i++) c->calib.XR[4 * i] = 1.0;
+    return SVB_OK;
+}
+
+void stats_reset(svb_context *c) {
+    memset(&c->stats, 0, sizeof(c->stats));
+    g_launch_counter = 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+//                                          C-ABI
+// =====================================================================================================
+extern "C" {
+
+const char *svb_last_error(void) { return g_err; }
+const char *svb_version(void) { return "elas_b200 0.1 (sm_100a)"; }
+
+int svb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int svb_default_params(int setting, svb_params *o) {
+    if (!o) return SVB_ERR_ARG;
+    // src/parallel_includes/elas/elas.h:90-113 (ROBOTICS) and :117-140 (MIDDLEBURY)
+    const bool rob = setting == SVB_ROBOTICS;
+    o->disp_min = 0;
+    o->disp_max = 255;
+    o->support_threshold = rob ? 0.85f : 0.95f;
+    o->support_texture = 10;
+    o->candidate_stepsize = 5;
+    o->incon_window_size = 5;
+    o->incon_threshold = 5;
+    o->incon_min_support = 5;
+    o->add_corners = rob ? 0 : 1;
+    o->grid_size = 20;
+    o->beta = 0.02f;
+    o->gamma = rob ? 3.f : 5.f;
+    o->sigma = 1.f;
+    o->sradius = rob ? 2.f : 3.f;
+    o->match_texture = rob ? 1 : 0;
+    o->lr_threshold = 2;
+    o->speckle_sim_threshold = 1.f;
+    o->speckle_size = 200;
+    o->ipol_gap_width = rob ? 3 : 5000;
+    o->filter_median = rob ? 0 : 1;
+    o->filter_adaptive_mean = rob ? 1 : 0;
+    o->postprocess_only_left = rob ? 1 : 0;
+    o->subsampling = 0;
+    if (setting == SVB_PIPELINE) {  // stereo_vision.cu:315-319
+        o->postprocess_only_left = 1;
+        o->filter_adaptive_mean = 1;
+    }
+    return SVB_OK;
+}
+
+svb_context *svb_create(const svb_params *params, int width, int height, int chunk, int device) {
+    if (!params) {
+        set_error("params is NULL");
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+        return nullptr;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= ndev) {
+        set_error("device %d out of range (%d devices)", device, ndev);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        set_error("cudaSetDevice(%d) failed", device);
+        return nullptr;
+    }
+    svb_context *c = new svb_context();
+    c->p = *params;
+    c->device = device;
+    c->chunk = chunk < 1 ? 1 : chunk;
+    if (make_dims(c->p, width, height, &c->d) != SVB_OK) {
+        delete c;
+        return nullptr;
+    }
+    for (int i = 0; i < LANES; i++)
+        if (lane_create(c, c->lanes[i]) != SVB_OK) {
+            svb_destroy(c);
+            return nullptr;
+        }
+    unsigned hw = std::thread::hardware_concurrency();
+    int nthreads = hw ? (int)hw : 4;
+    if (nthreads > 2 * c->chunk) nthreads = 2 * c->chunk;
+    if (nthreads > 64) nthreads = 64;
+    c->pool.reset(new ThreadPool(nthreads));
+    c->scratch.resize(c->pool->size());
+    memset(&c->stats, 0, sizeof(c->stats));
+    ensure_calib(c);
+    return c;
+}
+
+void svb_destroy(svb_context *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < LANES; i++) lane_destroy(c->lanes[i]);
+    for (auto &t : c->taps) cudaFree(t.dev);
+    for (int s = 0; s < 2; s++) {
+        cudaFree(c->planes_ref[s]);
+        cudaFree(c->in_img[s]);
+    }
+    cudaFree(c->out_D1);
+    cudaFree(c->out_points);
+    delete c;
+}
+
+int svb_set_mean_mode(svb_context *c, int mode) {
+    if (!c || (mode != 0 && mode != 1)) return SVB_ERR_ARG;
+    c->mean_mode = mode;
+    return SVB_OK;
+}
+
+int svb_set_delaunay_threads(svb_context *c, int n) {
+    if (!c || n < 1) return SVB_ERR_ARG;
+    c->pool->resize(n);
+    c->scratch.resize(c->pool->size());
+    return SVB_OK;
+}
+
+int svb_set_stage_timing(svb_context *c, int on) {
+    if (!c) return SVB_ERR_ARG;
+    c->stage_timing = on != 0;
+    return SVB_OK;
+}
+
+int svb_set_tap_mode(svb_context *c, int on) {
+    if (!c) return SVB_ERR_ARG;
+    SVB_CUDA(cudaSetDevice(c->device));
+    c->tap_mode = on != 0;
+    if (c->tap_mode && !c->planes_ref[0])
+        for (int s = 0; s < 2; s++) SVB_TRY(dev_alloc(&c->planes_ref[s], (size_t)c->d.maxT * 6));
+    return SVB_OK;
+}
+
+int svb_inject_triangles(svb_context *c, int side, const int32_t *tri, int n) {
+    if (!c || side < 0 || side > 1) return SVB_ERR_ARG;
+    if (n < 0 || !tri) {
+        c->inject[side] = false;
+        c->inject_tri[side].clear();
+        return SVB_OK;
+    }
+    c->inject_tri[side].assign(tri, tri + (size_t)3 * n);
+    c->inject[side] = true;
+    return SVB_OK;
+}
+
+int svb_set_calibration(svb_context *c, const double *Q16, const double *XR9, const double *XT3) {
+    if (!c || !Q16) return SVB_ERR_ARG;
+    memcpy(c->calib.Q, Q16, sizeof(double) * 16);
+    if (XR9)
+        memcpy(c->calib.XR, XR9, sizeof(double) * 9);
+    else {
+        memset(c->calib.XR, 0, sizeof(c->calib.XR));
+        for (int i = 0; i < 3; i++) c->calib.XR[4 * i] = 1.0;
+    }
+    if (XT3)
+        memcpy(c->calib.XT, XT3, sizeof(double) * 3);
+    else
+        memset(c->calib.XT, 0, sizeof(c->calib.XT));
+    c->have_calib = true;
+    return SVB_OK;
+}
+
+// ---- Elas::process ----------------------------------------------------------------------------------------
+int svb_process(svb_context *c, const uint8_t *I1, const uint8_t *I2, int stride, float *D1, float *D2) {
+    if (!c || !I1 || !I2 || !D1 || !D2 || stride < c->d.W) {
+        set_error("svb_process: bad argument");
+        return SVB_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    SVB_CUDA(cudaSetDevice(c->device));
+    stats_reset(c);
+    const Dims &d = c->d;
+    Lane &L = c->lanes[0];
+    const size_t N = (size_t)d.N, C = (size_t)c->chunk;
+    // elas.cpp:33-50: rows are copied out of the caller's stride
+    SVB_CUDA(cudaMemcpy2DAsync(L.img[0], d.W, I1, stride, d.W, d.H, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpy2DAsync(L.img[1], d.W, I2, stride, d.W, d.H, cudaMemcpyHostToDevice, L.stream));
+    SVB_TRY(stage_a(c, L, L.img[0], L.img[1], 1));
+    if (c->tap_mode) SVB_TRY(tap_after_a(c, L));
+    SVB_TRY(stage_host(c, L, 1));
+    c->stats.frames = 1;
+    const int n = L.h_nsupport[0];
+    if (c->tap_mode) {
+        SVB_TRY(tap_store(c, "support", L.support, (size_t)n * 12, L.stream));
+    }
+    if (n < 3) {
+        // elas.cpp:64-69: "ERROR: Need at least 3 support points!", D1/D2 untouched
+        SVB_CUDA(cudaStreamSynchronize(L.stream));
+        set_error("need at least 3 support points (got %d)", n);
+        c->stats.kernel_launches = g_launch_counter;
+        return SVB_ERR_FEW_SUPPORT;
+    }
+    SVB_TRY(stage_b(c, L, 1, nullptr, nullptr));
+    if (c->tap_mode) {
+        SVB_TRY(tap_store(c, "tri1", L.tri[0], (size_t)L.h_ntri[0] * 12, L.stream));
+        SVB_TRY(tap_store(c, "tri2", L.tri[1], (size_t)L.h_ntri[1] * 12, L.stream));
+        SVB_TRY(tap_store(c, "planes1", c->planes_ref[0], (size_t)L.h_ntri[0] * 24, L.stream));
+        SVB_TRY(tap_store(c, "planes2", c->planes_ref[1], (size_t)L.h_ntri[1] * 24, L.stream));
+        SVB_TRY(tap_store(c, "owner1", L.owner[0], N * 4, L.stream));
+        SVB_TRY(tap_store(c, "owner2", L.owner[1], N * 4, L.stream));
+        // grids in the reference's list layout
+        const size_t gbytes = (size_t)d.gw * d.gh * (c->p.disp_max + 2) * 4;
+        for (int s = 0; s < 2; s++) {
+            int32_t *tmp = nullptr;
+            SVB_TRY(dev_alloc(&tmp, gbytes / 4));
+            int r = launch_grid_expand(d, c->p, L.grid[s], tmp, L.stream);
+            if (r == SVB_OK) r = tap_store(c, s ? "grid2" : "grid1", tmp, gbytes, L.stream);
+            cudaStreamSynchronize(L.stream);
+            cudaFree(tmp);
+            SVB_TRY(r);
+        }
+    }
+    SVB_CUDA(cudaMemcpyAsync(D1, L.Dlr, N * 4, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(D2, L.Dlr + C * N, N * 4, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaStreamSynchronize(L.stream));
+    lane_collect_times(c, L, 0, ST_COUNT);
+    c->stats.kernel_launches = g_launch_counter;
+    return SVB_OK;
+}
+
+int64_t svb_tap(svb_context *c, const char *name, void *dst, int64_t cap) {
+    if (!c || !name || !dst) return SVB_ERR_ARG;
+    for (auto &t : c->taps)
+        if (t.name == name) {
+            if ((int64_t)t.bytes > cap) {
+                set_error("tap %s needs %zu bytes, capacity %lld", name, t.bytes, (long long)cap);
+                return SVB_ERR_ARG;
+            }
+            SVB_CUDA(cudaSetDevice(c->device));
+            SVB_CUDA(cudaMemcpy(dst, t.dev, t.bytes, cudaMemcpyDeviceToHost));
+            return (int64_t)t.bytes;
+        }
+    set_error("no such tap: %s", name);
+    return SVB_ERR_ARG;
+}
+
+// ---- stage-isolated entry points -------------------------------------------------------------------------
+#define STAGE_PROLOG()                              \
+    if (!c) return SVB_ERR_ARG;                     \
+    std::lock_guard<std::mutex> lk(c->mu);          \
+    SVB_CUDA(cudaSetDevice(c->device));             \
+    const Dims &d = c->d;                           \
+    Lane &L = c->lanes[0];                          \
+    const size_t N = (size_t)d.N;                   \
+    (void)N;                                        \
+    (void)L;
+
+int svb_stage_descriptor(svb_context *c, const uint8_t *I, int stride, uint8_t *desc_out) {
+    STAGE_PROLOG();
+    if (!I || !desc_out || stride < d.W) return SVB_ERR_ARG;
+    SVB_CUDA(cudaMemcpy2DAsync(L.img[0], d.W, I, stride, d.W, d.H, cudaMemcpyHostToDevice, L.stream));
+    SVB_TRY(launch_descriptor(d, L.img[0], L.desc[0], 1, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(desc_out, L.desc[0], N * 16, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaStreamSynchronize(L.stream));
+    return SVB_OK;
+}
+
+int svb_stage_support(svb_context *c, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int16_t *dcan, int32_t *support, int cap,
+                      int *n_out) {
+    STAGE_PROLOG();
+    if (!desc1 || !desc2) return SVB_ERR_ARG;
+    SVB_CUDA(cudaMemcpyAsync(L.desc[0], desc1, N * 16, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(L.desc[1], desc2, N * 16, cudaMemcpyHostToDevice, L.stream));
+    SVB_TRY(launch_support_match(d, c->p, L.desc[0], L.desc[1], L.dcan_raw, 1, L.stream));
+    SVB_TRY(launch_support_filter(d, c->p, L.dcan_raw, L.dcan, L.removed, L.support, L.nsupport, 1, L.stream));
+    const size_t cb = (size_t)d.cw * d.ch * 2;
+    if (dcan_raw) SVB_CUDA(cudaMemcpyAsync(dcan_raw, L.dcan_raw, cb, cudaMemcpyDeviceToHost, L.stream));
+    if (dcan) SVB_CUDA(cudaMemcpyAsync(dcan, L.dcan, cb, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(L.h_nsupport, L.nsupport, 4, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(L.h_support, L.support, (size_t)d.maxS * 12, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaStreamSynchronize(L.stream));
+    const int n = L.h_nsupport[0];
+    if (n_out) *n_out = n;
+    if (support) memcpy(support, L.h_support, (size_t)(n < cap ? n : cap) * 12);
+    return SVB_OK;
+}
+
+int svb_stage_delaunay(const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out) {
+    if (!support || !tri || n < 0 || cap < 0) return SVB_ERR_ARG;
+    DelaunayScratch scratch;
+    const int m = delaunay_support(support, n, right_image, tri, cap, scratch);
+    if (n_tri_out) *n_tri_out = m;
+    return SVB_OK;
+}
+
+static int upload_support_and_tris(svb_context *c, Lane &L, const int32_t *support, int n, const int32_t *tri1, int m1, const int32_t *tri2,
+                                   int m2) {
+    const Dims &d = c->d;
+    if (n < 0 || n > d.maxS || m1 > d.maxT || m2 > d.maxT) {
+        set_error("support/triangle list too large (n=%d maxS=%d, m=%d/%d maxT=%d)", n, d.maxS, m1, m2, d.maxT);
+        return SVB_ERR_ARG;
+    }
+    L.h_nsupport[0] = n;
+    L.h_ntri[0] = m1 > 0 ? m1 : 0;
+    L.h_ntri[1] = m2 > 0 ? m2 : 0;
+    memcpy(L.h_support, support, (size_t)n * 12);
+    if (tri1 && m1 > 0) memcpy(L.h_tri[0], tri1, (size_t)m1 * 12);
+    if (tri2 && m2 > 0) memcpy(L.h_tri[1], tri2, (size_t)m2 * 12);
+    SVB_CUDA(cudaMemcpyAsync(L.nsupport, L.h_nsupport, 4, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(L.ntri, L.h_ntri, 8, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(L.support, L.h_support, (size_t)n * 12, cudaMemcpyHostToDevice, L.stream));
+    if (tri1 && m1 > 0) SVB_CUDA(cudaMemcpyAsync(L.tri[0], L.h_tri[0], (size_t)m1 * 12, cudaMemcpyHostToDevice, L.stream));
+    if (tri2 && m2 > 0) SVB_CUDA(cudaMemcpyAsync(L.tri[1], L.h_tri[1], (size_t)m2 * 12, cudaMemcpyHostToDevice, L.stream));
+    return SVB_OK;
+}
+
+int svb_stage_planes(svb_context *c, const int32_t *support, int n, const int32_t *tri, int m, float *planes) {
+    STAGE_PROLOG();
+    if (!support || !tri || !planes) return SVB_ERR_ARG;
+    float *tmp = nullptr;
+    SVB_TRY(dev_alloc(&tmp, (size_t)d.maxT * 6));
+    int r = upload_support_and_tris(c, L, support, n, tri, m, nullptr, 0);
+    if (r == SVB_OK) r = launch_planes(d, L.support, L.tri[0], L.tri[1], L.ntri, tmp, nullptr, L.rec[0], L.rec[1], 1, m, L.stream);
+    if (r == SVB_OK && cudaMemcpyAsync(planes, tmp, (size_t)m * 24, cudaMemcpyDeviceToHost, L.stream) != cudaSuccess) r = SVB_ERR_CUDA;
+    cudaStreamSynchronize(L.stream);
+    cudaFree(tmp);
+    return r;
+}
+
+int svb_stage_grid(svb_context *c, const int32_t *support, int n, int right_image, int32_t *grid) {
+    STAGE_PROLOG();
+    if (!support || !grid) return SVB_ERR_ARG;
+    const size_t gcount = (size_t)d.gw * d.gh * (c->p.disp_max + 2);
+    int32_t *tmp = nullptr;
+    SVB_TRY(dev_alloc(&tmp, gcount));
+    int r = upload_support_and_tris(c, L, support, n, nullptr, 0, nullptr, 0);
+    if (r == SVB_OK) r = launch_grid(d, c->p, L.support, L.nsupport, L.grid_tmp, L.grid[0], L.grid[1], 1, n, L.stream);
+    if (r == SVB_OK) r = launch_grid_expand(d, c->p, L.grid[right_image ? 1 : 0], tmp, L.stream);
+    if (r == SVB_OK && cudaMemcpyAsync(grid, tmp, gcount * 4, cudaMemcpyDeviceToHost, L.stream) != cudaSuccess) r = SVB_ERR_CUDA;
+    cudaStreamSynchronize(L.stream);
+    cudaFree(tmp);
+    return r;
+}
+
+int svb_stage_disparity(svb_context *c, const int32_t *support, int n, const int32_t *tri, int m, const uint8_t *desc1, const uint8_t *desc2,
+                        int right_image, float *D) {
+    STAGE_PROLOG();
+    if (!support || !tri || !desc1 || !desc2 || !D) return SVB_ERR_ARG;
+    const size_t C = (size_t)c->chunk;
+    SVB_CUDA(cudaMemcpyAsync(L.desc[0], desc1, N * 16, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(L.desc[1], desc2, N * 16, cudaMemcpyHostToDevice, L.stream));
+    // the same list is used for both sides; only the requested side is read back
+    SVB_TRY(upload_support_and_tris(c, L, support, n, tri, m, tri, m));
+    SVB_TRY(launch_planes(d, L.support, L.tri[0], L.tri[1], L.ntri, nullptr, nullptr, L.rec[0], L.rec[1], 1, m, L.stream));
+    SVB_TRY(launch_grid(d, c->p, L.support, L.nsupport, L.grid_tmp, L.grid[0], L.grid[1], 1, n, L.stream));
+    SVB_TRY(launch_raster(d, L.support, L.tri[0], L.tri[1], L.ntri, L.owner[0], L.owner[1], 1, m, L.stream));
+    SVB_TRY(launch_dense(d, c->p, L.desc[0], L.desc[1], L.owner[0], L.owner[1], L.rec[0], L.rec[1], L.grid[0], L.grid[1], L.Draw, L.Draw + C * N,
+                         1, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(D, right_image ? L.Draw + C * N : L.Draw, N * 4, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaStreamSynchronize(L.stream));
+    return SVB_OK;
+}
+
+int svb_stage_lr_check(svb_context *c, float *D1, float *D2) {
+    STAGE_PROLOG();
+    if (!D1 || !D2) return SVB_ERR_ARG;
+    const size_t C = (size_t)c->chunk;
+    SVB_CUDA(cudaMemcpyAsync(L.Draw, D1, N * 4, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(L.Draw + C * N, D2, N * 4, cudaMemcpyHostToDevice, L.stream));
+    SVB_TRY(launch_lr_check(d, c->p, L.Draw, L.Draw + C * N, L.Dlr, L.Dlr + C * N, 1, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(D1, L.Dlr, N * 4, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(D2, L.Dlr + C * N, N * 4, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaStreamSynchronize(L.stream));
+    return SVB_OK;
+}
+
+static int stage_inplace(svb_context *c, float *D, int which) {
+    STAGE_PROLOG();
+    if (!D) return SVB_ERR_ARG;
+    SVB_CUDA(cudaMemcpyAsync(L.Dlr, D, N * 4, cudaMemcpyHostToDevice, L.stream));
+    if (which == 0) SVB_TRY(launch_remove_small_segments(d, c->p, L.Dlr, L.labels, L.sizes, 1, L.stream));
+    if (which == 1) SVB_TRY(launch_gap(d, c->p, L.Dlr, 1, L.stream));
+    if (which == 2) SVB_TRY(launch_adaptive_mean(d, c->mean_mode, L.Dlr, L.Dtmp, 1, L.stream));
+    if (which == 3) SVB_TRY(launch_median(d, L.Dlr, L.Dtmp, 1, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(D, L.Dlr, N * 4, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaStreamSynchronize(L.stream));
+    return SVB_OK;
+}
+int svb_stage_remove_small_segments(svb_context *c, float *D) { return stage_inplace(c, D, 0); }
+int svb_stage_gap_interpolation(svb_context *c, float *D) { return stage_inplace(c, D, 1); }
+int svb_stage_adaptive_mean(svb_context *c, float *D) { return stage_inplace(c, D, 2); }
+int svb_stage_median(svb_context *c, float *D) { return stage_inplace(c, D, 3); }
+
+int svb_stage_reproject(svb_context *c, const float *D, const double *Q16, const double *XR9, const double *XT3, uint8_t *dmap_out,
+                        double *points_out) {
+    STAGE_PROLOG();
+    if (!D || !Q16 || !points_out) return SVB_ERR_ARG;
+    Calib cal;
+    memcpy(cal.Q, Q16, sizeof(cal.Q));
+    memset(cal.XR, 0, sizeof(cal.XR));
+    memset(cal.XT, 0, sizeof(cal.XT));
+    for (int i = 0; i < 3; i++) cal.XR[4 * i] = 1.0;
+    if (XR9) memcpy(cal.XR, XR9, sizeof(cal.XR));
+    if (XT3) memcpy(cal.XT, XT3, sizeof(cal.XT));
+    double *pts = nullptr;
+    SVB_TRY(dev_alloc(&pts, N * 3));
+    int r = SVB_OK;
+    if (cudaMemcpyAsync(L.Dlr, D, N * 4, cudaMemcpyHostToDevice, L.stream) != cudaSuccess) r = SVB_ERR_CUDA;
+    if (r == SVB_OK) r = launch_reproject(d, cal, L.Dlr, L.dmap, pts, 1, L.stream);
+    if (r == SVB_OK && cudaMemcpyAsync(points_out, pts, N * 24, cudaMemcpyDeviceToHost, L.stream) != cudaSuccess) r = SVB_ERR_CUDA;
+    if (r == SVB_OK && dmap_out && cudaMemcpyAsync(dmap_out, L.dmap, N, cudaMemcpyDeviceToHost, L.stream) != cudaSuccess) r = SVB_ERR_CUDA;
+    cudaStreamSynchronize(L.stream);
+    cudaFree(pts);
+    if (r == SVB_ERR_CUDA) set_error("svb_stage_reproject: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
+    return r;
+}
+
+// ---- batch pipeline -----------------------------------------------------------------------------------------
+static int ensure_store(void **p, size_t *have_frames, size_t want_frames, size_t bytes_per_frame) {
+    if (*p && *have_frames >= want_frames) return SVB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have_frames = 0;
+    cudaError_t e = cudaMalloc(p, want_frames * bytes_per_frame + 256);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) for a batch store: %s", want_frames * bytes_per_frame, cudaGetErrorString(e));
+        return SVB_ERR_CUDA;
+    }
+    *have_frames = want_frames;
+    return SVB_OK;
+}
+
+int svb_batch_upload(svb_context *c, const uint8_t *left, const uint8_t *right, int n_frames) {
+    if (!c || !left || !right || n_frames < 1) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SVB_CUDA(cudaSetDevice(c->device));
+    const size_t N = (size_t)c->d.N;
+    if (!(c->in_img[0] && c->in_frames >= (size_t)n_frames)) {
+        for (int s = 0; s < 2; s++) {
+            if (c->in_img[s]) cudaFree(c->in_img[s]);
+            c->in_img[s] = nullptr;
+        }
+        c->in_frames = 0;
+        for (int s = 0; s < 2; s++) SVB_TRY(dev_alloc(&c->in_img[s], (size_t)n_frames * N));
+        c->in_frames = n_frames;
+    }
+    SVB_CUDA(cudaMemcpy(c->in_img[0], left, (size_t)n_frames * N, cudaMemcpyHostToDevice));
+    SVB_CUDA(cudaMemcpy(c->in_img[1], right, (size_t)n_frames * N, cudaMemcpyHostToDevice));
+    return SVB_OK;
+}
+
+// Shared driver of the resident and the host-buffer (e2e) batch paths.
+static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h_left, const uint8_t *h_right, float *h_D1, double *h_points) {
+    const Dims &d = c->d;
+    const size_t N = (size_t)d.N;
+    const int C = c->chunk;
+    const bool from_host = h_left != nullptr;
+    const bool want_D = (flags & SVB_OUT_DISPARITY) != 0, want_P = (flags & SVB_OUT_POINTS) != 0;
+    if (!want_D && !want_P) {
+        set_error("batch: flags select no output");
+        return SVB_ERR_ARG;
+    }
+    stats_reset(c);
+    if (want_D) SVB_TRY(ensure_store((void **)&c->out_D1, &c->out_D1_frames, n_frames, N * 4));
+    if (want_P) SVB_TRY(ensure_store((void **)&c->out_points, &c->out_points_frames, n_frames, N * 24));
+    const int nchunks = (n_frames + C - 1) / C;
+    cudaEvent_t ev0, ev1;
+    SVB_CUDA(cudaEventCreate(&ev0));
+    SVB_CUDA(cudaEventCreate(&ev1));
+    SVB_CUDA(cudaDeviceSynchronize());
+    SVB_CUDA(cudaEventRecord(ev0, c->lanes[0].stream));
+    for (int l = 1; l < LANES; l++) SVB_CUDA(cudaStreamWaitEvent(c->lanes[l].stream, ev0, 0));
+
+    auto frames_of = [&](int k) { return (k + 1) * C <= n_frames ? C : n_frames - k * C; };
+    auto issue_a = [&](int k) -> int {
+        Lane &L = c->lanes[k % LANES];
+        const int nf = frames_of(k);
+        const size_t off = (size_t)k * C * N;
+        if (from_host) {
+            SVB_CUDA(cudaMemcpyAsync(L.img[0], h_left + off, nf * N, cudaMemcpyHostToDevice, L.stream));
+            SVB_CUDA(cudaMemcpyAsync(L.img[1], h_right + off, nf * N, cudaMemcpyHostToDevice, L.stream));
+            return stage_a(c, L, L.img[0], L.img[1], nf);
+        }
+        return stage_a(c, L, c->in_img[0] + off, c->in_img[1] + off, nf);
+    };
+    for (int k = 0; k < nchunks && k < LANES; k++) SVB_TRY(issue_a(k));
+    for (int k = 0; k < nchunks; k++) {
+        Lane &L = c->lanes[k % LANES];
+        const int nf = frames_of(k);
+        SVB_TRY(stage_host(c, L, nf));
+        if (c->stage_timing) lane_collect_times(c, L, 0, ST_H2D_TRIANGLES);
+        const size_t off = (size_t)k * C * N;
+        SVB_TRY(stage_b(c, L, nf, want_D ? c->out_D1 + off : nullptr, want_P ? c->out_points + off * 3 : nullptr));
+        if (from_host) {
+            if (want_D && h_D1) SVB_CUDA(cudaMemcpyAsync(h_D1 + off, c->out_D1 + off, nf * N * 4, cudaMemcpyDeviceToHost, L.stream));
+            if (want_P && h_points)
+                SVB_CUDA(cudaMemcpyAsync(h_points + off * 3, c->out_points + off * 3, nf * N * 24, cudaMemcpyDeviceToHost, L.stream));
+        }
+        if (c->stage_timing) {
+            // stage events of this lane are about to be reused by chunk k+LANES: drain them first
+            SVB_CUDA(cudaStreamSynchronize(L.stream));
+            lane_collect_times(c, L, ST_H2D_TRIANGLES, ST_COUNT);
+        }
+        if (k + LANES < nchunks) SVB_TRY(issue_a(k + LANES));
+    }
+    for (int l = 1; l < LANES; l++) {
+        SVB_CUDA(cudaEventRecord(c->lanes[l].ev_done, c->lanes[l].stream));
+        SVB_CUDA(cudaStreamWaitEvent(c->lanes[0].stream, c->lanes[l].ev_done, 0));
+    }
+    SVB_CUDA(cudaEventRecord(ev1, c->lanes[0].stream));
+    SVB_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    SVB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    c->stats.gpu_ms_total = ms;
+    c->stats.frames = n_frames;
+    c->stats.kernel_launches = g_launch_counter;
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
+
+int svb_batch_run(svb_context *c, int n_frames, int flags) {
+    if (!c || n_frames < 1) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SVB_CUDA(cudaSetDevice(c->device));
+    if (!c->in_img[0] || c->in_frames < (size_t)n_frames) {
+        set_error("svb_batch_run: only %zu frames are resident (upload first)", c->in_frames);
+        return SVB_ERR_ARG;
+    }
+    return batch_drive(c, n_frames, flags, nullptr, nullptr, nullptr, nullptr);
+}
+
+int svb_batch_run_host(svb_context *c, const uint8_t *left, const uint8_t *right, int n_frames, int flags, float *D1_out, double *points_out) {
+    if (!c || !left || !right || n_frames < 1) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SVB_CUDA(cudaSetDevice(c->device));
+    return batch_drive(c, n_frames, flags, left, right, D1_out, points_out);
+}
+
+int svb_batch_download_disparity(svb_context *c, int frame, float *out) {
+    if (!c || !out || frame < 0 || (size_t)frame >= c->out_D1_frames || !c->out_D1) return SVB_ERR_ARG;
+    SVB_CUDA(cudaSetDevice(c->device));
+    SVB_CUDA(cudaMemcpy(out, c->out_D1 + (size_t)frame * c->d.N, (size_t)c->d.N * 4, cudaMemcpyDeviceToHost));
+    return SVB_OK;
+}
+
+int svb_batch_download_points(svb_context *c, int frame, double *out) {
+    if (!c || !out || frame < 0 || (size_t)frame >= c->out_points_frames || !c->out_points) return SVB_ERR_ARG;
+    SVB_CUDA(cudaSetDevice(c->device));
+    SVB_CUDA(cudaMemcpy(out, c->out_points + (size_t)frame * c->d.N * 3, (size_t)c->d.N * 24, cudaMemcpyDeviceToHost));
+    return SVB_OK;
+}
+
+int svb_get_stats(svb_context *c, svb_stats *out) {
+    if (!c || !out) return SVB_ERR_ARG;
+    *out = c->stats;
+    return SVB_OK;
+}
+
+const char *svb_stage_name(int id) { return (id >= 0 && id < ST_COUNT) ? kStageNames[id] : ""; }
+
+void *svb_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void svb_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// Internal declarations shared by the CUDA translation units of libelas_b200.so.
+// Nothing here crosses the C-ABI (include/elas_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/elas_b200.h"
+
+namespace svb {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern thread_local long long g_launch_counter;  // kernels launched by this library on this thread
+
+#define SVB_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (call);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            svb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));   \
+            return SVB_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+#define SVB_TRY(call)              \
+    do {                           \
+        int _r = (call);           \
+        if (_r != SVB_OK) return _r; \
+    } while (0)
+
+#define SVB_LAUNCH_CHECK()                                                                          \
+    do {                                                                                            \
+        svb::g_launch_counter++;                                                                    \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e != cudaSuccess) {                                                                    \
+            svb::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return SVB_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+// ---- geometry derived from (params, width, height) ---------------------------------------------
+struct Dims {
+    int W, H, N;          // image size, N = W*H
+    int step, cw, ch;     // candidate grid (elas.cpp:376-386)
+    int gw, gh, gwords;   // disparity grid cells (elas.cpp:88-89) and 32-bit words per cell bitmask
+    int maxS;             // capacity of the support list  ((cw-1)*(ch-1) + 6 corner points)
+    int maxT;             // capacity of one triangle list (2*maxS is an upper bound for a planar triangulation)
+    int plane_radius;     // elas.cpp:832
+    int P[8];             // prior table P[|d - d_plane|] for deltas 0..plane_radius (elas.cpp:831)
+};
+
+int make_dims(const svb_params &p, int W, int H, Dims *out);
+
+// plane of one triangle for one side, as consumed by the dense matcher
+struct PlaneRec {
+    float a, b, c;  // plane in the image being matched (t1* for left, t2* for right)
+    int valid;      // fabs(a) < 0.7 && fabs(other side's a) < 0.7 (elas.cpp:910)
+};
+
+enum StageId {
+    ST_DESCRIPTOR = 0,
+    ST_SUPPORT_MATCH,
+    ST_SUPPORT_FILTER,
+    ST_D2H_SUPPORT,
+    ST_H2D_TRIANGLES,
+    ST_PLANES,
+    ST_GRID,
+    ST_RASTER,
+    ST_DENSE,
+    ST_LR,
+    ST_SEGMENTS,
+    ST_GAP,
+    ST_MEAN,
+    ST_MEDIAN,
+    ST_REPROJECT,
+    ST_COUNT
+};
+
+// ---- kernel launchers (each one is batched: `nimg`/`nf` independent images or frames) ----------
+// k_descriptor.cu
+int launch_descriptor(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, cudaStream_t s);
+// k_support.cu
+int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int nf,
+                         cudaStream_t s);
+int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dcan_raw, int16_t *dcan, uint8_t *scratch, int32_t *support,
+                          int32_t *nsupport, int nf, cudaStream_t s);
+// k_prior.cu
+int launch_planes(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, float *planes_ref1,
+                  float *planes_ref2, PlaneRec *rec1, PlaneRec *rec2, int nf, int max_tri, cudaStream_t s);
+int launch_grid(const Dims &d, const svb_params &p, const int32_t *support, const int32_t *nsupport, uint32_t *tmp, uint32_t *grid1,
+                uint32_t *grid2, int nf, int max_support, cudaStream_t s);
+int launch_grid_expand(const Dims &d, const svb_params &p, const uint32_t *grid, int32_t *grid_ref, cudaStream_t s);
+int launch_raster(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, int32_t *owner1,
+                  int32_t *owner2, int nf, int max_tri, cudaStream_t s);
+// k_dense.cu
+int launch_dense(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, const int32_t *owner1, const int32_t *owner2,
+                 const PlaneRec *rec1, const PlaneRec *rec2, const uint32_t *grid1, const uint32_t *grid2, float *D1, float *D2, int nf,
+                 cudaStream_t s);
+// k_post.cu
+int launch_lr_check(const Dims &d, const svb_params &p, const float *D1in, const float *D2in, float *D1out, float *D2out, int nf,
+                    cudaStream_t s);
+int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s);
+int launch_adaptive_mean(const Dims &d, int mean_mode, float *D, float *tmp, int nimg, cudaStream_t s);
+int launch_median(const Dims &d, float *D, float *tmp, int nimg, cudaStream_t s);
+// k_ccl.cu
+int launch_remove_small_segments(const Dims &d, const svb_params &p, float *D, int32_t *labels, int32_t *sizes, int nimg, cudaStream_t s);
+// k_reproject.cu
+struct Calib {
+    double Q[16];  // row-major 4x4 (cv::stereoRectify's Q, stereo_vision.cu:447)
+    double XR[9];  // row-major 3x3
+    double XT[3];
+};
+int launch_reproject(const Dims &d, const Calib &c, const float *D, uint8_t *dmap, double *points, int nf, cudaStream_t s);
+
+}  // namespace svb
