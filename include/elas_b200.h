@@ -84,6 +84,9 @@ svb_context *svb_create(const svb_params *params, int width, int height, int chu
 void svb_destroy(svb_context *ctx);
 int svb_set_mean_mode(svb_context *ctx, int mode);
 int svb_set_delaunay_threads(svb_context *ctx, int n_threads);
+/* on: every lane issues its GPU work on ONE stream (kernels never overlap one another, so the per-stage CUDA-event
+ * times of svb_stats are exact); off (default): one stream per lane. */
+int svb_set_single_stream(svb_context *ctx, int on);
 
 /* Elas::process (src/parallel_includes/elas/elas.h:151-160, serial semantics of
  * src/serial_includes/elas/elas.cpp:31-150).  Host buffers; I1/I2 are u8 with `stride` bytes per

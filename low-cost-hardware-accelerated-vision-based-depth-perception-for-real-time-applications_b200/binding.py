@@ -96,6 +96,7 @@ def load():
         "svb_set_mean_mode": [vp, C.c_int],
         "svb_set_delaunay_threads": [vp, C.c_int],
         "svb_set_stage_timing": [vp, C.c_int],
+        "svb_set_single_stream": [vp, C.c_int],
         "svb_set_tap_mode": [vp, C.c_int],
         "svb_process": [vp, vp, vp, C.c_int, vp, vp],
         "svb_inject_triangles": [vp, C.c_int, vp, C.c_int],
@@ -239,6 +240,9 @@ class Context:
 
     def set_stage_timing(self, on=True):
         self._chk(self.lib.svb_set_stage_timing(self.h, int(on)))
+
+    def set_single_stream(self, on=True):
+        self._chk(self.lib.svb_set_single_stream(self.h, int(on)))
 
     def set_delaunay_threads(self, n):
         self._chk(self.lib.svb_set_delaunay_threads(self.h, int(n)))

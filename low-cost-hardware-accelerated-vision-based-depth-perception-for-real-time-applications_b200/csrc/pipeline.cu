@@ -83,10 +83,9 @@ static const char *kStageNames[ST_COUNT] = {"descriptor", "support_match", "supp
 constexpr int LANES = 3;
 
 struct Lane {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_a = nullptr, ev_done = nullptr, ev_a_end = nullptr;
-    cudaEvent_t ev_stage[ST_COUNT + 1] = {};
-    bool stage_events_valid = false;
+    cudaStream_t own_stream = nullptr;  // created with the lane
+    cudaStream_t stream = nullptr;      // the stream the lane's work is issued on (own_stream, or lane 0's in single-stream mode)
+    cudaEvent_t ev_a = nullptr, ev_done = nullptr;
     // device
     uint8_t *img[2] = {nullptr, nullptr};
     uint8_t *desc[2] = {nullptr, nullptr};
@@ -105,6 +104,14 @@ struct Lane {
     uint8_t *dmap = nullptr;
     // pinned host
     int32_t *h_support = nullptr, *h_nsupport = nullptr, *h_tri[2] = {nullptr, nullptr}, *h_ntri = nullptr;
+};
+
+// CUDA events bracketing every stage of one chunk (stage timing): [i] is recorded in front of stage i, [ST_COUNT] after
+// the last stage, a_end behind the D2H that ends stage A.
+struct StageEvents {
+    cudaEvent_t ev[ST_COUNT + 1] = {};
+    cudaEvent_t a_end = nullptr;
+    bool a_done = false, b_done = false;
 };
 
 struct Tap {
@@ -144,6 +151,8 @@ struct svb_context {
     // stats
     svb_stats stats;
     bool stage_timing = false;
+    bool single_stream = false;
+    std::vector<StageEvents> stage_ev;  // one set per chunk of the call in flight
     std::mutex mu;
 };
 
@@ -173,11 +182,10 @@ int host_alloc(T **p, size_t count) {
 int lane_create(svb_context *c, Lane &L) {
     const Dims &d = c->d;
     const size_t C = (size_t)c->chunk, N = (size_t)d.N;
-    SVB_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    SVB_CUDA(cudaStreamCreateWithFlags(&L.own_stream, cudaStreamNonBlocking));
+    L.stream = L.own_stream;
     SVB_CUDA(cudaEventCreateWithFlags(&L.ev_a, cudaEventDisableTiming));
     SVB_CUDA(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
-    for (int i = 0; i <= ST_COUNT; i++) SVB_CUDA(cudaEventCreate(&L.ev_stage[i]));
-    SVB_CUDA(cudaEventCreate(&L.ev_a_end));
     for (int s = 0; s < 2; s++) {
         SVB_TRY(dev_alloc(&L.img[s], C * N));
         SVB_TRY(dev_alloc(&L.desc[s], C * N * 16));
@@ -232,37 +240,54 @@ void lane_destroy(Lane &L) {
     cudaFreeHost(L.h_support);
     cudaFreeHost(L.h_nsupport);
     cudaFreeHost(L.h_ntri);
-    for (int i = 0; i <= ST_COUNT; i++)
-        if (L.ev_stage[i]) cudaEventDestroy(L.ev_stage[i]);
     if (L.ev_a) cudaEventDestroy(L.ev_a);
-    if (L.ev_a_end) cudaEventDestroy(L.ev_a_end);
     if (L.ev_done) cudaEventDestroy(L.ev_done);
-    if (L.stream) cudaStreamDestroy(L.stream);
+    if (L.own_stream) cudaStreamDestroy(L.own_stream);
     L = Lane();
 }
 
 struct StageTimer {
-    svb_context *c;
     Lane &L;
-    bool on;
-    StageTimer(svb_context *c_, Lane &L_) : c(c_), L(L_), on(c_->stage_timing) {}
+    StageEvents *se;
+    StageTimer(Lane &L_, StageEvents *se_) : L(L_), se(se_) {}
     int mark(int idx) {
-        if (!on) return SVB_OK;
-        SVB_CUDA(cudaEventRecord(L.ev_stage[idx], L.stream));
+        if (!se) return SVB_OK;
+        SVB_CUDA(cudaEventRecord(se->ev[idx], L.stream));
         return SVB_OK;
     }
 };
 
-// collect per-stage times of a lane whose work has completed
-int lane_collect_times(svb_context *c, Lane &L, int first, int last) {
+// make sure `n` per-chunk event sets exist and mark them unused
+int stage_events_prepare(svb_context *c, int n) {
     if (!c->stage_timing) return SVB_OK;
-    for (int i = first; i < last; i++) {
-        float ms = 0.f;
-        // the D2H of the support lists ends stage A; the host stage separates it from the next device stage
-        cudaError_t e = cudaEventElapsedTime(&ms, L.ev_stage[i], i == ST_D2H_SUPPORT ? L.ev_a_end : L.ev_stage[i + 1]);
-        if (e == cudaSuccess) c->stats.stage_ms[i] += ms;
+    while ((int)c->stage_ev.size() < n) {
+        StageEvents se;
+        for (int i = 0; i <= ST_COUNT; i++) SVB_CUDA(cudaEventCreate(&se.ev[i]));
+        SVB_CUDA(cudaEventCreate(&se.a_end));
+        c->stage_ev.push_back(se);
     }
+    for (auto &se : c->stage_ev) se.a_done = se.b_done = false;
     return SVB_OK;
+}
+
+StageEvents *stage_events_of(svb_context *c, int chunk_index) {
+    return (c->stage_timing && chunk_index < (int)c->stage_ev.size()) ? &c->stage_ev[chunk_index] : nullptr;
+}
+
+// accumulate per-stage times of every chunk of a call whose device work has completed
+void stage_events_collect(svb_context *c) {
+    if (!c->stage_timing) return;
+    for (auto &se : c->stage_ev) {
+        for (int i = 0; i < ST_COUNT; i++) {
+            const bool in_a = i < ST_H2D_TRIANGLES;
+            if (in_a ? !se.a_done : !se.b_done) continue;
+            float ms = 0.f;
+            // the D2H of the support lists ends stage A; the host stage separates it from the next device stage
+            if (cudaEventElapsedTime(&ms, se.ev[i], i == ST_D2H_SUPPORT ? se.a_end : se.ev[i + 1]) == cudaSuccess)
+                c->stats.stage_ms[i] += ms;
+        }
+    }
+    cudaGetLastError();
 }
 
 int tap_store(svb_context *c, const char *name, const void *dev_src, size_t bytes, cudaStream_t s) {
@@ -285,9 +310,9 @@ int tap_store(svb_context *c, const char *name, const void *dev_src, size_t byte
 }
 
 // ---- stage A: images (device) -> support lists (device + pinned host) ------------------------------
-int stage_a(svb_context *c, Lane &L, const uint8_t *img1, const uint8_t *img2, int nf) {
+int stage_a(svb_context *c, Lane &L, const uint8_t *img1, const uint8_t *img2, int nf, StageEvents *se) {
     const Dims &d = c->d;
-    StageTimer T(c, L);
+    StageTimer T(L, se);
     SVB_TRY(T.mark(ST_DESCRIPTOR));
     SVB_TRY(launch_descriptor(d, img1, L.desc[0], nf, L.stream));
     SVB_TRY(launch_descriptor(d, img2, L.desc[1], nf, L.stream));
@@ -298,7 +323,10 @@ int stage_a(svb_context *c, Lane &L, const uint8_t *img1, const uint8_t *img2, i
     SVB_TRY(T.mark(ST_D2H_SUPPORT));
     SVB_CUDA(cudaMemcpyAsync(L.h_nsupport, L.nsupport, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, L.stream));
     SVB_CUDA(cudaMemcpyAsync(L.h_support, L.support, sizeof(int32_t) * 3 * (size_t)d.maxS * nf, cudaMemcpyDeviceToHost, L.stream));
-    if (T.on) SVB_CUDA(cudaEventRecord(L.ev_a_end, L.stream));
+    if (se) {
+        SVB_CUDA(cudaEventRecord(se->a_end, L.stream));
+        se->a_done = true;
+    }
     SVB_CUDA(cudaEventRecord(L.ev_a, L.stream));
     return SVB_OK;
 }
@@ -339,11 +367,11 @@ int stage_host(svb_context *c, Lane &L, int nf) {
 
 // ---- stage B: triangles (pinned host) -> disparity / points -------------------------------------------
 // out_D1 / out_points may be null.  The final maps stay in L.Dlr ([0] = left, [1] = right).
-int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points) {
+int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, StageEvents *se) {
     const Dims &d = c->d;
     const svb_params &p = c->p;
     const size_t N = (size_t)d.N, C = (size_t)c->chunk;
-    StageTimer T(c, L);
+    StageTimer T(L, se);
     int max_tri = 0, max_support = 0;
     for (int i = 0; i < 2 * nf; i++) max_tri = L.h_ntri[i] > max_tri ? L.h_ntri[i] : max_tri;
     for (int i = 0; i < nf; i++) max_support = L.h_nsupport[i] > max_support ? L.h_nsupport[i] : max_support;
@@ -409,6 +437,7 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points) 
     if (out_D1) SVB_CUDA(cudaMemcpyAsync(out_D1, D1, N * 4 * nf, cudaMemcpyDeviceToDevice, L.stream));
     if (out_points) SVB_TRY(launch_reproject(d, c->calib, D1, L.dmap, out_points, nf, L.stream));
     SVB_TRY(T.mark(ST_COUNT));
+    if (se) se->b_done = true;
     SVB_CUDA(cudaEventRecord(L.ev_done, L.stream));
     return SVB_OK;
 }
@@ -543,6 +572,11 @@ void svb_destroy(svb_context *c) {
     cudaDeviceSynchronize();
     for (int i = 0; i < LANES; i++) lane_destroy(c->lanes[i]);
     for (auto &t : c->taps) cudaFree(t.dev);
+    for (auto &se : c->stage_ev) {
+        for (int i = 0; i <= ST_COUNT; i++)
+            if (se.ev[i]) cudaEventDestroy(se.ev[i]);
+        if (se.a_end) cudaEventDestroy(se.a_end);
+    }
     for (int s = 0; s < 2; s++) {
         cudaFree(c->planes_ref[s]);
         cudaFree(c->in_img[s]);
@@ -568,6 +602,16 @@ int svb_set_delaunay_threads(svb_context *c, int n) {
 int svb_set_stage_timing(svb_context *c, int on) {
     if (!c) return SVB_ERR_ARG;
     c->stage_timing = on != 0;
+    return SVB_OK;
+}
+
+int svb_set_single_stream(svb_context *c, int on) {
+    if (!c) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SVB_CUDA(cudaSetDevice(c->device));
+    SVB_CUDA(cudaDeviceSynchronize());
+    c->single_stream = on != 0;
+    for (int i = 0; i < LANES; i++) c->lanes[i].stream = c->single_stream ? c->lanes[0].own_stream : c->lanes[i].own_stream;
     return SVB_OK;
 }
 
@@ -624,7 +668,9 @@ int svb_process(svb_context *c, const uint8_t *I1, const uint8_t *I2, int stride
     // elas.cpp:33-50: rows are copied out of the caller's stride
     SVB_CUDA(cudaMemcpy2DAsync(L.img[0], d.W, I1, stride, d.W, d.H, cudaMemcpyHostToDevice, L.stream));
     SVB_CUDA(cudaMemcpy2DAsync(L.img[1], d.W, I2, stride, d.W, d.H, cudaMemcpyHostToDevice, L.stream));
-    SVB_TRY(stage_a(c, L, L.img[0], L.img[1], 1));
+    SVB_TRY(stage_events_prepare(c, 1));
+    StageEvents *se = stage_events_of(c, 0);
+    SVB_TRY(stage_a(c, L, L.img[0], L.img[1], 1, se));
     if (c->tap_mode) SVB_TRY(tap_after_a(c, L));
     SVB_TRY(stage_host(c, L, 1));
     c->stats.frames = 1;
@@ -639,7 +685,7 @@ int svb_process(svb_context *c, const uint8_t *I1, const uint8_t *I2, int stride
         c->stats.kernel_launches = g_launch_counter;
         return SVB_ERR_FEW_SUPPORT;
     }
-    SVB_TRY(stage_b(c, L, 1, nullptr, nullptr));
+    SVB_TRY(stage_b(c, L, 1, nullptr, nullptr, se));
     if (c->tap_mode) {
         SVB_TRY(tap_store(c, "tri1", L.tri[0], (size_t)L.h_ntri[0] * 12, L.stream));
         SVB_TRY(tap_store(c, "tri2", L.tri[1], (size_t)L.h_ntri[1] * 12, L.stream));
@@ -662,7 +708,7 @@ int svb_process(svb_context *c, const uint8_t *I1, const uint8_t *I2, int stride
     SVB_CUDA(cudaMemcpyAsync(D1, L.Dlr, N * 4, cudaMemcpyDeviceToHost, L.stream));
     SVB_CUDA(cudaMemcpyAsync(D2, L.Dlr + C * N, N * 4, cudaMemcpyDeviceToHost, L.stream));
     SVB_CUDA(cudaStreamSynchronize(L.stream));
-    lane_collect_times(c, L, 0, ST_COUNT);
+    stage_events_collect(c);
     c->stats.kernel_launches = g_launch_counter;
     return SVB_OK;
 }
@@ -903,6 +949,7 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
     if (want_D) SVB_TRY(ensure_store((void **)&c->out_D1, &c->out_D1_frames, n_frames, N * 4));
     if (want_P) SVB_TRY(ensure_store((void **)&c->out_points, &c->out_points_frames, n_frames, N * 24));
     const int nchunks = (n_frames + C - 1) / C;
+    SVB_TRY(stage_events_prepare(c, nchunks));
     cudaEvent_t ev0, ev1;
     SVB_CUDA(cudaEventCreate(&ev0));
     SVB_CUDA(cudaEventCreate(&ev1));
@@ -918,27 +965,21 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
         if (from_host) {
             SVB_CUDA(cudaMemcpyAsync(L.img[0], h_left + off, nf * N, cudaMemcpyHostToDevice, L.stream));
             SVB_CUDA(cudaMemcpyAsync(L.img[1], h_right + off, nf * N, cudaMemcpyHostToDevice, L.stream));
-            return stage_a(c, L, L.img[0], L.img[1], nf);
+            return stage_a(c, L, L.img[0], L.img[1], nf, stage_events_of(c, k));
         }
-        return stage_a(c, L, c->in_img[0] + off, c->in_img[1] + off, nf);
+        return stage_a(c, L, c->in_img[0] + off, c->in_img[1] + off, nf, stage_events_of(c, k));
     };
     for (int k = 0; k < nchunks && k < LANES; k++) SVB_TRY(issue_a(k));
     for (int k = 0; k < nchunks; k++) {
         Lane &L = c->lanes[k % LANES];
         const int nf = frames_of(k);
         SVB_TRY(stage_host(c, L, nf));
-        if (c->stage_timing) lane_collect_times(c, L, 0, ST_H2D_TRIANGLES);
         const size_t off = (size_t)k * C * N;
-        SVB_TRY(stage_b(c, L, nf, want_D ? c->out_D1 + off : nullptr, want_P ? c->out_points + off * 3 : nullptr));
+        SVB_TRY(stage_b(c, L, nf, want_D ? c->out_D1 + off : nullptr, want_P ? c->out_points + off * 3 : nullptr, stage_events_of(c, k)));
         if (from_host) {
             if (want_D && h_D1) SVB_CUDA(cudaMemcpyAsync(h_D1 + off, c->out_D1 + off, nf * N * 4, cudaMemcpyDeviceToHost, L.stream));
             if (want_P && h_points)
                 SVB_CUDA(cudaMemcpyAsync(h_points + off * 3, c->out_points + off * 3, nf * N * 24, cudaMemcpyDeviceToHost, L.stream));
-        }
-        if (c->stage_timing) {
-            // stage events of this lane are about to be reused by chunk k+LANES: drain them first
-            SVB_CUDA(cudaStreamSynchronize(L.stream));
-            lane_collect_times(c, L, ST_H2D_TRIANGLES, ST_COUNT);
         }
         if (k + LANES < nchunks) SVB_TRY(issue_a(k + LANES));
     }
@@ -952,6 +993,7 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
     SVB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    stage_events_collect(c);
     c->stats.gpu_ms_total = ms;
     c->stats.frames = n_frames;
     c->stats.kernel_launches = g_launch_counter;

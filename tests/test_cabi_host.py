@@ -1,0 +1,135 @@
+"""CPU tests of the boundary and the host stage: the C-ABI library loads and exports every symbol that include/*.h
+declares, refuses to compute without a CUDA device, mirrors Elas::parameters, and its host Delaunay stage
+reproduces the reference's triangle lists (set AND order) on the golden support lists and on hard random cases."""
+import ctypes as C
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    names = []
+    for h in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"//[^\n]*", "", src)
+        for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(([^;{}()]*)\)\s*;", src):
+            name = m.group(1)
+            if name in ("defined", "sizeof", "__attribute__"):
+                continue
+            names.append(name)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol(svb):
+    lib = svb.load()
+    names = declared_symbols()
+    assert len(names) >= 30, names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, "declared in include/*.h but not exported: %s" % missing
+
+
+def test_no_cpu_fallback_without_device(svb):
+    """Without a CUDA device the library must fail loudly instead of computing on the CPU."""
+    if svb.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    p = svb.default_params(svb.ROBOTICS)
+    with pytest.raises(svb.SvbError) as e:
+        svb.Context(p, 640, 240)
+    assert "no CUDA device" in str(e.value) or "CPU" in str(e.value)
+
+
+@pytest.mark.parametrize("setting", [0, 1])
+def test_default_params_mirror_reference(svb, ref, setting):
+    """svb_default_params == Elas::parameters(setting) as compiled from the reference header."""
+    a = svb.default_params(setting)
+    b = ref.params(setting)
+    for name, _ in a._fields_:
+        assert getattr(a, name) == getattr(b, name), name
+    assert C.sizeof(a) == C.sizeof(b) == 23 * 4
+
+
+def test_pipeline_preset(svb, ref):
+    a = svb.default_params(svb.PIPELINE)
+    b = ref.pipeline_params()
+    for name, _ in a._fields_:
+        assert getattr(a, name) == getattr(b, name), name
+
+
+def test_unsupported_arguments_are_rejected(svb):
+    lib = svb.load()
+    assert lib.svb_default_params(0, None) != 0
+    assert lib.svb_stage_delaunay(None, 0, 0, None, 0, None) != 0
+    assert lib.svb_synth_pair(0, 4, 4, 0, None, None) != 0
+
+
+@pytest.mark.parametrize("key", ["robotics_0", "pipeline_0", "robotics_7", "pipeline_7"])
+def test_host_delaunay_matches_golden_order(svb, golden, key):
+    s = golden[key + "_support"]
+    for side in (0, 1):
+        got = svb.delaunay(s, side)
+        want = golden[key + "_tri%d" % (side + 1)]
+        assert got.shape == want.shape
+        assert np.array_equal(got, want), "%s side %d: triangle list differs from Triangle 1.6's" % (key, side)
+
+
+def lattice_support(rng, n, W=1242, H=375, step=5, dmax=60):
+    """Column-major lattice support points like computeSupportMatches emits (massively co-circular)."""
+    cw, ch = (W + step - 1) // step, (H + step - 1) // step
+    cells = [(u, v) for u in range(1, cw) for v in range(1, ch)]
+    pick = sorted(rng.choice(len(cells), size=min(n, len(cells)), replace=False))
+    base = rng.integers(0, dmax)
+    pts = []
+    for i in pick:
+        u, v = cells[i]
+        d = int(np.clip(base + rng.integers(-3, 4) + (v * step) // 40, 0, min(dmax, u * step)))
+        pts.append((u * step, v * step, d))
+    return np.array(pts, np.int32)
+
+
+@pytest.mark.parametrize("seed,n", [(1, 3), (2, 4), (3, 7), (4, 50), (5, 400), (6, 2500), (7, 6000)])
+def test_host_delaunay_matches_reference_on_random_lattices(svb, ref, seed, n):
+    rng = np.random.default_rng(seed)
+    s = lattice_support(rng, n)
+    for side in (0, 1):
+        want = ref.delaunay(s, side)
+        got = svb.delaunay(s, side)
+        assert np.array_equal(got, want), "seed %d n %d side %d" % (seed, n, side)
+
+
+def test_host_delaunay_degenerate_inputs(svb, ref):
+    # all collinear (one lattice column): Triangle emits no triangle
+    col = np.array([(50, 5 * i, 3) for i in range(1, 30)], np.int32)
+    assert len(svb.delaunay(col, 0)) == len(ref.delaunay(col, 0)) == 0
+    # one lattice row
+    row = np.array([(5 * i, 100, 2) for i in range(1, 40)], np.int32)
+    assert len(svb.delaunay(row, 0)) == len(ref.delaunay(row, 0)) == 0
+    # fewer than 3 points
+    assert len(svb.delaunay(col[:2], 0)) == 0
+    # duplicates in the right image (x = u - d collides): same survivors as the reference
+    dup = np.array([(100, 50, 10), (95, 50, 5), (200, 80, 20), (60, 120, 1), (300, 20, 9), (110, 50, 20)], np.int32)
+    assert np.array_equal(svb.delaunay(dup, 1), ref.delaunay(dup, 1))
+    # with the corner points add_corners appends (negative-free, includes u beyond W)
+    rng = np.random.default_rng(11)
+    s = lattice_support(rng, 300)
+    corners = np.array([(0, 0, 7), (0, 374, 9), (1241, 0, 4), (1241, 374, 30), (1245, 0, 4), (1271, 374, 30)], np.int32)
+    s2 = np.concatenate([s, corners])
+    for side in (0, 1):
+        assert np.array_equal(svb.delaunay(s2, side), ref.delaunay(s2, side))
+
+
+def test_synth_pair_is_deterministic_and_has_known_disparity(svb):
+    L1, R1 = svb.synth_pair(3, 320, 120)
+    L2, R2 = svb.synth_pair(3, 320, 120)
+    assert np.array_equal(L1, L2) and np.array_equal(R1, R2)
+    L3, _ = svb.synth_pair(4, 320, 120)
+    assert not np.array_equal(L1, L3)
+    # top band has disparity 8: right(x) ~ left(x + 8) up to +-2 noise
+    diff = np.abs(R1[:40, :300].astype(int) - L1[:40, 8:308].astype(int))
+    assert diff.max() <= 3
+    assert L1.std() > 10

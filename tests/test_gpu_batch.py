@@ -1,0 +1,117 @@
+"""GPU tests of the frame-batch pipeline (BASELINE.json configs[1]): chunked, multi-lane execution with the host
+Delaunay stage in between must give, frame for frame, what the single-frame Elas::process drop-in gives, both
+from device-resident inputs and end to end from host buffers."""
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def make_batch(svb, n, W, H):
+    L = np.zeros((n, H, W), np.uint8)
+    R = np.zeros((n, H, W), np.uint8)
+    for i in range(n):
+        svb.synth_pair(100 + i, W, H, i & 1, L[i], R[i])
+    return L, R
+
+
+@pytest.mark.parametrize("chunk,n", [(4, 11), (8, 8), (1, 3)])
+def test_batch_equals_single_frame_process(svb, golden_meta, chunk, n):
+    W, H = 1242, 375
+    L, R = make_batch(svb, n, W, H)
+    p = svb.default_params(svb.PIPELINE)
+    one = svb.Context(p, W, H, chunk=1)
+    ctx = svb.Context(p, W, H, chunk=chunk)
+    try:
+        Q, XR, XT = np.array(golden_meta["Q"]), np.array(golden_meta["XR"]), np.array(golden_meta["XT"])
+        ctx.set_calibration(Q, XR, XT)
+        ctx.batch_upload(L, R)
+        ctx.batch_run(n, svb.OUT_DISPARITY | svb.OUT_POINTS)
+        st = ctx.stats()
+        assert st["frames"] == n and st["frames_failed"] == 0 and st["kernel_launches"] > 0
+        for i in range(n):
+            D1, _ = one.process(L[i], R[i])
+            assert np.array_equal(ctx.batch_disparity(i), D1), "frame %d" % i
+            _, pts_o = parity.reproject_oracle(D1, Q, XR, XT)
+            pts = ctx.batch_points(i)
+            fin = np.isfinite(pts_o).all(1)
+            assert np.array_equal(np.isfinite(pts).all(1), fin)
+            rel = np.abs(pts[fin] - pts_o[fin]) / np.maximum(np.abs(pts_o[fin]), 1e-300)
+            assert rel.max() <= 1e-4
+        # run again: same result (arenas are reused, nothing may leak from the previous batch)
+        ctx.batch_run(n, svb.OUT_DISPARITY)
+        D1, _ = one.process(L[n - 1], R[n - 1])
+        assert np.array_equal(ctx.batch_disparity(n - 1), D1)
+    finally:
+        ctx.close()
+        one.close()
+
+
+def test_batch_against_oracle(svb, ref):
+    """Batch path vs the reference itself on a few frames (both presets)."""
+    W, H = 1242, 375
+    n = 3
+    L, R = make_batch(svb, n, W, H)
+    for setting, p_ref in ((svb.PIPELINE, ref.pipeline_params()), (svb.ROBOTICS, ref.params(0))):
+        ctx = svb.Context(svb.default_params(setting), W, H, chunk=2)
+        try:
+            ctx.batch_upload(L, R)
+            ctx.batch_run(n, svb.OUT_DISPARITY)
+            for i in range(n):
+                D1_ref, _, _ = ref.process(p_ref, L[i], R[i])
+                assert np.array_equal(ctx.batch_disparity(i), D1_ref)
+        finally:
+            ctx.close()
+
+
+def test_batch_from_host_buffers_matches_resident_path(svb, golden_meta):
+    W, H = 1242, 375
+    n = 6
+    L, R = make_batch(svb, n, W, H)
+    p = svb.default_params(svb.PIPELINE)
+    ctx = svb.Context(p, W, H, chunk=4)
+    try:
+        ctx.set_calibration(np.array(golden_meta["Q"]))
+        ctx.batch_upload(L, R)
+        ctx.batch_run(n, svb.OUT_DISPARITY | svb.OUT_POINTS)
+        want_D = [ctx.batch_disparity(i) for i in range(n)]
+        want_P = [ctx.batch_points(i) for i in range(n)]
+        hl = svb.PinnedArray((n, H, W), np.uint8)
+        hr = svb.PinnedArray((n, H, W), np.uint8)
+        hD = svb.PinnedArray((n, H, W), np.float32)
+        hP = svb.PinnedArray((n, H * W, 3), np.float64)
+        hl.array[:] = L
+        hr.array[:] = R
+        ctx.batch_run_host(hl.array, hr.array, svb.OUT_DISPARITY | svb.OUT_POINTS, hD.array, hP.array)
+        for i in range(n):
+            assert np.array_equal(hD.array[i], want_D[i])
+            assert np.array_equal(hP.array[i], want_P[i], equal_nan=True)
+        for a in (hl, hr, hD, hP):
+            a.free()
+    finally:
+        ctx.close()
+
+
+def test_batch_with_a_textureless_frame(svb):
+    """A frame with < 3 support points must not disturb its neighbours in the chunk; it is counted as failed."""
+    W, H = 640, 240
+    n = 4
+    L, R = make_batch(svb, n, W, H)
+    L[2] = 90
+    R[2] = 90
+    p = svb.default_params(svb.ROBOTICS)
+    ctx = svb.Context(p, W, H, chunk=4)
+    one = svb.Context(p, W, H, chunk=1)
+    try:
+        ctx.batch_upload(L, R)
+        ctx.batch_run(n, svb.OUT_DISPARITY)
+        assert ctx.stats()["frames_failed"] == 1
+        for i in (0, 1, 3):
+            D1, _ = one.process(L[i], R[i])
+            assert np.array_equal(ctx.batch_disparity(i), D1)
+        assert (ctx.batch_disparity(2) < 0).all()  # nothing matched: every pixel invalid
+    finally:
+        ctx.close()
+        one.close()

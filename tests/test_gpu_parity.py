@@ -1,0 +1,239 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the reference's serial ELAS
+(oracle/_ref) on the same inputs, and against the committed golden fixtures.
+
+Bars (BASELINE.json north_star): bit-exact descriptors, support matches and pre-filter integer disparities; the
+filtered float disparity within 1e-3 px on >= 99.9 % of valid pixels with an identical invalid mask (the
+kernels actually reproduce it bit for bit, which is what is asserted); point cloud within 1e-4 relative."""
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+FLOAT_TOL_PX = 1e-3  # north_star tolerance for post-filter disparities
+FLOAT_FRAC = 0.999
+POINT_RTOL = 1e-4  # north_star tolerance for the point cloud
+
+
+def presets(svb, ref):
+    return {
+        "robotics": (svb.default_params(svb.ROBOTICS), ref.params(0)),
+        "pipeline": (svb.default_params(svb.PIPELINE), ref.pipeline_params()),
+        "middlebury": (svb.default_params(svb.MIDDLEBURY), ref.params(1)),
+    }
+
+
+def assert_all_equal(res, allow=()):
+    bad = {k: v for k, v in res.items() if isinstance(v, dict) and not v["equal"] and k not in allow}
+    assert not bad, "stages differing from the oracle: %s" % bad
+
+
+def assert_float_bar(res):
+    assert res["D1_mask_equal"]
+    assert res.get("D1_frac_within_1e-3", 1.0) >= FLOAT_FRAC
+
+
+@pytest.mark.parametrize("pname", ["robotics", "pipeline", "middlebury"])
+def test_kitti0_staged_parity_with_injected_triangles(svb, ref, kitti_gray, pname):
+    L, R = kitti_gray["L0"], kitti_gray["R0"]
+    p, p_ref = presets(svb, ref)[pname]
+    ctx = svb.Context(p, L.shape[1], L.shape[0])
+    try:
+        res, t, _ = parity.staged_parity(ctx, ref, p_ref, L, R, inject=True)
+        assert_all_equal(res)
+        assert_float_bar(res)
+        iso = parity.isolated_parity(ctx, ref, p_ref, t)
+        assert_all_equal(iso)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("frame", [0, 7])
+@pytest.mark.parametrize("pname", ["robotics", "pipeline"])
+def test_kitti_end_to_end_against_golden(svb, kitti_gray, golden, pname, frame):
+    """Own host Delaunay, no oracle in the loop: compare with the committed outputs of the reference."""
+    L, R = kitti_gray["L%d" % frame], kitti_gray["R%d" % frame]
+    p = svb.default_params(svb.ROBOTICS if pname == "robotics" else svb.PIPELINE)
+    ctx = svb.Context(p, L.shape[1], L.shape[0])
+    try:
+        ctx.set_tap_mode(True)
+        D1, D2 = ctx.process(L, R)
+        key = "%s_%d" % (pname, frame)
+        assert np.array_equal(ctx.tap("support"), golden[key + "_support"])
+        assert np.array_equal(ctx.tap("tri1"), golden[key + "_tri1"])
+        assert np.array_equal(ctx.tap("tri2"), golden[key + "_tri2"])
+        assert np.array_equal(ctx.tap("D1raw").astype(np.int16), golden[key + "_D1raw"])
+        assert np.array_equal(ctx.tap("D2raw").astype(np.int16), golden[key + "_D2raw"])
+        want = golden[key + "_D1"]
+        assert np.array_equal(D1 >= 0, want >= 0)
+        both = want >= 0
+        err = np.abs(D1[both] - want[both])
+        assert (err <= FLOAT_TOL_PX).mean() >= FLOAT_FRAC
+        assert np.array_equal(D1, want)  # in fact bit-exact
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("W,H,slanted,pname", [(1242, 375, 0, "pipeline"), (1242, 375, 1, "robotics"), (640, 240, 0, "robotics"),
+                                                (333, 127, 1, "pipeline"), (1920, 1080, 0, "pipeline")])
+def test_synthetic_end_to_end_parity(svb, ref, W, H, slanted, pname):
+    """Synthetic frames of the bench workload (and the 1080p config) end to end with the product's own Delaunay;
+    ragged sizes (W, H not multiples of the tile / lattice / grid sizes) included."""
+    L, R = svb.synth_pair(5, W, H, slanted)
+    p, p_ref = presets(svb, ref)[pname]
+    ctx = svb.Context(p, W, H)
+    try:
+        res, t, (D1, _) = parity.staged_parity(ctx, ref, p_ref, L, R, inject=False)
+        assert_all_equal(res)
+        assert_float_bar(res)
+        if not slanted and W >= 640:
+            # sanity against the known scene: >= 95 % of valid pixels within 1 px of the true band disparity
+            truth = np.empty((H, W), np.float32)
+            truth[: H // 3] = 8
+            truth[H // 3: 2 * H // 3] = 24
+            truth[2 * H // 3:] = 48
+            v = D1 >= 0
+            assert v.mean() > 0.5
+            assert (np.abs(D1[v] - truth[v]) <= 1).mean() >= 0.95
+    finally:
+        ctx.close()
+
+
+def test_few_support_points_leaves_outputs_untouched(svb, ref):
+    """elas.cpp:64-69: a textureless pair yields < 3 support points; D1/D2 stay as the caller passed them."""
+    W, H = 320, 120
+    L = np.full((H, W), 77, np.uint8)
+    p = svb.default_params(svb.ROBOTICS)
+    ctx = svb.Context(p, W, H)
+    try:
+        with pytest.raises(svb.SvbError) as e:
+            ctx.process(L, L)
+        assert e.value.code == svb.ERR_FEW_SUPPORT
+        D1, D2, _ = ref.process(ref.params(0), L, L)
+        assert not D1.any() and not D2.any()  # the oracle leaves the zero-initialised buffers alone too
+    finally:
+        ctx.close()
+
+
+def test_uniform_noise_pair(svb, ref):
+    """Uncorrelated noise: most candidates fail the ratio / L-R tests; whatever survives must match exactly."""
+    rng = np.random.default_rng(9)
+    W, H = 400, 160
+    L = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    R = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    p, p_ref = presets(svb, ref)["pipeline"]
+    ctx = svb.Context(p, W, H)
+    try:
+        t = ref.staged(p_ref, L, R)
+        if len(t["support"]) < 3:
+            with pytest.raises(svb.SvbError):
+                ctx.process(L, R)
+        else:
+            res, _, _ = parity.staged_parity(ctx, ref, p_ref, L, R, inject=False)
+            assert_all_equal(res)
+    finally:
+        ctx.close()
+
+
+def test_process_is_deterministic_and_restartable(svb, kitti_gray):
+    L, R = kitti_gray["L7"], kitti_gray["R7"]
+    p = svb.default_params(svb.PIPELINE)
+    ctx = svb.Context(p, L.shape[1], L.shape[0])
+    try:
+        a = ctx.process(L, R)
+        b = ctx.process(R, L)  # different content in between
+        c = ctx.process(L, R)
+        assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
+        assert not np.array_equal(a[0], b[0])
+        st = ctx.stats()
+        assert st["kernel_launches"] >= 15 and st["frames"] == 1
+    finally:
+        ctx.close()
+
+
+def test_strided_input(svb, kitti_gray, golden):
+    """dims[2] (bytes per line) larger than the width, as Elas::process allows (elas.cpp:33-50)."""
+    L, R = kitti_gray["L0"], kitti_gray["R0"]
+    H, W = L.shape
+    stride = W + 37
+    Lp = np.full((H, stride), 255, np.uint8)
+    Rp = np.full((H, stride), 255, np.uint8)
+    Lp[:, :W] = L
+    Rp[:, :W] = R
+    p = svb.default_params(svb.ROBOTICS)
+    ctx = svb.Context(p, W, H)
+    try:
+        import ctypes as C
+
+        D1 = np.zeros((H, W), np.float32)
+        D2 = np.zeros((H, W), np.float32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = ctx.lib.svb_process(ctx.h, vp(Lp), vp(Rp), stride, vp(D1), vp(D2))
+        assert rc == 0
+        assert np.array_equal(D1, golden["robotics_0_D1"])
+    finally:
+        ctx.close()
+
+
+def test_adaptive_mean_true_abs_switch(svb, ref, kitti_gray, golden):
+    """SURVEY.md finding 3: mode 1 is the parallel reference's true-abs weight; it must differ from the serial
+    bit-mask form only through the weights (numpy restatement of src/parallel_includes/elas/elas.cpp:1552-1612)."""
+    D = golden["robotics_0_D1raw"].astype(np.float32)
+    D[D < 0] = -10
+    H, W = D.shape
+    p = svb.default_params(svb.ROBOTICS)
+    ctx = svb.Context(p, W, H)
+    try:
+        serial = ctx.adaptive_mean(D)
+        assert np.array_equal(serial, ref.adaptive_mean(ref.params(0), D))
+        ctx.set_mean_mode(1)
+        true_abs = ctx.adaptive_mean(D)
+        ctx.set_mean_mode(0)
+        # numpy restatement with |x| weights (float64 accumulation: compare with a tolerance)
+        Dc = np.where(D < 0, -10.0, D).astype(np.float64)
+        tmp = np.where(D < 0, -10.0, 0.0)
+        for c in range(4, W - 3):
+            win = Dc[3:H - 3, c - 4:c + 4]
+            w = np.maximum(0, 4 - np.abs(win - win[:, 4:5]))
+            ws = w.sum(1)
+            val = (w * win).sum(1) / np.where(ws > 0, ws, 1)
+            ok = (ws > 0) & (val >= 0)
+            tmp[3:H - 3, c] = np.where(ok, val, tmp[3:H - 3, c])
+        out = D.astype(np.float64).copy()
+        for c in range(4, H - 3):
+            win = tmp[c - 4:c + 4, 3:W - 3]
+            w = np.maximum(0, 4 - np.abs(win - win[4:5, :]))
+            ws = w.sum(0)
+            val = (w * win).sum(0) / np.where(ws > 0, ws, 1)
+            ok = (ws > 0) & (val >= 0)
+            out[c, 3:W - 3] = np.where(ok, val, out[c, 3:W - 3])
+        assert np.allclose(true_abs, out, atol=1e-3)
+        assert not np.array_equal(true_abs, serial)
+    finally:
+        ctx.close()
+
+
+def test_reproject_parity(svb, golden, golden_meta):
+    D = golden["pipeline_0_D1"]
+    H, W = D.shape
+    ctx = svb.Context(svb.default_params(svb.PIPELINE), W, H)
+    try:
+        for XR, XT in ((np.eye(3), np.zeros(3)), (np.array(golden_meta["XR"]), np.array(golden_meta["XT"]))):
+            dm, pts = ctx.reproject(D, np.array(golden_meta["Q"]), XR, XT)
+            dm_o, pts_o = parity.reproject_oracle(D, golden_meta["Q"], XR, XT)
+            assert np.array_equal(dm, dm_o)
+            fin = np.isfinite(pts_o).all(1)
+            assert np.array_equal(np.isfinite(pts).all(1), fin)
+            assert np.array_equal(np.isnan(pts), np.isnan(pts_o))
+            rel = np.abs(pts[fin] - pts_o[fin]) / np.maximum(np.abs(pts_o[fin]), 1e-300)
+            assert rel.max() <= POINT_RTOL
+            assert rel.max() <= 1e-15  # same operation order in f64: equal to the last bit or two
+        # a map with invalid pixels: d8 = 0 -> w = 0 -> inf / nan exactly like the reference kernel
+        D2 = golden["robotics_0_D1"]
+        dm, pts = ctx.reproject(D2, np.array(golden_meta["Q"]))
+        dm_o, pts_o = parity.reproject_oracle(D2, golden_meta["Q"], np.eye(3), np.zeros(3))
+        assert np.array_equal(dm, dm_o)
+        assert np.array_equal(np.isfinite(pts), np.isfinite(pts_o))
+    finally:
+        ctx.close()

@@ -1,0 +1,90 @@
+"""CPU tests: the oracle (the reference's own serial ELAS compiled into oracle/_ref, strict IEEE) is pinned by the
+committed golden fixtures that tests/golden/make_golden.py produced from the reference in the build container.
+
+The reference's own tests hold no known-answer vector for this path (SURVEY.md finding 6); the known answers the
+survey recorded from the compiled reference are asserted here as well."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import parity
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def preset(ref, name):
+    return ref.params(0) if name == "robotics" else ref.pipeline_params()
+
+
+def test_oracle_build_flags_are_strict_ieee(ref, golden_meta):
+    # SURVEY.md finding 2: the parity oracle must not be a -ffast-math / -march=native build
+    assert "-ffast-math" not in ref.flags and "-march" not in ref.flags
+    assert "-ffp-contract=off" in ref.flags
+    assert ref.flags == golden_meta["oracle_flags"]
+
+
+@pytest.mark.parametrize("pname", ["robotics", "pipeline"])
+def test_oracle_stage_taps_match_golden_hashes(ref, kitti_gray, golden, golden_meta, pname):
+    """Every stage tap of the oracle, re-run here, hashes to what the fixture generator recorded."""
+    L, R = kitti_gray["L0"], kitti_gray["R0"]
+    t = ref.staged(preset(ref, pname), L, R)
+    want = golden_meta["hashes"]["%s_0" % pname]
+    assert set(want) <= set(t)
+    bad = [k for k in want if sha(t[k]) != want[k]]
+    assert not bad, "oracle taps differ from the committed golden hashes: %s" % bad
+    assert np.array_equal(t["support"], golden["%s_0_support" % pname])
+    assert np.array_equal(t["tri1"], golden["%s_0_tri1" % pname])
+    assert np.array_equal(t["tri2"], golden["%s_0_tri2" % pname])
+    assert np.array_equal(t["D1"], golden["%s_0_D1" % pname])
+    assert np.array_equal(t["D1raw"].astype(np.int16), golden["%s_0_D1raw" % pname])
+
+
+def test_oracle_process_equals_staged_and_is_deterministic(ref, kitti_gray, golden):
+    L, R = kitti_gray["L7"], kitti_gray["R7"]
+    p = ref.pipeline_params()
+    D1a, D2a, _ = ref.process(p, L, R)
+    D1b, D2b, _ = ref.process(p, L, R)
+    assert np.array_equal(D1a, D1b) and np.array_equal(D2a, D2b)
+    assert np.array_equal(D1a, golden["pipeline_7_D1"])
+
+
+def test_survey_known_answers(golden):
+    """numbers recorded from the compiled reference on kitti_mini frame 0."""
+    assert len(golden["robotics_0_support"]) == 1254
+    assert len(golden["robotics_0_tri1"]) == 2469 and len(golden["robotics_0_tri2"]) == 2469
+    assert int(golden["robotics_0_support"][:, 2].max()) == 88
+    assert int((golden["robotics_0_D1"] >= 0).sum()) == 315374
+    assert len(golden["pipeline_0_support"]) == 1952
+    assert len(golden["pipeline_0_tri1"]) == 3896
+    assert int((golden["pipeline_0_D1"] >= 0).sum()) == 465750
+
+
+def test_oracle_prior_table(ref):
+    """P[] of elas.cpp:831 as listed in SURVEY.md 8a row 11, restated in numpy."""
+    for setting, want in ((0, [-14, -9, -2, 0]), (1, [-9, -5, -1, 0])):
+        p = ref.params(setting)
+        tss = 2 * p.sigma * p.sigma
+        got = [int((-np.log(p.gamma + np.exp(-d * d / tss)) + np.log(p.gamma)) / p.beta) for d in range(4)]
+        assert got == want
+
+
+def test_reproject_restatement_known_point(golden_meta):
+    """The numpy restatement of stereo_vision.cu:188-212,324 on hand-computed points."""
+    Q = np.array(golden_meta["Q"])
+    assert abs(Q[0, 3] + 738.7995529175) < 1e-6 and abs(Q[2, 3] - 1027.855158176) < 1e-6 and abs(Q[3, 2] - 1.861616069957) < 1e-9
+    D = np.full((2, 3), -10.0, np.float32)
+    D[0, 0] = 10.0  # -> u8 40
+    D[1, 2] = 0.125  # 0.5 -> round half even -> 0  -> w = 0 -> inf
+    D[0, 1] = 0.375  # 1.5 -> 2
+    D[1, 1] = 70.0  # saturates at 255
+    d8, pts = parity.reproject_oracle(D, Q, np.eye(3), np.zeros(3))
+    assert d8.tolist() == [[40, 2, 0], [0, 255, 0]]
+    w = Q[3, 2] * 40
+    assert np.allclose(pts[0], [Q[0, 3] / w, Q[1, 3] / w, Q[2, 3] / w], rtol=1e-15)
+    assert not np.isfinite(pts[5]).all()
+    XR, XT = np.array(golden_meta["XR"]), np.array(golden_meta["XT"])
+    _, pts2 = parity.reproject_oracle(D, Q, XR, XT)
+    assert np.allclose(pts2[0], XR.reshape(3, 3) @ pts[0] + XT.reshape(3), rtol=1e-13)
