@@ -45,7 +45,7 @@ __device__ void unite(int32_t *labels, int a, int b) {
     }
 }
 
-// grid: (ceil(W/128), H, nimg)   labels are indices local to the image
+// grid: (ceil(W/128), H, nimg)   labels are indices local to the image; invalid pixels get label -1
 __global__ void __launch_bounds__(128) k_ccl_init(const float *__restrict__ D_all, int32_t *__restrict__ labels_all, int32_t *__restrict__ sizes_all,
                                                  int W, int H, float thr) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,46 +55,103 @@ __global__ void __launch_bounds__(128) k_ccl_init(const float *__restrict__ D_al
     const bool in = u < W;
     const int idx = v * W + u;
     const float d = in ? D_all[img + idx] : -10.f;
-    const float dl = (in && u > 0) ? D_all[img + idx - 1] : -10.f;
+    const float dl = __shfl_up_sync(0xFFFFFFFFu, d, 1);
+    const float dleft = (lane == 0) ? ((in && u > 0) ? D_all[img + idx - 1] : -10.f) : dl;
     // linked to the left neighbour?
-    const bool link = in && similar(d, dl, thr);
+    const bool link = in && u > 0 && similar(d, dleft, thr);
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, link);
     if (!in) return;
     // run start inside this warp: the nearest lane at or below `lane` whose link bit is clear
     const unsigned clear_below = ~bal & ((2u << lane) - 1u);  // lanes <= lane with no left link (lane 31: all bits)
     const unsigned mask = (lane == 31) ? ~bal : clear_below;
-    int start_lane = mask ? (31 - __clz(mask)) : -1;
+    const int start_lane = mask ? (31 - __clz(mask)) : -1;
     int label;
-    if (start_lane >= 0) {
+    if (d < 0.f) {
+        label = -1;  // never joins anything (|-10 - x| > thr); pruned unconditionally (a segment of one pixel)
+    } else if (start_lane >= 0) {
         label = idx - (lane - start_lane);
     } else {
         // the run continues into the previous warp: link to the pixel just left of this warp's first lane
         label = idx - lane - 1;
     }
     labels_all[img + idx] = label;
-    sizes_all[img + idx] = 0;
+    if (label == idx) sizes_all[img + idx] = 0;  // only run starts can end up as roots (a root is its segment's minimum index)
 }
 
+// Vertical edges.  An edge (u,v)-(u,v-1) is skipped when the edge one column to the left already unites the same two
+// runs: both pixels are linked to their left neighbours and those neighbours are vertically similar.
 __global__ void __launch_bounds__(128) k_ccl_merge(const float *__restrict__ D_all, int32_t *__restrict__ labels_all, int W, int H, float thr) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = blockIdx.y;
-    if (u >= W || v == 0) return;
+    const int v = blockIdx.y + 1;
+    if (u >= W) return;
     const size_t img = (size_t)blockIdx.z * W * H;
     const int idx = v * W + u;
     const float d = D_all[img + idx];
     const float du = D_all[img + idx - W];
-    if (similar(d, du, thr)) unite(labels_all + img, idx, idx - W);
+    if (!similar(d, du, thr)) return;
+    if (u > 0) {
+        const float dl = D_all[img + idx - 1];
+        const float dul = D_all[img + idx - W - 1];
+        if (similar(d, dl, thr) && similar(du, dul, thr) && similar(dl, dul, thr)) return;
+    }
+    unite(labels_all + img, idx, idx - W);
 }
 
-__global__ void __launch_bounds__(128) k_ccl_count(int32_t *__restrict__ labels_all, int32_t *__restrict__ sizes_all, int W, int H) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = blockIdx.y;
-    if (u >= W) return;
+// Flatten labels to roots and count segment sizes.  A CTA covers a 128 x 8 pixel tile; equal roots are first combined
+// inside each warp (match.any), then across the CTA in a small shared-memory hash table, so a large segment costs one
+// global atomic per tile instead of one per pixel.
+constexpr int CNT_ROWS = 8;
+constexpr int CNT_SLOTS = 64;
+
+__global__ void __launch_bounds__(32 * CNT_ROWS) k_ccl_count(int32_t *__restrict__ labels_all, int32_t *__restrict__ sizes_all, int W, int H) {
+    __shared__ int s_key[CNT_SLOTS];
+    __shared__ int s_val[CNT_SLOTS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x < CNT_SLOTS) {
+        s_key[threadIdx.x] = -1;
+        s_val[threadIdx.x] = 0;
+    }
+    __syncthreads();
     const size_t img = (size_t)blockIdx.z * W * H;
-    const int idx = v * W + u;
-    const int r = find_root(labels_all + img, idx);
-    labels_all[img + idx] = r;  // path compression to the root (roots are fixed once merging has finished)
-    atomicAdd(sizes_all + img + r, 1);
+    int32_t *labels = labels_all + img;
+    int32_t *sizes = sizes_all + img;
+    const int v = blockIdx.y * CNT_ROWS + wid;
+    if (v < H) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int u = blockIdx.x * 128 + k * 32 + lane;
+            int r = -1;
+            if (u < W) {
+                const int idx = v * W + u;
+                const int l = labels[idx];
+                if (l >= 0) {
+                    r = find_root(labels, l);
+                    if (r != l) labels[idx] = r;  // roots are fixed once merging has finished
+                }
+            }
+            const unsigned act = __ballot_sync(0xFFFFFFFFu, r >= 0);
+            if (r >= 0) {
+                const unsigned same = __match_any_sync(act, r);
+                if (lane == __ffs(same) - 1) {
+                    const int cnt = __popc(same);
+                    unsigned h = ((unsigned)r * 2654435761u) >> 26;
+                    bool done = false;
+#pragma unroll 1
+                    for (int t = 0; t < 4 && !done; t++) {
+                        const int old = atomicCAS(&s_key[h], -1, r);
+                        if (old == -1 || old == r) {
+                            atomicAdd(&s_val[h], cnt);
+                            done = true;
+                        }
+                        h = (h + 1) & (CNT_SLOTS - 1);
+                    }
+                    if (!done) atomicAdd(sizes + r, cnt);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < CNT_SLOTS && s_key[threadIdx.x] >= 0) atomicAdd(sizes + s_key[threadIdx.x], s_val[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(128) k_ccl_prune(float *__restrict__ D_all, const int32_t *__restrict__ labels_all,
@@ -105,7 +162,11 @@ __global__ void __launch_bounds__(128) k_ccl_prune(float *__restrict__ D_all, co
     const size_t img = (size_t)blockIdx.z * W * H;
     const int idx = v * W + u;
     const int r = labels_all[img + idx];
-    if (sizes_all[img + r] < min_size) D_all[img + idx] = -10.f;
+    if (r < 0) {
+        if (1 < min_size) D_all[img + idx] = -10.f;
+    } else if (sizes_all[img + r] < min_size) {
+        D_all[img + idx] = -10.f;
+    }
 }
 
 }  // namespace
@@ -115,9 +176,13 @@ int launch_remove_small_segments(const Dims &d, const svb_params &p, float *D, i
     dim3 grid((d.W + 127) / 128, d.H, nimg);
     k_ccl_init<<<grid, 128, 0, s>>>(D, labels, sizes, d.W, d.H, p.speckle_sim_threshold);
     SVB_LAUNCH_CHECK();
-    k_ccl_merge<<<grid, 128, 0, s>>>(D, labels, d.W, d.H, p.speckle_sim_threshold);
-    SVB_LAUNCH_CHECK();
-    k_ccl_count<<<grid, 128, 0, s>>>(labels, sizes, d.W, d.H);
+    if (d.H > 1) {
+        dim3 gm((d.W + 127) / 128, d.H - 1, nimg);
+        k_ccl_merge<<<gm, 128, 0, s>>>(D, labels, d.W, d.H, p.speckle_sim_threshold);
+        SVB_LAUNCH_CHECK();
+    }
+    dim3 gc((d.W + 127) / 128, (d.H + CNT_ROWS - 1) / CNT_ROWS, nimg);
+    k_ccl_count<<<gc, 32 * CNT_ROWS, 0, s>>>(labels, sizes, d.W, d.H);
     SVB_LAUNCH_CHECK();
     k_ccl_prune<<<grid, 128, 0, s>>>(D, labels, sizes, d.W, d.H, p.speckle_size);
     SVB_LAUNCH_CHECK();
