@@ -23,116 +23,124 @@ __device__ __forceinline__ uint32_t texture16(const uint4 &a) {
 // Matching (elas.cpp:266-371 for every lattice candidate, forward then backward, elas.cpp:394-411).
 //
 // energy(u, d) = sum over the 4 anchors (u-+2, v-+2) of SAD16(own anchor, other image at the anchor shifted by d)
-// depends on the candidate column u and on the MATCHED column x = u -+ d.  The kernel is organised around x:
-// a warp owns 32 consecutive candidates of one lattice row (lane l <-> candidate l: its anchors sit in shared
-// memory, its running best / second best in the lane's registers) and walks over blocks of 32 consecutive matched
-// columns.  For a block every lane loads the four "other image" descriptors of ITS column once (coalesced), then
-// the warp loops over the candidates whose disparity range overlaps the block: the anchors come from shared
-// memory as broadcasts (one wavefront per load instead of four), each lane evaluates one hypothesis, and two
-// REDUX.MIN give the block's smallest and second smallest (energy, d) keys, which the owning lane merges.
-// Per hypothesis this costs 16 VABSDIFF4 + 5 broadcast LDS.128 per 32 hypotheses, against 4 lane-distinct
-// LDG.128 (16 L1 wavefronts per 32 hypotheses) of the candidate-major formulation.
+// depends on the candidate column u and on the MATCHED column x = u -+ d.  The kernel walks over x:
+// a warp owns a patch of 8 consecutive candidates x 4 consecutive lattice rows, one candidate per lane, whose
+// four anchors (64 B) and running best / second-best keys live in the lane's registers.  In step x every lane
+// loads the four "other image" descriptors of column x of ITS lattice row -- 4 distinct addresses per load
+// instruction, i.e. 4 L1 wavefronts instead of the 32 a candidate-major walk needs -- and evaluates the one
+// hypothesis d = u - x (or x - u).  Nothing is reduced across lanes.  The integer pipe is the limiter (ncu: ALU
+// pipe > 80 % busy), so the loop body is kept to 16 chained VABSDIFF4.ACC plus 5 other ALU instructions; the
+// patch shape keeps 256 / (256 + 35) = 88 % of the evaluated hypotheses inside their candidates' ranges.
 //
-// best = smallest energy, lowest d on ties; second = second smallest energy of the multiset (elas.cpp:352-360).
-constexpr int SM_WARPS = 4;
+// best = smallest energy, lowest d on ties; second = second smallest energy of the multiset (elas.cpp:352-360);
+// both follow from keeping the two smallest keys (E << 16 | d), which are distinct per candidate.
+constexpr int SM_WARPS = 8;   // warps per CTA: 8 neighbouring patches of the same 4 lattice rows (shared L1 footprint)
+constexpr int PATCH_U = 8;    // candidates per patch row
+constexpr int PATCH_V = 4;    // lattice rows per patch
 
-struct __align__(16) CandMeta {
-    int u, xlo, xhi, pad;
-};
+__device__ __forceinline__ unsigned sad16_acc(const uint4 &a, const uint4 &b, unsigned acc) {
+    // one dependent chain of VABSDIFF4.U8.ACC (no separate adds)
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc) : "r"(a.x), "r"(b.x));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc) : "r"(a.y), "r"(b.y));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc) : "r"(a.z), "r"(b.z));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc) : "r"(a.w), "r"(b.w));
+    return acc;
+}
 
-__device__ __forceinline__ int match_pass(const uint4 *__restrict__ own, const uint4 *__restrict__ oth, int u, bool has, int v, bool right_image,
-                                          int W, int H, int disp_min, int disp_max, int support_texture, float support_threshold,
-                                          uint4 (*s_anchor)[4], CandMeta *s_meta, int lane) {
+// One pass over the patch: every lane holds one candidate (u, v) of image `own`; returns its disparity or -1.
+template <bool right_image>
+__device__ __forceinline__ int match_pass(const uint4 *__restrict__ own, const uint4 *__restrict__ oth, int u, int v, bool has, int W, int H,
+                                          int disp_min, int disp_max, int support_texture, float support_threshold) {
     // candidate validity and disparity range (elas.cpp:279,296-300,318-327)
     bool ok = has && u >= 5 && u <= W - 6 && v >= 5 && v <= H - 6;
     if (ok) ok = (int)texture16(__ldg(own + (size_t)v * W + u)) >= support_texture;
     const int dmin = max(disp_min, 0);
     const int dmax = right_image ? min(disp_max, W - u - 5) : min(disp_max, u - 5);
     ok = ok && (dmax - dmin >= 10);
+    if (!__any_sync(0xFFFFFFFFu, ok)) return -1;
     // matched columns x = u - d (left candidate) or u + d (right candidate)
     const int xlo = ok ? (right_image ? u + dmin : u - dmax) : 0x7FFFFFFF;
     const int xhi = ok ? (right_image ? u + dmax : u - dmin) : (int)0x80000000;
-    const unsigned okmask = __ballot_sync(0xFFFFFFFFu, ok);
-    if (!okmask) return -1;
-    const size_t rowt = (size_t)(v - 2) * W, rowb = (size_t)(v + 2) * W;  // v >= 5 whenever any lane is ok
-    __syncwarp();
+    const int vv = ok ? v : 2;  // lanes without a candidate read (and discard) a row that certainly exists
+    const uint4 *ot = oth + (size_t)(vv - 2) * W;
+    const uint4 *ob = oth + (size_t)(vv + 2) * W;
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
     if (ok) {
-        s_anchor[lane][0] = __ldg(own + rowt + u - 2);
-        s_anchor[lane][1] = __ldg(own + rowt + u + 2);
-        s_anchor[lane][2] = __ldg(own + rowb + u - 2);
-        s_anchor[lane][3] = __ldg(own + rowb + u + 2);
-        CandMeta m;
-        m.u = u;
-        m.xlo = xlo;
-        m.xhi = xhi;
-        m.pad = 0;
-        s_meta[lane] = m;
+        a0 = __ldg(own + (size_t)(v - 2) * W + u - 2);
+        a1 = __ldg(own + (size_t)(v - 2) * W + u + 2);
+        a2 = __ldg(own + (size_t)(v + 2) * W + u - 2);
+        a3 = __ldg(own + (size_t)(v + 2) * W + u + 2);
     }
-    __syncwarp();
-    const int wxlo = __reduce_min_sync(0xFFFFFFFFu, xlo);
+    const int wxlo = __reduce_min_sync(0xFFFFFFFFu, xlo);  // >= 5 - 0 ... every x in [wxlo, wxhi] has x-2 >= 0 and x+2 < W
     const int wxhi = __reduce_max_sync(0xFFFFFFFFu, xhi);
-    unsigned best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;  // (E << 16) | d
-    for (int xb = wxlo; xb <= wxhi; xb += 32) {
-        const int x = xb + lane;
-        uint4 ot0 = make_uint4(0, 0, 0, 0), ot1 = ot0, ob0 = ot0, ob1 = ot0;
-        if (x >= 2 && x + 2 < W) {
-            ot0 = __ldg(oth + rowt + x - 2);
-            ot1 = __ldg(oth + rowt + x + 2);
-            ob0 = __ldg(oth + rowb + x - 2);
-            ob1 = __ldg(oth + rowb + x + 2);
-        }
-        unsigned m = __ballot_sync(0xFFFFFFFFu, ok && xlo <= xb + 31 && xhi >= xb);
-        while (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            const CandMeta cm = s_meta[j];
-            const uint4 a0 = s_anchor[j][0], a1 = s_anchor[j][1], a2 = s_anchor[j][2], a3 = s_anchor[j][3];
-            const unsigned e = sad16(a0, ot0) + sad16(a1, ot1) + sad16(a2, ob0) + sad16(a3, ob1);
-            const int d = right_image ? x - cm.u : cm.u - x;
-            const unsigned key = (x >= cm.xlo && x <= cm.xhi) ? ((e << 16) | (unsigned)d) : 0xFFFFFFFFu;
-            const unsigned k1 = __reduce_min_sync(0xFFFFFFFFu, key);
-            const unsigned k2 = __reduce_min_sync(0xFFFFFFFFu, key == k1 ? 0xFFFFFFFFu : key);  // valid keys are distinct (distinct d)
-            if (lane == j) {
-                const unsigned hi = max(best, k1);
-                best = min(best, k1);
-                second = min(hi, min(second, k2));
-            }
-        }
+    // d = sgn * (u - x); valid iff 0 <= d - dmin <= dmax - dmin.  Lanes without a candidate compute garbage that is
+    // discarded below, so `ok` is not part of the loop.
+    constexpr int sgn = right_image ? -1 : 1;
+    unsigned drel = (unsigned)(sgn * (u - wxlo) - dmin);   // d - dmin at x = wxlo; moves by -sgn per step
+    constexpr unsigned dstep = (unsigned)(-sgn);
+    const unsigned span = (unsigned)(dmax - dmin);
+    unsigned best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;     // (E << 16) | (d - dmin)
+    // The descriptor of column x+2 is needed again four steps later as column (x+4)-2: a ring of four descriptors per
+    // row keeps it in registers, so a step issues two loads (2 x 4 L1 wavefronts) instead of four.  The trip count is
+    // rounded up to a multiple of 4; the extra steps evaluate out-of-range hypotheses (rejected by drel > span) on
+    // columns that still lie inside the frame (row v+2 <= H-4, so a few descriptors past its end are the next row).
+    const uint4 *pt = ot + wxlo, *pb = ob + wxlo;
+    uint4 t0 = __ldg(pt - 2), t1 = __ldg(pt - 1), t2 = __ldg(pt), t3 = __ldg(pt + 1);
+    uint4 b0 = __ldg(pb - 2), b1 = __ldg(pb - 1), b2 = __ldg(pb), b3 = __ldg(pb + 1);
+#define SVB_MATCH_STEP(TK, BK, OFF)                                                        \
+    {                                                                                      \
+        const uint4 tn = __ldg(pt + 2 + OFF), bn = __ldg(pb + 2 + OFF);                    \
+        unsigned e = sad16_acc(a0, TK, 0u);                                                \
+        e = sad16_acc(a1, tn, e);                                                          \
+        e = sad16_acc(a2, BK, e);                                                          \
+        e = sad16_acc(a3, bn, e);                                                          \
+        const unsigned key = (drel <= span) ? e * 65536u + drel : 0xFFFFFFFFu;             \
+        second = min(second, max(best, key));                                              \
+        best = min(best, key);                                                             \
+        drel += dstep;                                                                     \
+        TK = tn;                                                                           \
+        BK = bn;                                                                           \
     }
+#pragma unroll 2
+    for (int n = (wxhi - wxlo + 4) >> 2; n > 0; n--) {
+        SVB_MATCH_STEP(t0, b0, 0)
+        SVB_MATCH_STEP(t1, b1, 1)
+        SVB_MATCH_STEP(t2, b2, 2)
+        SVB_MATCH_STEP(t3, b3, 3)
+        pt += 4;
+        pb += 4;
+    }
+#undef SVB_MATCH_STEP
     if (!ok) return -1;
     // at least 11 hypotheses were evaluated, so both minima exist (min_1_d >= 0 && min_2_d >= 0)
-    const int min1_e = (int)(best >> 16), min1_d = (int)(best & 0xFFFFu), min2_e = (int)(second >> 16);
+    const int min1_e = (int)(best >> 16), min1_d = (int)(best & 0xFFFFu) + dmin, min2_e = (int)(second >> 16);
     if ((float)min1_e < __fmul_rn(support_threshold, (float)min2_e)) return min1_d;  // elas.cpp:364
     return -1;
 }
 
-// grid: (ceil(rows * groups / SM_WARPS), nf); one warp = 32 consecutive candidates of one lattice row
+// grid: (ceil(#patches / SM_WARPS), nf); patches are numbered along the lattice row first
 __global__ void __launch_bounds__(SM_WARPS * 32) k_support_match(const uint8_t *__restrict__ desc1, const uint8_t *__restrict__ desc2,
                                                                  int16_t *__restrict__ dcan_raw, int W, int H, int cw, int ch, int step,
                                                                  int disp_min, int disp_max, int support_texture, float support_threshold,
                                                                  int lr_threshold) {
-    __shared__ uint4 s_anchor[SM_WARPS][32][4];
-    __shared__ CandMeta s_meta[SM_WARPS][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int groups = (cw - 1 + 31) / 32;
-    const int wg = blockIdx.x * SM_WARPS + wid;
-    const int row = wg / groups;
-    if (row >= ch - 1) return;  // warp-uniform
-    const int g = wg - row * groups;
+    const int pu = (cw - 1 + PATCH_U - 1) / PATCH_U, pv = (ch - 1 + PATCH_V - 1) / PATCH_V;
+    const int patch = blockIdx.x * SM_WARPS + wid;
+    if (patch >= pu * pv) return;  // warp-uniform
+    const int prow = patch / pu, pcol = patch - prow * pu;
     const int f = blockIdx.y;
-    const int vc = 1 + row, uc = 1 + g * 32 + lane;
-    const bool has = uc < cw;
+    const int uc = 1 + pcol * PATCH_U + (lane & (PATCH_U - 1));
+    const int vc = 1 + prow * PATCH_V + (lane / PATCH_U);
+    const bool has = uc < cw && vc < ch;
     const int u = uc * step, v = vc * step;
     const size_t fo = (size_t)f * W * H;
     const uint4 *d1 = reinterpret_cast<const uint4 *>(desc1) + fo;
     const uint4 *d2 = reinterpret_cast<const uint4 *>(desc2) + fo;
 
     // forward: candidate in the left image, search the right image (elas.cpp:403)
-    const int d = match_pass(d1, d2, u, has, v, false, W, H, disp_min, disp_max, support_texture, support_threshold, s_anchor[wid], s_meta[wid],
-                             lane);
+    const int d = match_pass<false>(d1, d2, u, v, has, W, H, disp_min, disp_max, support_texture, support_threshold);
     // backward: the match (u-d, v) as a candidate of the right image, search the left image (elas.cpp:406)
-    const int dback = match_pass(d2, d1, u - d, has && d >= 0, v, true, W, H, disp_min, disp_max, support_texture, support_threshold,
-                                 s_anchor[wid], s_meta[wid], lane);
+    const int dback = match_pass<true>(d2, d1, u - d, v, has && d >= 0, W, H, disp_min, disp_max, support_texture, support_threshold);
     int result = -1;
     if (d >= 0 && dback >= 0 && abs(d - dback) <= lr_threshold) result = d;  // elas.cpp:404-409
     if (has) dcan_raw[(size_t)f * cw * ch + (size_t)vc * cw + uc] = (int16_t)result;
@@ -355,8 +363,8 @@ int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc
         SVB_LAUNCH_CHECK();
     }
     if (d.cw < 2 || d.ch < 2) return SVB_OK;
-    const int warps = (d.ch - 1) * ((d.cw - 1 + 31) / 32);
-    dim3 grid((warps + SM_WARPS - 1) / SM_WARPS, nf);
+    const int patches = ((d.cw - 1 + PATCH_U - 1) / PATCH_U) * ((d.ch - 1 + PATCH_V - 1) / PATCH_V);
+    dim3 grid((patches + SM_WARPS - 1) / SM_WARPS, nf);
     k_support_match<<<grid, SM_WARPS * 32, 0, s>>>(desc1, desc2, dcan_raw, d.W, d.H, d.cw, d.ch, d.step, p.disp_min, p.disp_max,
                                                    p.support_texture, p.support_threshold, p.lr_threshold);
     SVB_LAUNCH_CHECK();
