@@ -277,36 +277,50 @@ def main():
     max_over_ranks, sum_over_ranks = group.max, group.sum
 
     # ---- resident-input steps ---------------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        ctx.batch_run(args.batch, flags)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    stage_ms = {}
-    launches = 0
-    delaunay_ms = 0.0
-    delaunay_wall = 0.0
-    gpu_ms = 0.0
-    tw0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.batch_run(args.batch, flags)  # synchronises on its own end event; gpu_ms_total = CUDA-event time of the step
-        st = ctx.stats()
-        gpu_ms += st["gpu_ms_total"]
-        launches += st["kernel_launches"]
-        delaunay_ms += st["delaunay_ms_total"]
-        delaunay_wall += st["delaunay_ms_wall"]
-        for k, v in st["stage_ms"].items():
-            stage_ms[k] = stage_ms.get(k, 0.0) + v
-    barrier()
-    wall_ms = (time.perf_counter() - tw0) * 1e3
-    clocks = sampler.finish() if sampler else None
+    def timed_steps(n_warm, n_steps, with_clocks):
+        for _ in range(n_warm):
+            ctx.batch_run(args.batch, flags)
+        sampler = ClockSampler(local_rank) if (rank == 0 and with_clocks) else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.3)
+        barrier()
+        acc = {"stage_ms": {}, "launches": 0, "delaunay_ms": 0.0, "delaunay_wall": 0.0, "gpu_ms": 0.0}
+        tw0 = time.perf_counter()
+        for _ in range(n_steps):
+            ctx.batch_run(args.batch, flags)  # synchronises on its own end event; gpu_ms_total = CUDA-event time of the step
+            st = ctx.stats()
+            acc["gpu_ms"] += st["gpu_ms_total"]
+            acc["launches"] += st["kernel_launches"]
+            acc["delaunay_ms"] += st["delaunay_ms_total"]
+            acc["delaunay_wall"] += st["delaunay_ms_wall"]
+            for k, v in st["stage_ms"].items():
+                acc["stage_ms"][k] = acc["stage_ms"].get(k, 0.0) + v
+        barrier()
+        acc["wall_ms"] = (time.perf_counter() - tw0) * 1e3
+        acc["clocks"] = sampler.finish() if sampler else None
+        return acc
+
+    # (1) the headline: one stream per lane, kernels of neighbouring chunks overlap
+    main_run = timed_steps(args.warmup, args.steps, True)
+    clocks = main_run["clocks"]
+    launches = main_run["launches"]
+    delaunay_ms, delaunay_wall, wall_ms = main_run["delaunay_ms"], main_run["delaunay_wall"], main_run["wall_ms"]
     # device time of the K steps (CUDA events around each step, summed), max over ranks
-    t_ms = max_over_ranks(gpu_ms)
+    t_ms = max_over_ranks(main_run["gpu_ms"])
     frames_total = sum_over_ranks(float(args.batch * args.steps))
     value = frames_total / (t_ms * 1e-3)
     st_last = ctx.stats()
+    # (2) the same K steps with every lane on ONE stream: kernels never overlap, so the CUDA events that bracket each
+    #     stage measure that stage alone -- these are the durations the roofline is computed from
+    if not args.single_stream:
+        ctx.set_single_stream(True)
+        exact_run = timed_steps(1, args.steps, False)
+        ctx.set_single_stream(False)
+    else:
+        exact_run = main_run
+    stage_ms = exact_run["stage_ms"]
+    value_single_stream = sum_over_ranks(float(args.batch * args.steps)) / (max_over_ranks(exact_run["gpu_ms"]) * 1e-3)
 
     # ---- end to end from pinned host buffers ----------------------------------------------------------------
     nb = min(args.e2e_batch, args.batch)
@@ -350,15 +364,18 @@ def main():
     per_stage = {}
     for k, v in kernel_stages.items():
         gbs = sb[k] * args.batch * args.steps / (v * 1e-3) / 1e9
-        per_stage[k] = {"ms_per_frame": v / (args.batch * args.steps), "GBps": gbs, "frac": gbs / peak}
+        per_stage[k] = {"us_per_frame": 1e3 * v / (args.batch * args.steps), "GBps": gbs, "frac": gbs / peak}
+    for k, v in stage_ms.items():
+        if k not in per_stage and v > 0:
+            per_stage[k] = {"us_per_frame": 1e3 * v / (args.batch * args.steps)}
     if top:
         ach = per_stage[top]["GBps"]
         roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peak_src, "bytes_per_launch": sb[top] * args.chunk,
                 "avg_launch_ms": kernel_stages[top] / nlaunch_per_stage,
                 "share_of_step": kernel_stages[top] / sum(stage_ms.values()),
-                "note": "stage time = CUDA events on the launching stream inside the timed region; with one stream per lane "
-                        "kernels of other lanes may share the GPU, see DESIGN.md"}
+                "note": "durations from the single-stream timed steps (CUDA events on the launching stream bracket each stage; "
+                        "no other kernel of ours runs concurrently), see DESIGN.md"}
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------
     cpu = None
@@ -388,6 +405,8 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clocks,
             "stages": per_stage,
+            "stages_overlapped_us_per_frame": {k: 1e3 * v / (args.batch * args.steps) for k, v in main_run["stage_ms"].items() if v > 0},
+            "value_single_stream": value_single_stream,
             "host_delaunay": {"ms_per_frame_cpu": delaunay_ms / (args.batch * args.steps), "wall_ms_per_step": delaunay_wall / args.steps,
                               "threads": min(threads_per_rank, 64) if args.delaunay_threads <= 0 else args.delaunay_threads},
             "wall_ms_per_step": wall_ms / args.steps,

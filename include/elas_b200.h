@@ -152,6 +152,17 @@ int svb_batch_download_points(svb_context *ctx, int frame, double *points_out);
 int svb_batch_run_host(svb_context *ctx, const uint8_t *left, const uint8_t *right, int n_frames, int flags, float *D1_out,
                        double *points_out);
 
+/* Body of generatePointCloud() after its one-time init (stereo_vision.cu:596-618): BGRA -> gray (cvtColor), Elas::process
+ * with the context's parameters, u8 conversion (convertTo(CV_8UC1, 4.0)) and projectParallel with the calibration set by
+ * svb_set_calibration.  left/right: height*width*4 BGRA bytes (host); points_out: width*height*3 doubles (host, pinned
+ * for full PCIe rate); dmap_out (u8) and D1_out (f32) may be NULL.  times_ms (may be NULL) receives {disparity part,
+ * point-cloud part} in CUDA-event milliseconds (the reference's dmap_t / pc_t).  With < 3 support points the disparity
+ * is 0 everywhere, like the reference's untouched zero-initialised map, and SVB_ERR_FEW_SUPPORT is returned. */
+int svb_point_cloud_bgra(svb_context *ctx, const uint8_t *left_bgra, const uint8_t *right_bgra, double *points_out, uint8_t *dmap_out,
+                         float *D1_out, double *times_ms);
+/* cv::cvtColor(BGRA2GRAY) on its own (stereo_vision.cu:346-347) */
+int svb_stage_bgra_to_gray(svb_context *ctx, const uint8_t *bgra, uint8_t *gray_out);
+
 /* timing / accounting of the most recent batch or process call */
 typedef struct svb_stats {
     double gpu_ms_total;       /* CUDA-event time from first to last kernel of the call */
@@ -167,6 +178,25 @@ typedef struct svb_stats {
 int svb_get_stats(svb_context *ctx, svb_stats *out);
 const char *svb_stage_name(int stage_id);
 int svb_set_stage_timing(svb_context *ctx, int on);
+
+/* ---- calibration without OpenCV (host only) -------------------------------------------------------------
+ * svb_calib_load_yaml replaces the cv::FileStorage reads of externalInit()/main()
+ * (src/parallel_includes/main/stereo_vision.cu:536-545,824-832): K1 K2 D1 D2 R T XR XT from an OpenCV-YAML file
+ * (XR/XT default to identity/zero when absent).
+ * svb_stereo_rectify replaces findRectificationMap() (stereo_vision.cu:368-447): K1/K2's first two rows are divided
+ * by scale_factor, then cv::stereoRectify(K1, D1, K2, D2, calib size, R, T, ..., CALIB_ZERO_DISPARITY, alpha, new
+ * size) is restated; the reference passes alpha = 0.  Outputs are row-major R1[9] R2[9] P1[12] P2[12] Q[16]; any may be
+ * NULL. */
+typedef struct svb_calibration {
+    double K1[9], K2[9];
+    double D1[14], D2[14];
+    int32_t n_d1, n_d2;
+    double R[9], T[3];
+    double XR[9], XT[3];
+} svb_calibration;
+int svb_calib_load_yaml(const char *path, svb_calibration *out);
+int svb_stereo_rectify(const svb_calibration *cal, int calib_width, int calib_height, int new_width, int new_height, double scale_factor,
+                       double alpha, double *R1, double *R2, double *P1, double *P2, double *Q);
 
 /* Deterministic synthetic rectified stereo pair of known disparity (bench / parity INPUT generator, host only;
  * SURVEY.md 8d).  left/right: W*H u8 each.  slanted = 0: bands of disparity 8/24/48; 1: d = 10 + 0.03 u. */

@@ -63,6 +63,13 @@ class Stats(C.Structure):
     ]
 
 
+class Calibration(C.Structure):
+    """svb_calibration: K1 K2 D1 D2 R T XR XT of an OpenCV-YAML calibration file."""
+
+    _fields_ = [("K1", C.c_double * 9), ("K2", C.c_double * 9), ("D1", C.c_double * 14), ("D2", C.c_double * 14), ("n_d1", C.c_int32),
+                ("n_d2", C.c_int32), ("R", C.c_double * 9), ("T", C.c_double * 3), ("XR", C.c_double * 9), ("XT", C.c_double * 3)]
+
+
 class SvbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("svb error %d: %s" % (code, msg))
@@ -121,6 +128,10 @@ def load():
         "svb_get_stats": [vp, C.POINTER(Stats)],
         "svb_default_params": [C.c_int, C.POINTER(Params)],
         "svb_synth_pair": [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp],
+        "svb_point_cloud_bgra": [vp, vp, vp, vp, vp, vp, vp],
+        "svb_stage_bgra_to_gray": [vp, vp, vp],
+        "svb_calib_load_yaml": [C.c_char_p, C.POINTER(Calibration)],
+        "svb_stereo_rectify": [C.POINTER(Calibration), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp],
     }.items():
         fn = getattr(lib, name)
         fn.argtypes = args
@@ -165,6 +176,28 @@ def delaunay(support, right):
     if rc != 0:
         raise SvbError(rc, lib.svb_last_error().decode())
     return tri[: m.value].copy()
+
+
+def load_calibration(path):
+    """K1 K2 D1 D2 R T XR XT from an OpenCV-YAML file (replaces cv::FileStorage, stereo_vision.cu:536-545)."""
+    lib = load()
+    cal = Calibration()
+    rc = lib.svb_calib_load_yaml(str(path).encode(), C.byref(cal))
+    if rc != 0:
+        raise SvbError(rc, lib.svb_last_error().decode())
+    return cal
+
+
+def stereo_rectify(cal, calib_size, new_size=None, scale_factor=1.0, alpha=0.0):
+    """findRectificationMap() without OpenCV (stereo_vision.cu:368-447): returns dict R1 R2 P1 P2 Q."""
+    lib = load()
+    new_size = new_size or calib_size
+    out = {"R1": np.zeros((3, 3)), "R2": np.zeros((3, 3)), "P1": np.zeros((3, 4)), "P2": np.zeros((3, 4)), "Q": np.zeros((4, 4))}
+    rc = lib.svb_stereo_rectify(C.byref(cal), calib_size[0], calib_size[1], new_size[0], new_size[1], float(scale_factor), float(alpha),
+                                _ptr(out["R1"]), _ptr(out["R2"]), _ptr(out["P1"]), _ptr(out["P2"]), _ptr(out["Q"]))
+    if rc != 0:
+        raise SvbError(rc, lib.svb_last_error().decode())
+    return out
 
 
 def synth_pair(frame_index, W=1242, H=375, slanted=0, left=None, right=None):
@@ -371,6 +404,27 @@ class Context:
         pts = np.zeros((self.H * self.W, 3), np.float64)
         self._chk(self.lib.svb_stage_reproject(self.h, _ptr(D), _ptr(Q), _ptr(XR), _ptr(XT), _ptr(dmap), _ptr(pts)))
         return dmap, pts
+
+    def bgra_to_gray(self, bgra):
+        """cv::cvtColor(BGRA2GRAY) (stereo_vision.cu:346-347) on the device."""
+        bgra = np.ascontiguousarray(bgra, np.uint8)
+        assert bgra.shape == (self.H, self.W, 4)
+        out = np.zeros((self.H, self.W), np.uint8)
+        self._chk(self.lib.svb_stage_bgra_to_gray(self.h, _ptr(bgra), _ptr(out)))
+        return out
+
+    def point_cloud_bgra(self, left_bgra, right_bgra):
+        """Body of generatePointCloud(): returns (points[N,3] f64, dmap u8, D1 f32, (dmap_ms, pc_ms))."""
+        left_bgra = np.ascontiguousarray(left_bgra, np.uint8)
+        right_bgra = np.ascontiguousarray(right_bgra, np.uint8)
+        pts = np.zeros((self.H * self.W, 3), np.float64)
+        dmap = np.zeros((self.H, self.W), np.uint8)
+        D1 = np.zeros((self.H, self.W), np.float32)
+        t = np.zeros(2, np.float64)
+        rc = self.lib.svb_point_cloud_bgra(self.h, _ptr(left_bgra), _ptr(right_bgra), _ptr(pts), _ptr(dmap), _ptr(D1), _ptr(t))
+        if rc not in (0, ERR_FEW_SUPPORT):
+            self._chk(rc)
+        return pts, dmap, D1, (float(t[0]), float(t[1]))
 
     # ---- batch pipeline ------------------------------------------------------------------------------------
     def batch_upload(self, left, right):

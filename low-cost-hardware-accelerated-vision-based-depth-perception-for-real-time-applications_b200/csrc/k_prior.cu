@@ -77,14 +77,15 @@ __device__ void fit_plane(const int32_t *__restrict__ support, int c1, int c2, i
 // grid: (ceil(maxT/128), 2 sides, nf).  Side s consumes triangle list s (left / right triangulation).
 __global__ void __launch_bounds__(128) k_planes(const int32_t *__restrict__ support_all, const int32_t *__restrict__ tri1_all,
                                                const int32_t *__restrict__ tri2_all, const int32_t *__restrict__ ntri_all,
-                                               float *__restrict__ planes1_all, float *__restrict__ planes2_all, PlaneRec *__restrict__ rec1_all,
-                                               PlaneRec *__restrict__ rec2_all, int maxS, int maxT) {
+                                               const int32_t *__restrict__ trioff_all, float *__restrict__ planes1_all,
+                                               float *__restrict__ planes2_all, PlaneRec *__restrict__ rec1_all, PlaneRec *__restrict__ rec2_all,
+                                               int maxS, int maxT) {
     const int f = blockIdx.z, side = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = ntri_all[2 * f + side];
     if (i >= n) return;
     const int32_t *support = support_all + (size_t)f * maxS * 3;
-    const int32_t *tri = (side ? tri2_all : tri1_all) + ((size_t)f * maxT + i) * 3;
+    const int32_t *tri = (side ? tri2_all : tri1_all) + ((size_t)trioff_all[f] + i) * 3;  // packed lists, see stage_host()
     float t1[3], t2[3];
     fit_plane(support, tri[0], tri[1], tri[2], false, t1);
     fit_plane(support, tri[0], tri[1], tri[2], true, t2);
@@ -186,14 +187,14 @@ __device__ __forceinline__ int f2u_as_int_x86(float x) {
 
 __global__ void __launch_bounds__(128) k_raster(const int32_t *__restrict__ support_all, const int32_t *__restrict__ tri1_all,
                                                const int32_t *__restrict__ tri2_all, const int32_t *__restrict__ ntri_all,
-                                               int32_t *__restrict__ owner1_all, int32_t *__restrict__ owner2_all, int W, int H, int maxS,
-                                               int maxT) {
+                                               const int32_t *__restrict__ trioff_all, int32_t *__restrict__ owner1_all,
+                                               int32_t *__restrict__ owner2_all, int W, int H, int maxS) {
     const int f = blockIdx.z, side = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (i >= ntri_all[2 * f + side]) return;
     const int32_t *support = support_all + (size_t)f * maxS * 3;
-    const int32_t *tri = (side ? tri2_all : tri1_all) + ((size_t)f * maxT + i) * 3;
+    const int32_t *tri = (side ? tri2_all : tri1_all) + ((size_t)trioff_all[f] + i) * 3;
     int32_t *owner = (side ? owner2_all : owner1_all) + (size_t)f * W * H;
 
     float tu[3], tv[3];
@@ -246,12 +247,12 @@ __global__ void __launch_bounds__(128) k_raster(const int32_t *__restrict__ supp
 
 }  // namespace
 
-int launch_planes(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, float *planes_ref1,
-                  float *planes_ref2, PlaneRec *rec1, PlaneRec *rec2, int nf, int max_tri, cudaStream_t s) {
+int launch_planes(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,
+                  float *planes_ref1, float *planes_ref2, PlaneRec *rec1, PlaneRec *rec2, int nf, int max_tri, cudaStream_t s) {
     if (nf <= 0 || max_tri <= 0) return SVB_OK;
     if (max_tri > d.maxT) max_tri = d.maxT;
     dim3 grid((max_tri + 127) / 128, 2, nf);
-    k_planes<<<grid, 128, 0, s>>>(support, tri1, tri2, ntri, planes_ref1, planes_ref2, rec1, rec2, d.maxS, d.maxT);
+    k_planes<<<grid, 128, 0, s>>>(support, tri1, tri2, ntri, trioff, planes_ref1, planes_ref2, rec1, rec2, d.maxS, d.maxT);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }
@@ -286,8 +287,8 @@ int launch_grid_expand(const Dims &d, const svb_params &p, const uint32_t *grid,
     return SVB_OK;
 }
 
-int launch_raster(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, int32_t *owner1,
-                  int32_t *owner2, int nf, int max_tri, cudaStream_t s) {
+int launch_raster(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,
+                  int32_t *owner1, int32_t *owner2, int nf, int max_tri, cudaStream_t s) {
     if (nf <= 0) return SVB_OK;
     if (max_tri > d.maxT) max_tri = d.maxT;
     cudaError_t e = cudaMemsetAsync(owner1, 0xFF, (size_t)nf * d.N * sizeof(int32_t), s);
@@ -298,7 +299,7 @@ int launch_raster(const Dims &d, const int32_t *support, const int32_t *tri1, co
     }
     if (max_tri <= 0) return SVB_OK;
     dim3 grid((max_tri + 3) / 4, 2, nf);
-    k_raster<<<grid, 128, 0, s>>>(support, tri1, tri2, ntri, owner1, owner2, d.W, d.H, d.maxS, d.maxT);
+    k_raster<<<grid, 128, 0, s>>>(support, tri1, tri2, ntri, trioff, owner1, owner2, d.W, d.H, d.maxS);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

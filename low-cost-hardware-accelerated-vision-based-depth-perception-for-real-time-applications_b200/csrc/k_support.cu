@@ -209,8 +209,9 @@ __device__ __forceinline__ void redundant_line(int16_t *work, int base, int stri
 // SMEM = false: it is worked on in place in the global dcan array (4K frames).
 template <bool SMEM>
 __global__ void __launch_bounds__(SF_THREADS) k_support_filter(const int16_t *__restrict__ dcan_raw_all, int16_t *__restrict__ dcan_all,
-                                                               int32_t *__restrict__ support_all, int32_t *__restrict__ nsupport_all, int W, int H,
-                                                               int cw, int ch, int step, int incon_window, int incon_threshold,
+                                                               int32_t *__restrict__ support_all, int32_t *__restrict__ nsupport_all,
+                                                               int32_t *__restrict__ h_support_all, int32_t *__restrict__ h_nsupport_all, int W,
+                                                               int H, int cw, int ch, int step, int incon_window, int incon_threshold,
                                                                int incon_min_support, int add_corners, int maxS) {
     extern __shared__ int16_t s_lattice[];
     const int f = blockIdx.x;
@@ -349,6 +350,14 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(const int16_t *__
         n += 6;
     }
     if (tid == 0) nsupport_all[f] = n;
+    // The host stage (Delaunay) needs the list: it is written straight into mapped pinned host memory, so only the
+    // n points that exist cross PCIe and no device-to-host copy has to be queued behind this kernel.
+    if (h_support_all) {
+        __syncthreads();
+        int32_t *hs = h_support_all + (size_t)f * maxS * 3;
+        for (int i = tid; i < 3 * n; i += SF_THREADS) hs[i] = support[i];
+        if (tid == 0) h_nsupport_all[f] = n;
+    }
 }
 
 }  // namespace
@@ -371,9 +380,8 @@ int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc
     return SVB_OK;
 }
 
-int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dcan_raw, int16_t *dcan, uint8_t *scratch, int32_t *support,
-                          int32_t *nsupport, int nf, cudaStream_t s) {
-    (void)scratch;
+int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dcan_raw, int16_t *dcan, int32_t *support, int32_t *nsupport,
+                          int32_t *h_support, int32_t *h_nsupport, int nf, cudaStream_t s) {
     if (nf <= 0) return SVB_OK;
     if (p.disp_max >= SF_REMOVED) {
         set_error("support filter: disp_max %d too large for the lattice cell encoding", p.disp_max);
@@ -388,10 +396,10 @@ int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dca
                 return SVB_ERR_CUDA;
             }
         }
-        k_support_filter<true><<<nf, SF_THREADS, smem, s>>>(dcan_raw, dcan, support, nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
+        k_support_filter<true><<<nf, SF_THREADS, smem, s>>>(dcan_raw, dcan, support, nsupport, h_support, h_nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
                                                             p.incon_threshold, p.incon_min_support, p.add_corners, d.maxS);
     } else {
-        k_support_filter<false><<<nf, SF_THREADS, 0, s>>>(dcan_raw, dcan, support, nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
+        k_support_filter<false><<<nf, SF_THREADS, 0, s>>>(dcan_raw, dcan, support, nsupport, h_support, h_nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
                                                           p.incon_threshold, p.incon_min_support, p.add_corners, d.maxS);
     }
     SVB_LAUNCH_CHECK();

@@ -12,6 +12,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <memory>
 #include <mutex>
@@ -90,10 +91,10 @@ struct Lane {
     uint8_t *img[2] = {nullptr, nullptr};
     uint8_t *desc[2] = {nullptr, nullptr};
     int16_t *dcan_raw = nullptr, *dcan = nullptr;
-    uint8_t *removed = nullptr;
     int32_t *support = nullptr, *nsupport = nullptr;
     int32_t *tri[2] = {nullptr, nullptr};
-    int32_t *ntri = nullptr;
+    int32_t *ntri = nullptr;    // [2*chunk] triangle counts (2f + side), then [chunk] first triangle of frame f in tri[]
+    int32_t *trioff = nullptr;  // = ntri + 2*chunk
     PlaneRec *rec[2] = {nullptr, nullptr};
     uint32_t *grid_tmp = nullptr, *grid[2] = {nullptr, nullptr};
     int32_t *owner[2] = {nullptr, nullptr};
@@ -141,6 +142,9 @@ struct svb_context {
     float *planes_ref[2] = {nullptr, nullptr};  // [maxT][6], tap mode only
     std::vector<int32_t> inject_tri[2];
     bool inject[2] = {false, false};
+    // generatePointCloud path: BGRA staging on the device
+    uint8_t *bgra[2] = {nullptr, nullptr};
+    cudaEvent_t ev_pc[4] = {nullptr, nullptr, nullptr, nullptr};
     // resident batch stores
     uint8_t *in_img[2] = {nullptr, nullptr};
     size_t in_frames = 0;
@@ -171,7 +175,7 @@ int dev_alloc(T **p, size_t count) {
 template <typename T>
 int host_alloc(T **p, size_t count) {
     *p = nullptr;
-    cudaError_t e = cudaHostAlloc((void **)p, count * sizeof(T) + 64, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc((void **)p, count * sizeof(T) + 64, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) {
         set_error("cudaHostAlloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
         return SVB_ERR_CUDA;
@@ -197,10 +201,10 @@ int lane_create(svb_context *c, Lane &L) {
     }
     SVB_TRY(dev_alloc(&L.dcan_raw, C * d.cw * d.ch));
     SVB_TRY(dev_alloc(&L.dcan, C * d.cw * d.ch));
-    SVB_TRY(dev_alloc(&L.removed, C * d.cw * d.ch));
     SVB_TRY(dev_alloc(&L.support, C * d.maxS * 3));
     SVB_TRY(dev_alloc(&L.nsupport, C));
-    SVB_TRY(dev_alloc(&L.ntri, C * 2));
+    SVB_TRY(dev_alloc(&L.ntri, C * 3));
+    L.trioff = L.ntri + 2 * C;
     SVB_TRY(dev_alloc(&L.grid_tmp, C * 2 * d.gw * d.gh * d.gwords));
     SVB_TRY(dev_alloc(&L.Draw, 2 * C * N));
     SVB_TRY(dev_alloc(&L.Dlr, 2 * C * N));
@@ -210,7 +214,7 @@ int lane_create(svb_context *c, Lane &L) {
     SVB_TRY(dev_alloc(&L.dmap, C * N));
     SVB_TRY(host_alloc(&L.h_support, C * d.maxS * 3));
     SVB_TRY(host_alloc(&L.h_nsupport, C));
-    SVB_TRY(host_alloc(&L.h_ntri, C * 2));
+    SVB_TRY(host_alloc(&L.h_ntri, C * 3));
     return SVB_OK;
 }
 
@@ -226,7 +230,6 @@ void lane_destroy(Lane &L) {
     }
     cudaFree(L.dcan_raw);
     cudaFree(L.dcan);
-    cudaFree(L.removed);
     cudaFree(L.support);
     cudaFree(L.nsupport);
     cudaFree(L.ntri);
@@ -319,10 +322,9 @@ int stage_a(svb_context *c, Lane &L, const uint8_t *img1, const uint8_t *img2, i
     SVB_TRY(T.mark(ST_SUPPORT_MATCH));
     SVB_TRY(launch_support_match(d, c->p, L.desc[0], L.desc[1], L.dcan_raw, nf, L.stream));
     SVB_TRY(T.mark(ST_SUPPORT_FILTER));
-    SVB_TRY(launch_support_filter(d, c->p, L.dcan_raw, L.dcan, L.removed, L.support, L.nsupport, nf, L.stream));
+    // the kernel writes the lists into the mapped pinned buffers itself: no device-to-host copy is queued
+    SVB_TRY(launch_support_filter(d, c->p, L.dcan_raw, L.dcan, L.support, L.nsupport, L.h_support, L.h_nsupport, nf, L.stream));
     SVB_TRY(T.mark(ST_D2H_SUPPORT));
-    SVB_CUDA(cudaMemcpyAsync(L.h_nsupport, L.nsupport, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, L.stream));
-    SVB_CUDA(cudaMemcpyAsync(L.h_support, L.support, sizeof(int32_t) * 3 * (size_t)d.maxS * nf, cudaMemcpyDeviceToHost, L.stream));
     if (se) {
         SVB_CUDA(cudaEventRecord(se->a_end, L.stream));
         se->a_done = true;
@@ -337,19 +339,40 @@ int stage_host(svb_context *c, Lane &L, int nf) {
     SVB_CUDA(cudaEventSynchronize(L.ev_a));
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<double> per_worker(c->pool->size(), 0.0);
+    // The triangle lists of a chunk are packed back to back: a triangulation of n points has at most 2n - 5 triangles,
+    // so frame f gets room for 2 n_f (or the injected list) starting at h_trioff[f]; only that much crosses PCIe.
+    int32_t *h_trioff = L.h_ntri + 2 * c->chunk;
+    {
+        int off = 0;
+        for (int f = 0; f < nf; f++) {
+            int n = L.h_nsupport[f];
+            if (n < 0 || n > d.maxS) n = L.h_nsupport[f] = 0;
+            int cap = 2 * n + 8;
+            for (int side = 0; side < 2; side++)
+                if (c->inject[side]) cap = std::max(cap, (int)(c->inject_tri[side].size() / 3));
+            h_trioff[f] = off;
+            off += cap;
+        }
+        h_trioff[nf] = off;  // total (h_ntri holds 3*chunk ints + slack, h_trioff[chunk] is the slack slot)
+        if ((size_t)off > (size_t)c->chunk * d.maxT) {
+            set_error("triangle lists do not fit the arena (%d > %zu)", off, (size_t)c->chunk * d.maxT);
+            return SVB_ERR_ARG;
+        }
+    }
     c->pool->parallel_for(nf * 2, [&](int job, int worker) {
         const auto w0 = std::chrono::steady_clock::now();
         const int f = job >> 1, side = job & 1;
         const int n = L.h_nsupport[f];
-        int32_t *out = L.h_tri[side] + (size_t)f * d.maxT * 3;
+        const int cap = h_trioff[f + 1] - h_trioff[f];
+        int32_t *out = L.h_tri[side] + (size_t)h_trioff[f] * 3;
         int m = 0;
         if (c->inject[side]) {
             m = (int)(c->inject_tri[side].size() / 3);
-            if (m > d.maxT) m = d.maxT;
+            if (m > cap) m = cap;
             memcpy(out, c->inject_tri[side].data(), sizeof(int32_t) * 3 * m);
         } else if (n >= 3) {
-            m = delaunay_support(L.h_support + (size_t)f * d.maxS * 3, n, side, out, d.maxT, c->scratch[worker]);
-            if (m > d.maxT) m = d.maxT;
+            m = delaunay_support(L.h_support + (size_t)f * d.maxS * 3, n, side, out, cap, c->scratch[worker]);
+            if (m > cap) m = cap;
         }
         L.h_ntri[2 * f + side] = m;
         per_worker[worker] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
@@ -376,17 +399,18 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, 
     for (int i = 0; i < 2 * nf; i++) max_tri = L.h_ntri[i] > max_tri ? L.h_ntri[i] : max_tri;
     for (int i = 0; i < nf; i++) max_support = L.h_nsupport[i] > max_support ? L.h_nsupport[i] : max_support;
     SVB_TRY(T.mark(ST_H2D_TRIANGLES));
-    SVB_CUDA(cudaMemcpyAsync(L.ntri, L.h_ntri, sizeof(int32_t) * 2 * nf, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(L.ntri, L.h_ntri, sizeof(int32_t) * 3 * C, cudaMemcpyHostToDevice, L.stream));
+    const size_t tri_total = (size_t)L.h_ntri[2 * C + nf];  // packed size of this chunk's lists, in triangles
     for (int s = 0; s < 2; s++)
-        SVB_CUDA(cudaMemcpyAsync(L.tri[s], L.h_tri[s], sizeof(int32_t) * 3 * (size_t)d.maxT * nf, cudaMemcpyHostToDevice, L.stream));
+        if (tri_total) SVB_CUDA(cudaMemcpyAsync(L.tri[s], L.h_tri[s], sizeof(int32_t) * 3 * tri_total, cudaMemcpyHostToDevice, L.stream));
     SVB_TRY(T.mark(ST_PLANES));
     float *pr1 = (c->tap_mode && nf == 1) ? c->planes_ref[0] : nullptr;
     float *pr2 = (c->tap_mode && nf == 1) ? c->planes_ref[1] : nullptr;
-    SVB_TRY(launch_planes(d, L.support, L.tri[0], L.tri[1], L.ntri, pr1, pr2, L.rec[0], L.rec[1], nf, max_tri, L.stream));
+    SVB_TRY(launch_planes(d, L.support, L.tri[0], L.tri[1], L.ntri, L.trioff, pr1, pr2, L.rec[0], L.rec[1], nf, max_tri, L.stream));
     SVB_TRY(T.mark(ST_GRID));
     SVB_TRY(launch_grid(d, p, L.support, L.nsupport, L.grid_tmp, L.grid[0], L.grid[1], nf, max_support, L.stream));
     SVB_TRY(T.mark(ST_RASTER));
-    SVB_TRY(launch_raster(d, L.support, L.tri[0], L.tri[1], L.ntri, L.owner[0], L.owner[1], nf, max_tri, L.stream));
+    SVB_TRY(launch_raster(d, L.support, L.tri[0], L.tri[1], L.ntri, L.trioff, L.owner[0], L.owner[1], nf, max_tri, L.stream));
     SVB_TRY(T.mark(ST_DENSE));
     float *D1raw = L.Draw, *D2raw = L.Draw + C * N;
     float *D1 = L.Dlr, *D2 = L.Dlr + C * N;
@@ -580,7 +604,10 @@ void svb_destroy(svb_context *c) {
     for (int s = 0; s < 2; s++) {
         cudaFree(c->planes_ref[s]);
         cudaFree(c->in_img[s]);
+        cudaFree(c->bgra[s]);
     }
+    for (int i = 0; i < 4; i++)
+        if (c->ev_pc[i]) cudaEventDestroy(c->ev_pc[i]);
     cudaFree(c->out_D1);
     cudaFree(c->out_points);
     delete c;
@@ -757,12 +784,10 @@ int svb_stage_support(svb_context *c, const uint8_t *desc1, const uint8_t *desc2
     SVB_CUDA(cudaMemcpyAsync(L.desc[0], desc1, N * 16, cudaMemcpyHostToDevice, L.stream));
     SVB_CUDA(cudaMemcpyAsync(L.desc[1], desc2, N * 16, cudaMemcpyHostToDevice, L.stream));
     SVB_TRY(launch_support_match(d, c->p, L.desc[0], L.desc[1], L.dcan_raw, 1, L.stream));
-    SVB_TRY(launch_support_filter(d, c->p, L.dcan_raw, L.dcan, L.removed, L.support, L.nsupport, 1, L.stream));
+    SVB_TRY(launch_support_filter(d, c->p, L.dcan_raw, L.dcan, L.support, L.nsupport, L.h_support, L.h_nsupport, 1, L.stream));
     const size_t cb = (size_t)d.cw * d.ch * 2;
     if (dcan_raw) SVB_CUDA(cudaMemcpyAsync(dcan_raw, L.dcan_raw, cb, cudaMemcpyDeviceToHost, L.stream));
     if (dcan) SVB_CUDA(cudaMemcpyAsync(dcan, L.dcan, cb, cudaMemcpyDeviceToHost, L.stream));
-    SVB_CUDA(cudaMemcpyAsync(L.h_nsupport, L.nsupport, 4, cudaMemcpyDeviceToHost, L.stream));
-    SVB_CUDA(cudaMemcpyAsync(L.h_support, L.support, (size_t)d.maxS * 12, cudaMemcpyDeviceToHost, L.stream));
     SVB_CUDA(cudaStreamSynchronize(L.stream));
     const int n = L.h_nsupport[0];
     if (n_out) *n_out = n;
@@ -788,11 +813,12 @@ static int upload_support_and_tris(svb_context *c, Lane &L, const int32_t *suppo
     L.h_nsupport[0] = n;
     L.h_ntri[0] = m1 > 0 ? m1 : 0;
     L.h_ntri[1] = m2 > 0 ? m2 : 0;
+    L.h_ntri[2 * c->chunk] = 0;  // one frame: its lists start at triangle 0
     memcpy(L.h_support, support, (size_t)n * 12);
     if (tri1 && m1 > 0) memcpy(L.h_tri[0], tri1, (size_t)m1 * 12);
     if (tri2 && m2 > 0) memcpy(L.h_tri[1], tri2, (size_t)m2 * 12);
     SVB_CUDA(cudaMemcpyAsync(L.nsupport, L.h_nsupport, 4, cudaMemcpyHostToDevice, L.stream));
-    SVB_CUDA(cudaMemcpyAsync(L.ntri, L.h_ntri, 8, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(L.ntri, L.h_ntri, sizeof(int32_t) * 3 * c->chunk, cudaMemcpyHostToDevice, L.stream));
     SVB_CUDA(cudaMemcpyAsync(L.support, L.h_support, (size_t)n * 12, cudaMemcpyHostToDevice, L.stream));
     if (tri1 && m1 > 0) SVB_CUDA(cudaMemcpyAsync(L.tri[0], L.h_tri[0], (size_t)m1 * 12, cudaMemcpyHostToDevice, L.stream));
     if (tri2 && m2 > 0) SVB_CUDA(cudaMemcpyAsync(L.tri[1], L.h_tri[1], (size_t)m2 * 12, cudaMemcpyHostToDevice, L.stream));
@@ -805,7 +831,7 @@ int svb_stage_planes(svb_context *c, const int32_t *support, int n, const int32_
     float *tmp = nullptr;
     SVB_TRY(dev_alloc(&tmp, (size_t)d.maxT * 6));
     int r = upload_support_and_tris(c, L, support, n, tri, m, nullptr, 0);
-    if (r == SVB_OK) r = launch_planes(d, L.support, L.tri[0], L.tri[1], L.ntri, tmp, nullptr, L.rec[0], L.rec[1], 1, m, L.stream);
+    if (r == SVB_OK) r = launch_planes(d, L.support, L.tri[0], L.tri[1], L.ntri, L.trioff, tmp, nullptr, L.rec[0], L.rec[1], 1, m, L.stream);
     if (r == SVB_OK && cudaMemcpyAsync(planes, tmp, (size_t)m * 24, cudaMemcpyDeviceToHost, L.stream) != cudaSuccess) r = SVB_ERR_CUDA;
     cudaStreamSynchronize(L.stream);
     cudaFree(tmp);
@@ -836,9 +862,9 @@ int svb_stage_disparity(svb_context *c, const int32_t *support, int n, const int
     SVB_CUDA(cudaMemcpyAsync(L.desc[1], desc2, N * 16, cudaMemcpyHostToDevice, L.stream));
     // the same list is used for both sides; only the requested side is read back
     SVB_TRY(upload_support_and_tris(c, L, support, n, tri, m, tri, m));
-    SVB_TRY(launch_planes(d, L.support, L.tri[0], L.tri[1], L.ntri, nullptr, nullptr, L.rec[0], L.rec[1], 1, m, L.stream));
+    SVB_TRY(launch_planes(d, L.support, L.tri[0], L.tri[1], L.ntri, L.trioff, nullptr, nullptr, L.rec[0], L.rec[1], 1, m, L.stream));
     SVB_TRY(launch_grid(d, c->p, L.support, L.nsupport, L.grid_tmp, L.grid[0], L.grid[1], 1, n, L.stream));
-    SVB_TRY(launch_raster(d, L.support, L.tri[0], L.tri[1], L.ntri, L.owner[0], L.owner[1], 1, m, L.stream));
+    SVB_TRY(launch_raster(d, L.support, L.tri[0], L.tri[1], L.ntri, L.trioff, L.owner[0], L.owner[1], 1, m, L.stream));
     SVB_TRY(launch_dense(d, c->p, L.desc[0], L.desc[1], L.owner[0], L.owner[1], L.rec[0], L.rec[1], L.grid[0], L.grid[1], L.Draw, L.Draw + C * N,
                          1, L.stream));
     SVB_CUDA(cudaMemcpyAsync(D, right_image ? L.Draw + C * N : L.Draw, N * 4, cudaMemcpyDeviceToHost, L.stream));
@@ -1030,6 +1056,78 @@ int svb_batch_download_points(svb_context *c, int frame, double *out) {
     if (!c || !out || frame < 0 || (size_t)frame >= c->out_points_frames || !c->out_points) return SVB_ERR_ARG;
     SVB_CUDA(cudaSetDevice(c->device));
     SVB_CUDA(cudaMemcpy(out, c->out_points + (size_t)frame * c->d.N * 3, (size_t)c->d.N * 24, cudaMemcpyDeviceToHost));
+    return SVB_OK;
+}
+
+// ---- generatePointCloud body: BGRA in, double3 point cloud out (stereo_vision.cu:596-618) ------------------------
+int svb_point_cloud_bgra(svb_context *c, const uint8_t *left_bgra, const uint8_t *right_bgra, double *points_out, uint8_t *dmap_out, float *D1_out,
+                         double *times_ms) {
+    if (!c || !left_bgra || !right_bgra || !points_out) {
+        set_error("svb_point_cloud_bgra: bad argument");
+        return SVB_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    SVB_CUDA(cudaSetDevice(c->device));
+    stats_reset(c);
+    const Dims &d = c->d;
+    Lane &L = c->lanes[0];
+    const size_t N = (size_t)d.N;
+    for (int s = 0; s < 2; s++)
+        if (!c->bgra[s]) SVB_TRY(dev_alloc(&c->bgra[s], N * 4));
+    for (int i = 0; i < 4; i++)
+        if (!c->ev_pc[i]) SVB_CUDA(cudaEventCreate(&c->ev_pc[i]));
+    SVB_TRY(ensure_store((void **)&c->out_points, &c->out_points_frames, 1, N * 24));
+    SVB_CUDA(cudaMemcpyAsync(c->bgra[0], left_bgra, N * 4, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(c->bgra[1], right_bgra, N * 4, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaEventRecord(c->ev_pc[0], L.stream));
+    // imgCallback_video(): cvtColor(BGRA2GRAY) of both images (stereo_vision.cu:346-347)
+    SVB_TRY(launch_bgra_to_gray(c->bgra[0], L.img[0], d.N, L.stream));
+    SVB_TRY(launch_bgra_to_gray(c->bgra[1], L.img[1], d.N, L.stream));
+    SVB_TRY(stage_events_prepare(c, 1));
+    StageEvents *se = stage_events_of(c, 0);
+    SVB_TRY(stage_a(c, L, L.img[0], L.img[1], 1, se));
+    SVB_TRY(stage_host(c, L, 1));
+    c->stats.frames = 1;
+    int rc = SVB_OK;
+    if (L.h_nsupport[0] < 3) {
+        // elas.cpp:64-69 leaves the zero-initialised leftdpf alone (stereo_vision.cu:312): disparity 0 everywhere
+        set_error("need at least 3 support points (got %d)", L.h_nsupport[0]);
+        rc = SVB_ERR_FEW_SUPPORT;
+        SVB_CUDA(cudaMemsetAsync(L.Dlr, 0, N * 4, L.stream));
+        SVB_CUDA(cudaEventRecord(c->ev_pc[1], L.stream));
+        SVB_TRY(launch_reproject(d, c->calib, L.Dlr, L.dmap, c->out_points, 1, L.stream));
+    } else {
+        // generateDisparityMap(): Elas::process, then convertTo(CV_8UC1, 4.0) fused with publishPointCloud()'s kernel
+        SVB_TRY(stage_b(c, L, 1, nullptr, nullptr, se));
+        SVB_CUDA(cudaEventRecord(c->ev_pc[1], L.stream));
+        SVB_TRY(launch_reproject(d, c->calib, L.Dlr, L.dmap, c->out_points, 1, L.stream));
+    }
+    SVB_CUDA(cudaMemcpyAsync(points_out, c->out_points, N * 24, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaEventRecord(c->ev_pc[2], L.stream));
+    if (dmap_out) SVB_CUDA(cudaMemcpyAsync(dmap_out, L.dmap, N, cudaMemcpyDeviceToHost, L.stream));
+    if (D1_out) SVB_CUDA(cudaMemcpyAsync(D1_out, L.Dlr, N * 4, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaStreamSynchronize(L.stream));
+    if (times_ms) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, c->ev_pc[0], c->ev_pc[1]);
+        cudaEventElapsedTime(&b, c->ev_pc[1], c->ev_pc[2]);
+        times_ms[0] = a;
+        times_ms[1] = b;
+    }
+    stage_events_collect(c);
+    c->stats.kernel_launches = g_launch_counter;
+    return rc;
+}
+
+// BGRA -> gray on its own (parity harness for the colour conversion)
+int svb_stage_bgra_to_gray(svb_context *c, const uint8_t *bgra, uint8_t *gray_out) {
+    STAGE_PROLOG();
+    if (!bgra || !gray_out) return SVB_ERR_ARG;
+    if (!c->bgra[0]) SVB_TRY(dev_alloc(&c->bgra[0], N * 4));
+    SVB_CUDA(cudaMemcpyAsync(c->bgra[0], bgra, N * 4, cudaMemcpyHostToDevice, L.stream));
+    SVB_TRY(launch_bgra_to_gray(c->bgra[0], L.img[0], d.N, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(gray_out, L.img[0], N, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaStreamSynchronize(L.stream));
     return SVB_OK;
 }
 

@@ -84,16 +84,18 @@ int launch_descriptor(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg
 // k_support.cu
 int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int nf,
                          cudaStream_t s);
-int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dcan_raw, int16_t *dcan, uint8_t *scratch, int32_t *support,
-                          int32_t *nsupport, int nf, cudaStream_t s);
+// h_support / h_nsupport: device-accessible (mapped pinned) host copies written by the kernel itself, may be null
+int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dcan_raw, int16_t *dcan, int32_t *support, int32_t *nsupport,
+                          int32_t *h_support, int32_t *h_nsupport, int nf, cudaStream_t s);
 // k_prior.cu
-int launch_planes(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, float *planes_ref1,
-                  float *planes_ref2, PlaneRec *rec1, PlaneRec *rec2, int nf, int max_tri, cudaStream_t s);
+// tri1 / tri2 hold the frames' triangle lists packed back to back: frame f starts at triangle trioff[f] (both sides)
+int launch_planes(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,
+                  float *planes_ref1, float *planes_ref2, PlaneRec *rec1, PlaneRec *rec2, int nf, int max_tri, cudaStream_t s);
 int launch_grid(const Dims &d, const svb_params &p, const int32_t *support, const int32_t *nsupport, uint32_t *tmp, uint32_t *grid1,
                 uint32_t *grid2, int nf, int max_support, cudaStream_t s);
 int launch_grid_expand(const Dims &d, const svb_params &p, const uint32_t *grid, int32_t *grid_ref, cudaStream_t s);
-int launch_raster(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, int32_t *owner1,
-                  int32_t *owner2, int nf, int max_tri, cudaStream_t s);
+int launch_raster(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,
+                  int32_t *owner1, int32_t *owner2, int nf, int max_tri, cudaStream_t s);
 // k_dense.cu
 int launch_dense(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, const int32_t *owner1, const int32_t *owner2,
                  const PlaneRec *rec1, const PlaneRec *rec2, const uint32_t *grid1, const uint32_t *grid2, float *D1, float *D2, int nf,
@@ -113,5 +115,7 @@ struct Calib {
     double XT[3];
 };
 int launch_reproject(const Dims &d, const Calib &c, const float *D, uint8_t *dmap, double *points, int nf, cudaStream_t s);
+// k_convert.cu
+int launch_bgra_to_gray(const uint8_t *bgra, uint8_t *gray, int n, cudaStream_t s);
 
 }  // namespace svb
