@@ -29,69 +29,128 @@ struct DenseArgs {
     int P[8];
 };
 
-// grid: (ceil(W/128), H, nf*2); blockIdx.z = 2*frame + side
-__global__ void __launch_bounds__(128) k_dense(const DenseArgs a) {
+__device__ __forceinline__ unsigned sad16_acc(const uint4 &a, const uint4 &b, unsigned acc) {
+    // one dependent chain of VABSDIFF4.U8.ACC seeded with `acc`
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc) : "r"(a.x), "r"(b.x));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc) : "r"(a.y), "r"(b.y));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc) : "r"(a.z), "r"(b.z));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc) : "r"(a.w), "r"(b.w));
+    return acc;
+}
+
+// base + idx as one IMAD.WIDE (FMA pipe) instead of a 4-instruction 64-bit LEA sequence on the ALU pipe
+__device__ __forceinline__ const uint4 *desc_at(const uint4 *base, int idx) {
+    unsigned long long r;
+    asm("mad.wide.s32 %0, %1, 16, %2;" : "=l"(r) : "r"(idx), "l"(base));
+    return reinterpret_cast<const uint4 *>(r);
+}
+
+// mask of the bits lo..hi (inclusive, any ints) that fall into a 32-bit word covering values base..base+31
+__device__ __forceinline__ uint32_t range_mask(int lo, int hi, int base) {
+    lo = max(lo - base, 0);
+    hi = min(hi - base, 31);
+    if (lo > hi) return 0u;
+    return (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+}
+
+// grid: (ceil(W/128), H, nf*2); blockIdx.z = 2*frame + side.  One thread = one pixel, one warp = 32 consecutive
+// pixels of a row.  The candidate loops are WARP-UNIFORM: the warp walks the union of its lanes' grid-cell bit
+// masks (REDUX.OR) in ascending d, so in every step all lanes look at the same disparity -- their loads hit 32
+// consecutive descriptors (one coalesced 512-byte access) and there is no loop divergence; a lane takes part in a
+// step iff d is in ITS cell's list, outside ITS plane band and its warped column is inside the image.  The band
+// (d_plane - r .. d_plane + r) is walked by the offset k, uniform as well, so the prior P[|k|] is a scalar.
+//
+// The running minimum is one packed key  (SAD + prior + 16) << 13 | phase << 12 | d :
+//   smaller cost wins; on equal cost the grid phase (0) beats the band phase (1) and, inside a phase, the smaller d
+//   wins -- exactly "first evaluated wins" of the reference's strict `<` over its evaluation order
+//   (elas.cpp:757-794: grid candidates ascending, then the band ascending).  min_val starts at 10000 > any cost.
+template <int SIDE>
+__device__ __forceinline__ void dense_body(const DenseArgs &a) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y;
-    const int side = blockIdx.z & 1;
     const int f = blockIdx.z >> 1;
-    if (u >= a.W) return;
     const int W = a.W, H = a.H;
     const size_t N = (size_t)W * H;
-    const size_t pix = (size_t)v * W + u;
-    float *D = a.D[side] + (size_t)f * N;
+    const bool in = u < W;
+    const size_t pix = (size_t)v * W + (in ? u : 0);
+    float *D = a.D[SIDE] + (size_t)f * N;
 
-    float out = -10.f;  // elas.cpp:820-826: pixels nobody writes keep -10
-    const int o = a.owner[side][(size_t)f * N + pix];
-    if (o >= 0 && u >= 2 && u < W - 2) {  // elas.cpp:714
-        const int row = max(min(v, H - 3), 2);  // elas.cpp:718
-        const uint4 *own = reinterpret_cast<const uint4 *>(a.desc[side]) + (size_t)f * N + (size_t)row * W;
-        const uint4 *oth = reinterpret_cast<const uint4 *>(a.desc[side ^ 1]) + (size_t)f * N + (size_t)row * W;
-        const uint4 c = __ldg(own + u);
-        const uint4 k128 = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
-        if ((int)sad16(c, k128) >= a.match_texture) {  // elas.cpp:731-736
-            const PlaneRec pr = a.rec[side][(size_t)f * a.maxT + o];
-            // elas.cpp:739: (a*u + b*v) + c in f32, separate roundings, truncation like cvttss2si
-            const float fp = __fadd_rn(__fadd_rn(__fmul_rn(pr.a, (float)u), __fmul_rn(pr.b, (float)v)), pr.c);
-            const int d_plane = f2i_trunc_x86(fp);
-            const int d_plane_min = max((int)((unsigned)d_plane - (unsigned)a.plane_radius), 0);
-            const int d_plane_max = min((int)((unsigned)d_plane + (unsigned)a.plane_radius), a.disp_max);
+    const int row = max(min(v, H - 3), 2);  // elas.cpp:718
+    const uint4 *own = reinterpret_cast<const uint4 *>(a.desc[SIDE]) + (size_t)f * N + (size_t)row * W;
+    // descriptor of the other image at this pixel's own column; hypothesis d reads po[-d] (left) / po[+d] (right).
+    // Rows are contiguous and 2 <= row <= H-3, so po[+-d] stays inside the frame's descriptor image for every
+    // d <= disp_max even where the warped column leaves the row: loads never need a guard, only the result does.
+    const uint4 *po = reinterpret_cast<const uint4 *>(a.desc[SIDE ^ 1]) + (size_t)f * N + (size_t)row * W + u;
 
-            const int gx = u / a.grid_size, gy = v / a.grid_size;  // u, v >= 0 so this equals the float floor
-            const uint32_t *cell = a.grid[side] + ((size_t)f * a.gw * a.gh + (size_t)gy * a.gw + gx) * a.gwords;
-
-            int min_val = 10000, min_d = -1;
-            // (i) grid candidates outside the band, ascending (elas.cpp:759-767 / 778-786)
-            for (int w = 0; w < a.gwords; w++) {
-                uint32_t bits = __ldg(cell + w);
-                while (bits) {
-                    const int b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const int d = (w << 5) + b;
-                    if (d >= d_plane_min && d <= d_plane_max) continue;
-                    const int uw = side ? u + d : u - d;
-                    if (uw < 2 || uw >= W - 2) continue;
-                    const int val = (int)sad16(c, __ldg(oth + uw));
-                    if (val < min_val) {
-                        min_val = val;
-                        min_d = d;
-                    }
-                }
-            }
-            // (ii) the plane band with the prior (elas.cpp:768-774 / 787-793)
-            for (int d = d_plane_min; d <= d_plane_max; d++) {
-                const int uw = side ? u + d : u - d;
-                if (uw < 2 || uw >= W - 2) continue;
-                const int val = (int)sad16(c, __ldg(oth + uw)) + (pr.valid ? a.P[abs(d - d_plane)] : 0);
-                if (val < min_val) {
-                    min_val = val;
-                    min_d = d;
-                }
-            }
-            out = min_d >= 0 ? (float)min_d : -1.f;  // elas.cpp:797-800
+    bool active = false;
+    uint4 c = make_uint4(0, 0, 0, 0);
+    int o = -1;
+    if (in) {
+        o = a.owner[SIDE][(size_t)f * N + pix];
+        if (o >= 0 && u >= 2 && u < W - 2) {  // elas.cpp:714
+            c = __ldg(own + u);
+            const uint4 k128 = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+            active = (int)sad16(c, k128) >= a.match_texture;  // elas.cpp:731-736
         }
     }
-    D[pix] = out;
+    int d_plane = 0, dmin = 1, dmax = 0;  // empty band for inactive lanes
+    unsigned prior_on = 0u;
+    if (active) {
+        const PlaneRec pr = a.rec[SIDE][(size_t)f * a.maxT + o];
+        // elas.cpp:739: (a*u + b*v) + c in f32, separate roundings, truncation like cvttss2si
+        const float fp = __fadd_rn(__fadd_rn(__fmul_rn(pr.a, (float)u), __fmul_rn(pr.b, (float)v)), pr.c);
+        d_plane = f2i_trunc_x86(fp);
+        dmin = max((int)((unsigned)d_plane - (unsigned)a.plane_radius), 0);
+        dmax = min((int)((unsigned)d_plane + (unsigned)a.plane_radius), a.disp_max);
+        prior_on = pr.valid ? 0xFFFFFFFFu : 0u;
+    }
+    // warped column u -+ d must lie in [2, W-2): an interval of admissible d
+    const int dlo = SIDE ? 2 - u : u - (W - 3);
+    const int dhi = SIDE ? (W - 3) - u : u - 2;
+
+    unsigned key = 0xFFFFFFFFu;
+    // (i) grid candidates outside the band, ascending (elas.cpp:759-767 / 778-786)
+    const int gx = (in ? u : W - 1) / a.grid_size, gy = v / a.grid_size;  // u, v >= 0 so this equals the float floor
+    const uint32_t *cell = a.grid[SIDE] + ((size_t)f * a.gw * a.gh + (size_t)gy * a.gw + gx) * a.gwords;
+    for (int w = 0; w < a.gwords; w++) {
+        uint32_t mine = active ? __ldg(cell + w) : 0u;
+        if (mine) mine &= ~range_mask(dmin, dmax, w << 5) & range_mask(dlo, dhi, w << 5);
+        uint32_t uni = __reduce_or_sync(0xFFFFFFFFu, mine);
+        while (uni) {
+            const uint32_t bit = uni & (0u - uni);  // lowest candidate of the union
+            uni ^= bit;
+            const int d = (w << 5) + (31 - __clz(bit));
+            const unsigned cost = sad16_acc(c, __ldg(desc_at(po, SIDE ? d : -d)), 16u);
+            const unsigned cand = (cost << 13) + (unsigned)d;
+            key = min(key, (mine & bit) ? cand : 0xFFFFFFFFu);
+        }
+    }
+    // (ii) the plane band with the prior (elas.cpp:768-774 / 787-793)
+    const int lo2 = max(dmin, dlo), hi2 = min(dmax, dhi);
+    const unsigned span = hi2 >= lo2 ? (unsigned)(hi2 - lo2) : 0u;
+    const int lo3 = hi2 >= lo2 ? lo2 : 0x40000000;  // empty interval: nothing passes the unsigned range test
+    const int r = a.plane_radius;
+    for (int k = -r; k <= r; k++) {
+        const int d = (int)((unsigned)d_plane + (unsigned)k);
+        const bool ok = (unsigned)(d - lo3) <= span;
+        const int ds = ok ? d : 0;
+        const unsigned seed = 16u + ((unsigned)a.P[k < 0 ? -k : k] & prior_on);
+        const unsigned cost = sad16_acc(c, __ldg(desc_at(po, SIDE ? ds : -ds)), seed);
+        const unsigned cand = (cost << 13) + (0x1000u + (unsigned)ds);
+        key = min(key, ok ? cand : 0xFFFFFFFFu);
+    }
+    if (in) {
+        float out = -10.f;                                                    // elas.cpp:820-826: pixels nobody writes keep -10
+        if (active) out = key != 0xFFFFFFFFu ? (float)(key & 0xFFFu) : -1.f;  // elas.cpp:797-800
+        D[pix] = out;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_dense(const DenseArgs a) {
+    if (blockIdx.z & 1)
+        dense_body<1>(a);
+    else
+        dense_body<0>(a);
 }
 
 }  // namespace

@@ -140,31 +140,105 @@ __global__ void __launch_bounds__(128) k_gap_cols(float *__restrict__ D_all, int
     }
 }
 
+// The same walk on a strip of COLS columns staged in shared memory: the strip is loaded and stored with coalesced row
+// segments by the whole CTA, the COLS walkers then step through shared memory (29-cycle latency instead of an L2
+// round trip per step -- the global-memory walk above is purely latency bound: ncu shows 6 % issue utilisation).
+template <int COLS>
+__global__ void __launch_bounds__(256) k_gap_cols_smem(float *__restrict__ D_all, int W, int H, int gap_width, int add_corners) {
+    extern __shared__ float s_strip[];  // [H][COLS]
+    const int u0 = blockIdx.x * COLS;
+    float *Dimg = D_all + (size_t)blockIdx.y * W * H;
+    const int total = H * COLS;
+    for (int i = threadIdx.x; i < total; i += 256) {
+        const int v = i / COLS, c = i - v * COLS;
+        s_strip[i] = (u0 + c < W) ? Dimg[(size_t)v * W + u0 + c] : -10.f;
+    }
+    __syncthreads();
+    if (threadIdx.x < COLS && u0 + threadIdx.x < W) {
+        float *D = s_strip + threadIdx.x;
+        int count = 0;
+        int first_valid = -1, last_valid = -1;
+        for (int v = 0; v < H; v++) {
+            const float val = D[v * COLS];
+            if (val >= 0.f) {
+                if (count >= 1 && count <= gap_width) {
+                    const int v_first = v - count, v_last = v - 1;
+                    if (v_first > 0 && v_last < H - 1) {
+                        const float fill = gap_fill_value(D[(v_first - 1) * COLS], val);
+                        for (int vc = v_first; vc <= v_last; vc++) D[vc * COLS] = fill;
+                    }
+                }
+                count = 0;
+                if (first_valid < 0) first_valid = v;
+                last_valid = v;
+            } else {
+                count++;
+            }
+        }
+        if (add_corners && first_valid >= 0) {
+            const float top = D[first_valid * COLS];
+            for (int v2 = max(first_valid - gap_width, 0); v2 < first_valid; v2++) D[v2 * COLS] = top;
+            const float bot = D[last_valid * COLS];
+            for (int v2 = last_valid + 1; v2 <= min(last_valid + gap_width, H - 1); v2++) D[v2 * COLS] = bot;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += 256) {
+        const int v = i / COLS, c = i - v * COLS;
+        if (u0 + c < W) Dimg[(size_t)v * W + u0 + c] = s_strip[i];
+    }
+}
+
+template <int COLS>
+int launch_gap_cols_smem(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s) {
+    const size_t smem = (size_t)d.H * COLS * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_gap_cols_smem<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(k_gap_cols_smem): %s", cudaGetErrorString(e));
+            return SVB_ERR_CUDA;
+        }
+    }
+    dim3 grid((d.W + COLS - 1) / COLS, nimg);
+    k_gap_cols_smem<COLS><<<grid, 256, smem, s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners);
+    SVB_LAUNCH_CHECK();
+    return SVB_OK;
+}
+
 // ---- adaptive mean ----------------------------------------------------------------------------------
 // 8-tap horizontal then 8-tap vertical weighted mean (elas.cpp:1401-1485).  Tap coordinates of a centre c are
 // c-4 .. c+3.  The reference keeps the window in a ring buffer indexed by (coordinate mod 8) and sums the SSE
-// lanes as ((s0+s1)+s2)+s3 with s_k = term(slot k) + term(slot k+4); the same association is used here.
+// lanes as ((s0+s1)+s2)+s3 with s_k = term(slot k) + term(slot k+4): taps whose coordinates are congruent mod 4
+// are added first, then the four pair sums in the order of (coordinate mod 4).  A thread produces FOUR consecutive
+// centres c0 .. c0+3 with c0 a multiple of 4, so that every tap's residue is known at compile time (no dynamic
+// indexing) and the 11 loaded values are shared by the four windows.  Both passes are integer/FP32-ALU bound, not
+// memory bound (ncu: ALU pipe 73-81 %), which is why instruction count per pixel is what is optimised here.
 // mode 0: weight = max(0, 4 - float_and(x - xc, 0x4F000000))   (the serial reference's bit-mask "abs")
 // mode 1: weight = max(0, 4 - |x - xc|)                         (the parallel reference)
-__device__ __forceinline__ float mean_weight(float x, float xc, int mode) {
+template <int MODE>
+__device__ __forceinline__ float mean_weight(float x, float xc) {
     const float diff = __fsub_rn(x, xc);
-    const float m = mode ? fabsf(diff) : __int_as_float(__float_as_int(diff) & 0x4F000000);
+    const float m = MODE ? fabsf(diff) : __int_as_float(__float_as_int(diff) & 0x4F000000);
     return fmaxf(0.f, __fsub_rn(4.f, m));
 }
 
-// window[k] = value at coordinate base+k, k = 0..7 (base = centre-4).  Returns true and *out if the pixel is written.
-__device__ __forceinline__ bool mean8(const float window[8], int base, int mode, float *out) {
-    const float xc = window[4];
+// x[0..10] = values at coordinates c0-4 .. c0+6 (c0 % 4 == 0); J = which of the four centres (c = c0 + J).
+// Returns true and *out if the reference writes the pixel.
+template <int MODE, int J>
+__device__ __forceinline__ bool mean8(const float (&x)[11], float *out) {
+    const float xc = x[J + 4];
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = mean_weight<MODE>(x[J + i], xc);
     float wsum[4], fsum[4];
 #pragma unroll
-    for (int s = 0; s < 4; s++) {
-        // slot s holds the coordinate congruent to s (mod 8), slot s+4 the one 4 further
-        const int k0 = (s - base) & 7;
-        const int k1 = (k0 + 4) & 7;
-        const float x0 = window[k0], x1 = window[k1];
-        const float w0 = mean_weight(x0, xc, mode), w1 = mean_weight(x1, xc, mode);
-        wsum[s] = __fadd_rn(w0, w1);
-        fsum[s] = __fadd_rn(__fmul_rn(x0, w0), __fmul_rn(x1, w1));
+    for (int p = 0; p < 4; p++) {
+        // window element i sits at coordinate c0 - 4 + J + i, i.e. residue (J + i) mod 4: pair p = {i0, i0 + 4}
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int i0 = (p - J) & 3;
+        wsum[p] = __fadd_rn(w[i0], w[i0 + 4]);
+        fsum[p] = __fadd_rn(__fmul_rn(x[J + i0], w[i0]), __fmul_rn(x[J + i0 + 4], w[i0 + 4]));
     }
     const float weight_sum = __fadd_rn(__fadd_rn(__fadd_rn(wsum[0], wsum[1]), wsum[2]), wsum[3]);
     const float factor_sum = __fadd_rn(__fadd_rn(__fadd_rn(fsum[0], fsum[1]), fsum[2]), fsum[3]);
@@ -180,91 +254,118 @@ __device__ __forceinline__ bool mean8(const float window[8], int base, int mode,
 
 // Horizontal pass: tmp = (D < 0 ? -10 : 0) overwritten by the filtered value where the reference writes D_tmp.
 // (D_tmp is malloc'ed and only partly written in the reference; unwritten valid pixels are DEFINED as 0,
-// SURVEY.md finding 5.)  grid: (ceil(W/256), H, nimg)
-__global__ void __launch_bounds__(256) k_mean_h(const float *__restrict__ D_all, float *__restrict__ tmp_all, int W, int H, int mode) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= W) return;
+// SURVEY.md finding 5.)  grid: (ceil(ceil(W/4)/128), H, nimg); a thread owns columns c0 .. c0+3
+template <int MODE>
+__global__ void __launch_bounds__(128) k_mean_h(const float *__restrict__ D_all, float *__restrict__ tmp_all, int W, int H) {
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c0 >= W) return;
     const int v = blockIdx.y;
     const size_t base = ((size_t)blockIdx.z * H + v) * W;
     const float *row = D_all + base;
-    const float own = row[c];
-    float out = own < 0.f ? -10.f : 0.f;
-    if (v >= 3 && v < H - 3 && c >= 4 && c <= W - 4) {
-        float win[8];
+    float x[11];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const float x = row[c - 4 + k];
-            win[k] = x < 0.f ? -10.f : x;  // D_copy (elas.cpp:1313-1316)
-        }
-        float r;
-        if (mean8(win, c - 4, mode, &r)) out = r;
+    for (int k = 0; k < 11; k++) {
+        const int cc = c0 - 4 + k;
+        const float val = (cc >= 0 && cc < W) ? row[cc] : -10.f;
+        x[k] = val < 0.f ? -10.f : val;  // D_copy (elas.cpp:1313-1316)
     }
-    tmp_all[base + c] = out;
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[j] = x[j + 4] < 0.f ? -10.f : 0.f;
+    if (v >= 3 && v < H - 3) {
+        float r;
+        if (c0 + 0 >= 4 && c0 + 0 <= W - 4 && mean8<MODE, 0>(x, &r)) out[0] = r;
+        if (c0 + 1 >= 4 && c0 + 1 <= W - 4 && mean8<MODE, 1>(x, &r)) out[1] = r;
+        if (c0 + 2 >= 4 && c0 + 2 <= W - 4 && mean8<MODE, 2>(x, &r)) out[2] = r;
+        if (c0 + 3 >= 4 && c0 + 3 <= W - 4 && mean8<MODE, 3>(x, &r)) out[3] = r;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (c0 + j < W) tmp_all[base + c0 + j] = out[j];
 }
 
-// Vertical pass on tmp, writing D in place.  grid: (ceil(W/256), H, nimg)
-__global__ void __launch_bounds__(256) k_mean_v(const float *__restrict__ tmp_all, float *__restrict__ D_all, int W, int H, int mode) {
+// Vertical pass on tmp, writing D in place.  grid: (ceil(W/128), ceil(H/4), nimg); a thread owns rows r0 .. r0+3 of a column
+template <int MODE>
+__global__ void __launch_bounds__(128) k_mean_v(const float *__restrict__ tmp_all, float *__restrict__ D_all, int W, int H) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= W) return;
-    const int c = blockIdx.y;  // centre row
-    if (!(u >= 3 && u < W - 3 && c >= 4 && c <= H - 4)) return;
+    if (u < 3 || u >= W - 3) return;
+    const int r0 = blockIdx.y * 4;
     const size_t img = (size_t)blockIdx.z * H * W;
-    float win[8];
+    float x[11];
 #pragma unroll
-    for (int k = 0; k < 8; k++) win[k] = tmp_all[img + (size_t)(c - 4 + k) * W + u];
+    for (int k = 0; k < 11; k++) {
+        const int rr = r0 - 4 + k;
+        x[k] = (rr >= 0 && rr < H) ? tmp_all[img + (size_t)rr * W + u] : -10.f;
+    }
     float r;
-    if (mean8(win, c - 4, mode, &r)) D_all[img + (size_t)c * W + u] = r;
+    if (r0 + 0 >= 4 && r0 + 0 <= H - 4 && mean8<MODE, 0>(x, &r)) D_all[img + (size_t)(r0 + 0) * W + u] = r;
+    if (r0 + 1 >= 4 && r0 + 1 <= H - 4 && mean8<MODE, 1>(x, &r)) D_all[img + (size_t)(r0 + 1) * W + u] = r;
+    if (r0 + 2 >= 4 && r0 + 2 <= H - 4 && mean8<MODE, 2>(x, &r)) D_all[img + (size_t)(r0 + 2) * W + u] = r;
+    if (r0 + 3 >= 4 && r0 + 3 <= H - 4 && mean8<MODE, 3>(x, &r)) D_all[img + (size_t)(r0 + 3) * W + u] = r;
 }
 
 // ---- median -------------------------------------------------------------------------------------------
-__device__ __forceinline__ float median7(float a[7]) {
-    // insertion sort exactly as elas.cpp:1519-1528 (selection only, so any correct sort gives the same value)
-#pragma unroll
-    for (int j = 1; j < 7; j++) {
-        const float t = a[j];
-        int i = j - 1;
-        while (i >= 0 && a[i] > t) {
-            a[i + 1] = a[i];
-            i--;
-        }
-        a[i + 1] = t;
-    }
-    return a[3];
+// Median of 7 by a 13-exchange selection network (the reference sorts with an insertion sort, elas.cpp:1519-1528;
+// the median is a selection, so any correct method gives the same value; the inputs are never NaN).
+__device__ __forceinline__ void cswap(float &a, float &b) {
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = lo;
+    b = hi;
+}
+__device__ __forceinline__ float median7(float p0, float p1, float p2, float p3, float p4, float p5, float p6) {
+    cswap(p0, p5); cswap(p0, p3); cswap(p1, p6); cswap(p2, p4); cswap(p0, p1); cswap(p3, p5); cswap(p2, p6);
+    cswap(p2, p3); cswap(p3, p6); cswap(p4, p5); cswap(p1, p4); cswap(p1, p3); cswap(p3, p4);
+    return p3;
 }
 
-// D_temp is calloc'ed (elas.cpp:1506): 0 outside [3,W-3)x[3,H-3).  grid: (ceil(W/256), H, nimg)
-__global__ void __launch_bounds__(256) k_median_h(const float *__restrict__ D_all, float *__restrict__ tmp_all, int W, int H) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= W) return;
+// D_temp is calloc'ed (elas.cpp:1506): 0 outside [3,W-3)x[3,H-3).  A thread owns 4 consecutive columns.
+// grid: (ceil(ceil(W/4)/128), H, nimg)
+__global__ void __launch_bounds__(128) k_median_h(const float *__restrict__ D_all, float *__restrict__ tmp_all, int W, int H) {
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c0 >= W) return;
     const int v = blockIdx.y;
     const size_t base = ((size_t)blockIdx.z * H + v) * W;
-    float out = 0.f;
-    if (u >= 3 && u < W - 3 && v >= 3 && v < H - 3) {
-        const float own = D_all[base + u];
-        if (own >= 0.f) {
-            float a[7];
+    float out[4] = {0.f, 0.f, 0.f, 0.f};
+    if (v >= 3 && v < H - 3) {
+        float x[10];
 #pragma unroll
-            for (int k = 0; k < 7; k++) a[k] = D_all[base + u - 3 + k];
-            out = median7(a);
-        } else {
-            out = own;
+        for (int k = 0; k < 10; k++) {
+            const int cc = c0 - 3 + k;
+            x[k] = (cc >= 0 && cc < W) ? D_all[base + cc] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int u = c0 + j;
+            if (u >= 3 && u < W - 3) {
+                const float own = x[j + 3];
+                out[j] = own >= 0.f ? median7(x[j], x[j + 1], x[j + 2], x[j + 3], x[j + 4], x[j + 5], x[j + 6]) : own;
+            }
         }
     }
-    tmp_all[base + u] = out;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (c0 + j < W) tmp_all[base + c0 + j] = out[j];
 }
 
-__global__ void __launch_bounds__(256) k_median_v(const float *__restrict__ tmp_all, float *__restrict__ D_all, int W, int H) {
+// grid: (ceil(W/128), ceil(H/4), nimg); a thread owns rows r0 .. r0+3 of a column
+__global__ void __launch_bounds__(128) k_median_v(const float *__restrict__ tmp_all, float *__restrict__ D_all, int W, int H) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= W) return;
-    const int v = blockIdx.y;
-    if (!(u >= 3 && u < W - 3 && v >= 3 && v < H - 3)) return;
+    if (u < 3 || u >= W - 3) return;
+    const int r0 = blockIdx.y * 4;
     const size_t img = (size_t)blockIdx.z * H * W;
-    const size_t idx = img + (size_t)v * W + u;
-    if (D_all[idx] >= 0.f) {
-        float a[7];
+    float x[10];
 #pragma unroll
-        for (int k = 0; k < 7; k++) a[k] = tmp_all[img + (size_t)(v - 3 + k) * W + u];
-        D_all[idx] = median7(a);
+    for (int k = 0; k < 10; k++) {
+        const int rr = r0 - 3 + k;
+        x[k] = (rr >= 0 && rr < H) ? tmp_all[img + (size_t)rr * W + u] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int v = r0 + j;
+        if (v >= 3 && v < H - 3) {
+            const size_t idx = img + (size_t)v * W + u;
+            if (D_all[idx] >= 0.f) D_all[idx] = median7(x[j], x[j + 1], x[j + 2], x[j + 3], x[j + 4], x[j + 5], x[j + 6]);
+        }
     }
 }
 
@@ -287,6 +388,10 @@ int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStrea
         k_gap_rows<<<grid, GAP_WARPS * 32, (size_t)GAP_WARPS * Wpad * sizeof(int), s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners, Wpad);
         SVB_LAUNCH_CHECK();
     }
+    const size_t budget = 200 * 1024;
+    if ((size_t)d.H * 32 * sizeof(float) <= budget) return launch_gap_cols_smem<32>(d, p, D, nimg, s);
+    if ((size_t)d.H * 16 * sizeof(float) <= budget) return launch_gap_cols_smem<16>(d, p, D, nimg, s);
+    if ((size_t)d.H * 8 * sizeof(float) <= budget) return launch_gap_cols_smem<8>(d, p, D, nimg, s);
     {
         dim3 grid((d.W + 127) / 128, nimg);
         k_gap_cols<<<grid, 128, 0, s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners);
@@ -297,20 +402,29 @@ int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStrea
 
 int launch_adaptive_mean(const Dims &d, int mean_mode, float *D, float *tmp, int nimg, cudaStream_t s) {
     if (nimg <= 0) return SVB_OK;
-    dim3 grid((d.W + 255) / 256, d.H, nimg);
-    k_mean_h<<<grid, 256, 0, s>>>(D, tmp, d.W, d.H, mean_mode);
-    SVB_LAUNCH_CHECK();
-    k_mean_v<<<grid, 256, 0, s>>>(tmp, D, d.W, d.H, mean_mode);
-    SVB_LAUNCH_CHECK();
+    const dim3 gh(((d.W + 3) / 4 + 127) / 128, d.H, nimg);
+    const dim3 gv((d.W + 127) / 128, (d.H + 3) / 4, nimg);
+    if (mean_mode == SVB_MEAN_TRUE_ABS) {
+        k_mean_h<1><<<gh, 128, 0, s>>>(D, tmp, d.W, d.H);
+        SVB_LAUNCH_CHECK();
+        k_mean_v<1><<<gv, 128, 0, s>>>(tmp, D, d.W, d.H);
+        SVB_LAUNCH_CHECK();
+    } else {
+        k_mean_h<0><<<gh, 128, 0, s>>>(D, tmp, d.W, d.H);
+        SVB_LAUNCH_CHECK();
+        k_mean_v<0><<<gv, 128, 0, s>>>(tmp, D, d.W, d.H);
+        SVB_LAUNCH_CHECK();
+    }
     return SVB_OK;
 }
 
 int launch_median(const Dims &d, float *D, float *tmp, int nimg, cudaStream_t s) {
     if (nimg <= 0) return SVB_OK;
-    dim3 grid((d.W + 255) / 256, d.H, nimg);
-    k_median_h<<<grid, 256, 0, s>>>(D, tmp, d.W, d.H);
+    const dim3 gh(((d.W + 3) / 4 + 127) / 128, d.H, nimg);
+    const dim3 gv((d.W + 127) / 128, (d.H + 3) / 4, nimg);
+    k_median_h<<<gh, 128, 0, s>>>(D, tmp, d.W, d.H);
     SVB_LAUNCH_CHECK();
-    k_median_v<<<grid, 256, 0, s>>>(tmp, D, d.W, d.H);
+    k_median_v<<<gv, 128, 0, s>>>(tmp, D, d.W, d.H);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }
