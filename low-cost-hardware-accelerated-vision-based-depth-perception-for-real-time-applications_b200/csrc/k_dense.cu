@@ -26,6 +26,7 @@ struct DenseArgs {
     const uint32_t *grid[2];
     float *D[2];
     int W, H, maxT, gw, gh, gwords, grid_size, disp_max, match_texture, plane_radius;
+    unsigned grid_magic;  // ceil(2^32 / grid_size)
     int P[8];
 };
 
@@ -64,7 +65,9 @@ __device__ __forceinline__ uint32_t range_mask(int lo, int hi, int base) {
 //   smaller cost wins; on equal cost the grid phase (0) beats the band phase (1) and, inside a phase, the smaller d
 //   wins -- exactly "first evaluated wins" of the reference's strict `<` over its evaluation order
 //   (elas.cpp:757-794: grid candidates ascending, then the band ascending).  min_val starts at 10000 > any cost.
-template <int SIDE>
+// RADIUS > 0: plane radius known at compile time (the band loop is fully unrolled and all of its loads are issued up
+// front); RADIUS == 0: generic radius from the arguments.
+template <int SIDE, int RADIUS>
 __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y;
@@ -110,34 +113,70 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
 
     unsigned key = 0xFFFFFFFFu;
     // (i) grid candidates outside the band, ascending (elas.cpp:759-767 / 778-786)
-    const int gx = (in ? u : W - 1) / a.grid_size, gy = v / a.grid_size;  // u, v >= 0 so this equals the float floor
+    // u / grid_size by a host-computed reciprocal (exact for u < 2^16: u * (magic * g - 2^32) < 2^32)
+    const int uc = in ? u : W - 1;
+    const int gx = a.grid_size == 1 ? uc : (int)__umulhi((unsigned)uc, a.grid_magic), gy = v / a.grid_size;  // u, v >= 0: equals the float floor
     const uint32_t *cell = a.grid[SIDE] + ((size_t)f * a.gw * a.gh + (size_t)gy * a.gw + gx) * a.gwords;
-    for (int w = 0; w < a.gwords; w++) {
-        uint32_t mine = active ? __ldg(cell + w) : 0u;
-        if (mine) mine &= ~range_mask(dmin, dmax, w << 5) & range_mask(dlo, dhi, w << 5);
-        uint32_t uni = __reduce_or_sync(0xFFFFFFFFu, mine);
-        while (uni) {
-            const uint32_t bit = uni & (0u - uni);  // lowest candidate of the union
-            uni ^= bit;
-            const int d = (w << 5) + (31 - __clz(bit));
-            const unsigned cost = sad16_acc(c, __ldg(desc_at(po, SIDE ? d : -d)), 16u);
-            const unsigned cand = (cost << 13) + (unsigned)d;
-            key = min(key, (mine & bit) ? cand : 0xFFFFFFFFu);
+    // gwords is a multiple of 4 (make_dims): a cell is read as 16-byte vectors, and a group of four words (128
+    // disparities) without any candidate in the whole warp is skipped with one vote
+    for (int w4 = 0; w4 < a.gwords; w4 += 4) {
+        const uint4 m4 = active ? __ldg(reinterpret_cast<const uint4 *>(cell + w4)) : make_uint4(0, 0, 0, 0);
+        if (!__any_sync(0xFFFFFFFFu, (m4.x | m4.y | m4.z | m4.w) != 0u)) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int w = w4 + j;
+            uint32_t mine = j == 0 ? m4.x : j == 1 ? m4.y : j == 2 ? m4.z : m4.w;
+            if (mine) mine &= ~range_mask(dmin, dmax, w << 5) & range_mask(dlo, dhi, w << 5);
+            uint32_t uni = __reduce_or_sync(0xFFFFFFFFu, mine);
+            while (uni) {
+                // two candidates per trip: both loads are in flight before either SAD chain starts
+                const uint32_t bit0 = uni & (0u - uni);  // lowest candidate of the union
+                uni ^= bit0;
+                const uint32_t bit1 = uni & (0u - uni);  // next one (0 if there is none: it then re-evaluates bit0's d, masked out)
+                uni ^= bit1;
+                const int d0 = (w << 5) + (31 - __clz(bit0));
+                const int d1 = bit1 ? (w << 5) + (31 - __clz(bit1)) : d0;
+                const uint4 o0 = __ldg(desc_at(po, SIDE ? d0 : -d0));
+                const uint4 o1 = __ldg(desc_at(po, SIDE ? d1 : -d1));
+                const unsigned cand0 = (sad16_acc(c, o0, 16u) << 13) + (unsigned)d0;
+                const unsigned cand1 = (sad16_acc(c, o1, 16u) << 13) + (unsigned)d1;
+                key = min(key, (mine & bit0) ? cand0 : 0xFFFFFFFFu);
+                key = min(key, (mine & bit1) ? cand1 : 0xFFFFFFFFu);
+            }
         }
     }
     // (ii) the plane band with the prior (elas.cpp:768-774 / 787-793)
     const int lo2 = max(dmin, dlo), hi2 = min(dmax, dhi);
     const unsigned span = hi2 >= lo2 ? (unsigned)(hi2 - lo2) : 0u;
     const int lo3 = hi2 >= lo2 ? lo2 : 0x40000000;  // empty interval: nothing passes the unsigned range test
-    const int r = a.plane_radius;
-    for (int k = -r; k <= r; k++) {
-        const int d = (int)((unsigned)d_plane + (unsigned)k);
-        const bool ok = (unsigned)(d - lo3) <= span;
-        const int ds = ok ? d : 0;
-        const unsigned seed = 16u + ((unsigned)a.P[k < 0 ? -k : k] & prior_on);
-        const unsigned cost = sad16_acc(c, __ldg(desc_at(po, SIDE ? ds : -ds)), seed);
-        const unsigned cand = (cost << 13) + (0x1000u + (unsigned)ds);
-        key = min(key, ok ? cand : 0xFFFFFFFFu);
+    if (RADIUS > 0) {
+        uint4 ob[2 * RADIUS + 1];
+        bool okb[2 * RADIUS + 1];
+        int dsb[2 * RADIUS + 1];
+#pragma unroll
+        for (int k = -RADIUS; k <= RADIUS; k++) {
+            const int d = (int)((unsigned)d_plane + (unsigned)k);
+            okb[k + RADIUS] = (unsigned)(d - lo3) <= span;
+            dsb[k + RADIUS] = okb[k + RADIUS] ? d : 0;
+            ob[k + RADIUS] = __ldg(desc_at(po, SIDE ? dsb[k + RADIUS] : -dsb[k + RADIUS]));
+        }
+#pragma unroll
+        for (int k = -RADIUS; k <= RADIUS; k++) {
+            const unsigned seed = 16u + ((unsigned)a.P[k < 0 ? -k : k] & prior_on);
+            const unsigned cand = (sad16_acc(c, ob[k + RADIUS], seed) << 13) + (0x1000u + (unsigned)dsb[k + RADIUS]);
+            key = min(key, okb[k + RADIUS] ? cand : 0xFFFFFFFFu);
+        }
+    } else {
+        const int r = a.plane_radius;
+        for (int k = -r; k <= r; k++) {
+            const int d = (int)((unsigned)d_plane + (unsigned)k);
+            const bool ok = (unsigned)(d - lo3) <= span;
+            const int ds = ok ? d : 0;
+            const unsigned seed = 16u + ((unsigned)a.P[k < 0 ? -k : k] & prior_on);
+            const unsigned cost = sad16_acc(c, __ldg(desc_at(po, SIDE ? ds : -ds)), seed);
+            const unsigned cand = (cost << 13) + (0x1000u + (unsigned)ds);
+            key = min(key, ok ? cand : 0xFFFFFFFFu);
+        }
     }
     if (in) {
         float out = -10.f;                                                    // elas.cpp:820-826: pixels nobody writes keep -10
@@ -146,11 +185,12 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     }
 }
 
+template <int RADIUS>
 __global__ void __launch_bounds__(128) k_dense(const DenseArgs a) {
     if (blockIdx.z & 1)
-        dense_body<1>(a);
+        dense_body<1, RADIUS>(a);
     else
-        dense_body<0>(a);
+        dense_body<0, RADIUS>(a);
 }
 
 }  // namespace
@@ -177,12 +217,18 @@ int launch_dense(const Dims &d, const svb_params &p, const uint8_t *desc1, const
     a.gh = d.gh;
     a.gwords = d.gwords;
     a.grid_size = p.grid_size;
+    a.grid_magic = p.grid_size > 1 ? (unsigned)((0x100000000ull + p.grid_size - 1) / p.grid_size) : 0u;
     a.disp_max = p.disp_max;
     a.match_texture = p.match_texture;
     a.plane_radius = d.plane_radius;
     for (int i = 0; i < 8; i++) a.P[i] = d.P[i];
     dim3 grid((d.W + 127) / 128, d.H, nf * 2);
-    k_dense<<<grid, 128, 0, s>>>(a);
+    if (d.plane_radius == 2)
+        k_dense<2><<<grid, 128, 0, s>>>(a);
+    else if (d.plane_radius == 3)
+        k_dense<3><<<grid, 128, 0, s>>>(a);
+    else
+        k_dense<0><<<grid, 128, 0, s>>>(a);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

@@ -48,59 +48,92 @@ __device__ __forceinline__ float gap_fill_value(float d1, float d2) {
     return d2 < d1 ? d2 : d1;  // std::min(d1, d2)
 }
 
+// One line (a row in global memory, or a column of a shared-memory strip) handled by one warp: `line[i * stride]`,
+// i = 0 .. n-1; prev = n ints of scratch.
+__device__ __forceinline__ void gap_line(float *line, int stride, int n, int *prev, int lane, int gap_width, int add_corners) {
+    int carry = -1;
+    const int chunks = (n + 31) / 32;
+    for (int k = 0; k < chunks; k++) {
+        const int u = k * 32 + lane;
+        const bool valid = (u < n) && (line[u * stride] >= 0.f);
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid);
+        const unsigned below = bal & ((1u << lane) - 1u);
+        if (u < n) prev[u] = below ? (k * 32 + 31 - __clz(below)) : carry;
+        if (bal) carry = k * 32 + 31 - __clz(bal);
+    }
+    __syncwarp();
+    int ncarry = -1;  // next valid position beyond the current chunk
+    for (int k = chunks - 1; k >= 0; k--) {
+        const int u = k * 32 + lane;
+        const float val = (u < n) ? line[u * stride] : -1.f;
+        const bool valid = (u < n) && (val >= 0.f);
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid);
+        const unsigned above = (lane == 31) ? 0u : (bal & ~((2u << lane) - 1u));
+        const int nx = above ? (k * 32 + __ffs(above) - 1) : ncarry;
+        if (u < n && !valid) {
+            const int p = prev[u];
+            float fill = 0.f;
+            bool do_fill = false;
+            if (p >= 0 && nx >= 0) {
+                if (nx - p - 1 <= gap_width) {
+                    fill = gap_fill_value(line[p * stride], line[nx * stride]);
+                    do_fill = true;
+                }
+            } else if (add_corners && p < 0 && nx >= 0) {
+                if (nx - u <= gap_width) {
+                    fill = line[nx * stride];
+                    do_fill = true;
+                }
+            } else if (add_corners && p >= 0 && nx < 0) {
+                if (u - p <= gap_width) {
+                    fill = line[p * stride];
+                    do_fill = true;
+                }
+            }
+            // values at p and nx are valid pixels, which this pass never modifies: reading them while other
+            // lanes write invalid positions is race free
+            if (do_fill) line[u * stride] = fill;
+        }
+        if (bal) ncarry = k * 32 + __ffs(bal) - 1;
+    }
+}
+
 // grid: (ceil(H/GAP_WARPS), nimg); dynamic smem: GAP_WARPS * Wpad int32
 __global__ void __launch_bounds__(GAP_WARPS * 32) k_gap_rows(float *__restrict__ D_all, int W, int H, int gap_width, int add_corners, int Wpad) {
     extern __shared__ int s_prev[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int v = blockIdx.x * GAP_WARPS + wid;
     if (v >= H) return;
-    float *row = D_all + ((size_t)blockIdx.y * H + v) * W;
-    int *prev = s_prev + wid * Wpad;
+    gap_line(D_all + ((size_t)blockIdx.y * H + v) * W, 1, W, s_prev + wid * Wpad, lane, gap_width, add_corners);
+}
 
-    int carry = -1;
-    const int chunks = (W + 31) / 32;
-    for (int k = 0; k < chunks; k++) {
-        const int u = k * 32 + lane;
-        const bool valid = (u < W) && (row[u] >= 0.f);
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid);
-        const unsigned below = bal & ((1u << lane) - 1u);
-        if (u < W) prev[u] = below ? (k * 32 + 31 - __clz(below)) : carry;
-        if (bal) carry = k * 32 + 31 - __clz(bal);
+// Column pass with the same warp-parallel line algorithm: a CTA stages a strip of GC_COLS columns in shared memory
+// (row stride GC_COLS + 1, so that a warp reading 32 consecutive ROWS of one column hits 32 different banks), each of
+// its warps handles GC_COLS / GC_WARPS columns, and the strip is written back.  Every invalid pixel only depends on
+// the nearest valid pixels above and below in the state BEFORE the pass (fills never create a boundary for another
+// gap, elas.cpp:1220-1293), so the sequential walk and this formulation agree exactly.
+constexpr int GC_COLS = 16;
+constexpr int GC_WARPS = 8;
+
+__global__ void __launch_bounds__(GC_WARPS * 32) k_gap_cols_strip(float *__restrict__ D_all, int W, int H, int gap_width, int add_corners,
+                                                                  int Hpad) {
+    extern __shared__ float s_gc[];  // [H][GC_COLS + 1] floats, then GC_WARPS * Hpad ints
+    float *strip = s_gc;
+    int *prev_all = reinterpret_cast<int *>(s_gc + (size_t)H * (GC_COLS + 1));
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int u0 = blockIdx.x * GC_COLS;
+    float *Dimg = D_all + (size_t)blockIdx.y * W * H;
+    for (int i = threadIdx.x; i < H * GC_COLS; i += GC_WARPS * 32) {
+        const int v = i / GC_COLS, c = i - v * GC_COLS;
+        strip[v * (GC_COLS + 1) + c] = (u0 + c < W) ? Dimg[(size_t)v * W + u0 + c] : -10.f;
     }
-    __syncwarp();
-    int ncarry = -1;  // next valid column to the right of the current chunk
-    for (int k = chunks - 1; k >= 0; k--) {
-        const int u = k * 32 + lane;
-        const float val = (u < W) ? row[u] : -1.f;
-        const bool valid = (u < W) && (val >= 0.f);
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid);
-        const unsigned above = (lane == 31) ? 0u : (bal & ~((2u << lane) - 1u));
-        const int n = above ? (k * 32 + __ffs(above) - 1) : ncarry;
-        if (u < W && !valid) {
-            const int p = prev[u];
-            float fill = 0.f;
-            bool do_fill = false;
-            if (p >= 0 && n >= 0) {
-                if (n - p - 1 <= gap_width) {
-                    fill = gap_fill_value(row[p], row[n]);
-                    do_fill = true;
-                }
-            } else if (add_corners && p < 0 && n >= 0) {
-                if (n - u <= gap_width) {
-                    fill = row[n];
-                    do_fill = true;
-                }
-            } else if (add_corners && p >= 0 && n < 0) {
-                if (u - p <= gap_width) {
-                    fill = row[p];
-                    do_fill = true;
-                }
-            }
-            // values at p and n are valid pixels, which this pass never modifies: reading them while other
-            // lanes write invalid positions is race free
-            if (do_fill) row[u] = fill;
-        }
-        if (bal) ncarry = k * 32 + __ffs(bal) - 1;
+    __syncthreads();
+    for (int c = wid; c < GC_COLS; c += GC_WARPS)
+        if (u0 + c < W) gap_line(strip + c, GC_COLS + 1, H, prev_all + wid * Hpad, lane, gap_width, add_corners);
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * GC_COLS; i += GC_WARPS * 32) {
+        const int v = i / GC_COLS, c = i - v * GC_COLS;
+        if (u0 + c < W) Dimg[(size_t)v * W + u0 + c] = strip[v * (GC_COLS + 1) + c];
     }
 }
 
@@ -138,71 +171,6 @@ __global__ void __launch_bounds__(128) k_gap_cols(float *__restrict__ D_all, int
         const float bot = D[(size_t)last_valid * W];
         for (int v2 = last_valid + 1; v2 <= min(last_valid + gap_width, H - 1); v2++) D[(size_t)v2 * W] = bot;
     }
-}
-
-// The same walk on a strip of COLS columns staged in shared memory: the strip is loaded and stored with coalesced row
-// segments by the whole CTA, the COLS walkers then step through shared memory (29-cycle latency instead of an L2
-// round trip per step -- the global-memory walk above is purely latency bound: ncu shows 6 % issue utilisation).
-template <int COLS>
-__global__ void __launch_bounds__(256) k_gap_cols_smem(float *__restrict__ D_all, int W, int H, int gap_width, int add_corners) {
-    extern __shared__ float s_strip[];  // [H][COLS]
-    const int u0 = blockIdx.x * COLS;
-    float *Dimg = D_all + (size_t)blockIdx.y * W * H;
-    const int total = H * COLS;
-    for (int i = threadIdx.x; i < total; i += 256) {
-        const int v = i / COLS, c = i - v * COLS;
-        s_strip[i] = (u0 + c < W) ? Dimg[(size_t)v * W + u0 + c] : -10.f;
-    }
-    __syncthreads();
-    if (threadIdx.x < COLS && u0 + threadIdx.x < W) {
-        float *D = s_strip + threadIdx.x;
-        int count = 0;
-        int first_valid = -1, last_valid = -1;
-        for (int v = 0; v < H; v++) {
-            const float val = D[v * COLS];
-            if (val >= 0.f) {
-                if (count >= 1 && count <= gap_width) {
-                    const int v_first = v - count, v_last = v - 1;
-                    if (v_first > 0 && v_last < H - 1) {
-                        const float fill = gap_fill_value(D[(v_first - 1) * COLS], val);
-                        for (int vc = v_first; vc <= v_last; vc++) D[vc * COLS] = fill;
-                    }
-                }
-                count = 0;
-                if (first_valid < 0) first_valid = v;
-                last_valid = v;
-            } else {
-                count++;
-            }
-        }
-        if (add_corners && first_valid >= 0) {
-            const float top = D[first_valid * COLS];
-            for (int v2 = max(first_valid - gap_width, 0); v2 < first_valid; v2++) D[v2 * COLS] = top;
-            const float bot = D[last_valid * COLS];
-            for (int v2 = last_valid + 1; v2 <= min(last_valid + gap_width, H - 1); v2++) D[v2 * COLS] = bot;
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < total; i += 256) {
-        const int v = i / COLS, c = i - v * COLS;
-        if (u0 + c < W) Dimg[(size_t)v * W + u0 + c] = s_strip[i];
-    }
-}
-
-template <int COLS>
-int launch_gap_cols_smem(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s) {
-    const size_t smem = (size_t)d.H * COLS * sizeof(float);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_gap_cols_smem<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(k_gap_cols_smem): %s", cudaGetErrorString(e));
-            return SVB_ERR_CUDA;
-        }
-    }
-    dim3 grid((d.W + COLS - 1) / COLS, nimg);
-    k_gap_cols_smem<COLS><<<grid, 256, smem, s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners);
-    SVB_LAUNCH_CHECK();
-    return SVB_OK;
 }
 
 // ---- adaptive mean ----------------------------------------------------------------------------------
@@ -388,10 +356,21 @@ int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStrea
         k_gap_rows<<<grid, GAP_WARPS * 32, (size_t)GAP_WARPS * Wpad * sizeof(int), s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners, Wpad);
         SVB_LAUNCH_CHECK();
     }
-    const size_t budget = 200 * 1024;
-    if ((size_t)d.H * 32 * sizeof(float) <= budget) return launch_gap_cols_smem<32>(d, p, D, nimg, s);
-    if ((size_t)d.H * 16 * sizeof(float) <= budget) return launch_gap_cols_smem<16>(d, p, D, nimg, s);
-    if ((size_t)d.H * 8 * sizeof(float) <= budget) return launch_gap_cols_smem<8>(d, p, D, nimg, s);
+    const int Hpad = (d.H + 31) & ~31;
+    const size_t smem = (size_t)d.H * (GC_COLS + 1) * sizeof(float) + (size_t)GC_WARPS * Hpad * sizeof(int);
+    if (smem <= 200 * 1024) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_gap_cols_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) {
+                set_error("cudaFuncSetAttribute(k_gap_cols_strip): %s", cudaGetErrorString(e));
+                return SVB_ERR_CUDA;
+            }
+        }
+        dim3 grid((d.W + GC_COLS - 1) / GC_COLS, nimg);
+        k_gap_cols_strip<<<grid, GC_WARPS * 32, smem, s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners, Hpad);
+        SVB_LAUNCH_CHECK();
+        return SVB_OK;
+    }
     {
         dim3 grid((d.W + 127) / 128, nimg);
         k_gap_cols<<<grid, 128, 0, s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners);

@@ -61,7 +61,7 @@ int make_dims(const svb_params &p, int W, int H, Dims *out) {
     d.ch = (H + d.step - 1) / d.step;
     d.gw = (int)ceil((float)W / (float)p.grid_size);  // elas.cpp:88-89
     d.gh = (int)ceil((float)H / (float)p.grid_size);
-    d.gwords = (p.disp_max + 1 + 31) / 32;
+    d.gwords = (((p.disp_max + 1 + 31) / 32) + 3) & ~3;  // multiple of 4: cells are read as 16-byte vectors
     d.maxS = (d.cw - 1) * (d.ch - 1) + 6;
     d.maxT = 2 * d.maxS;
     // elas.cpp:828-832
