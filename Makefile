@@ -13,6 +13,7 @@ $(LIB): FORCE
 shared_library: $(LIB)
 	@mkdir -p build/bin
 	cp $(LIB) build/bin/stereo_vision_parallel.so
+	ln -sf stereo_vision_parallel.so build/bin/libelas_b200.so
 
 stereo_vision: $(LIB)
 	@mkdir -p build/bin

@@ -198,6 +198,12 @@ int svb_calib_load_yaml(const char *path, svb_calibration *out);
 int svb_stereo_rectify(const svb_calibration *cal, int calib_width, int calib_height, int new_width, int new_height, double scale_factor,
                        double alpha, double *R1, double *R2, double *P1, double *P2, double *Q);
 
+/* Image file input of the sequence driver without OpenCV / libpng (host only): 8/16-bit non-interlaced PNG (decoded
+ * with zlib) or binary PGM, chosen by the file extension.  Replaces cv::imread (stereo_vision.cu:661-662) and loadPGM
+ * (src/common_includes/image.h:134-161).  Colour PNGs are returned as BGRA (4 channels), gray images as 1 channel.
+ * With out == NULL only the dimensions are returned. */
+int svb_image_read(const char *path, uint8_t *out, int64_t capacity, int *width, int *height, int *channels);
+
 /* Deterministic synthetic rectified stereo pair of known disparity (bench / parity INPUT generator, host only;
  * SURVEY.md 8d).  left/right: W*H u8 each.  slanted = 0: bands of disparity 8/24/48; 1: d = 10 + 0.03 u. */
 int svb_synth_pair(int frame_index, int width, int height, int slanted, uint8_t *left, uint8_t *right);

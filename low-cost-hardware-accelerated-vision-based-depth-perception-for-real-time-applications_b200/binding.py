@@ -130,6 +130,7 @@ def load():
         "svb_synth_pair": [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp],
         "svb_point_cloud_bgra": [vp, vp, vp, vp, vp, vp, vp],
         "svb_stage_bgra_to_gray": [vp, vp, vp],
+        "svb_image_read": [C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "svb_calib_load_yaml": [C.c_char_p, C.POINTER(Calibration)],
         "svb_stereo_rectify": [C.POINTER(Calibration), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp],
     }.items():
@@ -176,6 +177,20 @@ def delaunay(support, right):
     if rc != 0:
         raise SvbError(rc, lib.svb_last_error().decode())
     return tri[: m.value].copy()
+
+
+def image_read(path):
+    """PNG / PGM reader of the sequence driver (replaces cv::imread / loadPGM): HxWx4 BGRA or HxWx1 gray, uint8."""
+    lib = load()
+    w, h, c = C.c_int(), C.c_int(), C.c_int()
+    rc = lib.svb_image_read(str(path).encode(), None, 0, C.byref(w), C.byref(h), C.byref(c))
+    if rc != 0:
+        raise SvbError(rc, lib.svb_last_error().decode())
+    buf = np.zeros((h.value, w.value, c.value), np.uint8)
+    rc = lib.svb_image_read(str(path).encode(), _ptr(buf), buf.size, C.byref(w), C.byref(h), C.byref(c))
+    if rc != 0:
+        raise SvbError(rc, lib.svb_last_error().decode())
+    return buf
 
 
 def load_calibration(path):
