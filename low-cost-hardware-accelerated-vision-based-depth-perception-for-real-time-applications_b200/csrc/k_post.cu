@@ -353,7 +353,15 @@ int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStrea
     const int Wpad = (d.W + 31) & ~31;
     {
         dim3 grid((d.H + GAP_WARPS - 1) / GAP_WARPS, nimg);
-        k_gap_rows<<<grid, GAP_WARPS * 32, (size_t)GAP_WARPS * Wpad * sizeof(int), s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners, Wpad);
+        const size_t smem_rows = (size_t)GAP_WARPS * Wpad * sizeof(int);
+        if (smem_rows > 48 * 1024) {  // 4K-wide rows: opt in to large dynamic shared memory
+            cudaError_t e = cudaFuncSetAttribute(k_gap_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows);
+            if (e != cudaSuccess) {
+                set_error("cudaFuncSetAttribute(k_gap_rows, %zu): %s", smem_rows, cudaGetErrorString(e));
+                return SVB_ERR_CUDA;
+            }
+        }
+        k_gap_rows<<<grid, GAP_WARPS * 32, smem_rows, s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners, Wpad);
         SVB_LAUNCH_CHECK();
     }
     const int Hpad = (d.H + 31) & ~31;

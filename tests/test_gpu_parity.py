@@ -100,6 +100,25 @@ def test_synthetic_end_to_end_parity(svb, ref, W, H, slanted, pname):
         ctx.close()
 
 
+def test_4k_disp512_single_gpu_parity(svb, ref):
+    """BASELINE.json configs[3] shape: 3840x2160, disparity range 512 (disp_max 511), whole pipeline with L/R check and
+    all post-filters, on one GPU.  Exercises the large-frame code paths (lattice filters in global memory, 16-word
+    cell masks, the global-memory gap column walk)."""
+    W, H = 3840, 2160
+    L, R = svb.synth_pair(9, W, H, 0)
+    p = svb.default_params(svb.MIDDLEBURY, disp_max=511)
+    p_ref = ref.params(1, disp_max=511)
+    ctx = svb.Context(p, W, H)
+    try:
+        D1, D2 = ctx.process(L, R)
+        R1, R2, _ = ref.process(p_ref, L, R)
+        assert np.array_equal(D1, R1)
+        assert np.array_equal(D2, R2)
+        assert (D1 >= 0).mean() > 0.5
+    finally:
+        ctx.close()
+
+
 def test_few_support_points_leaves_outputs_untouched(svb, ref):
     """elas.cpp:64-69: a textureless pair yields < 3 support points; D1/D2 stay as the caller passed them."""
     W, H = 320, 120
