@@ -163,6 +163,27 @@ int svb_point_cloud_bgra(svb_context *ctx, const uint8_t *left_bgra, const uint8
 /* cv::cvtColor(BGRA2GRAY) on its own (stereo_vision.cu:346-347) */
 int svb_stage_bgra_to_gray(svb_context *ctx, const uint8_t *bgra, uint8_t *gray_out);
 
+/* ---- one frame split into row bands over several GPUs (BASELINE.json configs[3]: 3840x2160, disparity range 512) ------
+ * New relative to the reference (single GPU).  Same semantics and bit-identical results as svb_process / Elas::process
+ * (src/parallel_includes/elas/elas.h:151-160).  One process drives all devices; descriptor halo rows, the candidate
+ * lattice and the L/R-checked band rows move between the GPUs' memories with peer-to-peer copies (NVLink 5 / NVSwitch
+ * when peer access is available).  A device may be listed more than once. */
+typedef struct svb_band_group svb_band_group;
+typedef struct svb_band_stats {
+    double gpu_ms;          /* CUDA-event time of the call on device 0 (first upload to last download) */
+    double wall_ms;         /* host wall time of the call */
+    double delaunay_ms;     /* host Delaunay stage inside the call */
+    int64_t p2p_bytes;      /* bytes moved by peer-to-peer copies */
+    int64_t p2p_copies;
+    int32_t peer_links;     /* directed device pairs with peer access enabled */
+    int32_t bands;
+    int64_t support_points, triangles;
+} svb_band_stats;
+svb_band_group *svb_band_create(const svb_params *params, int width, int height, const int *devices, int n_devices);
+void svb_band_destroy(svb_band_group *g);
+int svb_band_process(svb_band_group *g, const uint8_t *I1, const uint8_t *I2, int stride, float *D1, float *D2);
+int svb_band_get_stats(svb_band_group *g, svb_band_stats *out);
+
 /* timing / accounting of the most recent batch or process call */
 typedef struct svb_stats {
     double gpu_ms_total;       /* CUDA-event time from first to last kernel of the call */

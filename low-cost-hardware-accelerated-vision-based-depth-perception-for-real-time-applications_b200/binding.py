@@ -70,6 +70,11 @@ class Calibration(C.Structure):
                 ("n_d2", C.c_int32), ("R", C.c_double * 9), ("T", C.c_double * 3), ("XR", C.c_double * 9), ("XT", C.c_double * 3)]
 
 
+class BandStats(C.Structure):
+    _fields_ = [("gpu_ms", C.c_double), ("wall_ms", C.c_double), ("delaunay_ms", C.c_double), ("p2p_bytes", C.c_int64), ("p2p_copies", C.c_int64),
+                ("peer_links", C.c_int32), ("bands", C.c_int32), ("support_points", C.c_int64), ("triangles", C.c_int64)]
+
+
 class SvbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("svb error %d: %s" % (code, msg))
@@ -93,6 +98,9 @@ def load():
     lib.svb_create.restype = C.c_void_p
     lib.svb_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int]
     lib.svb_destroy.argtypes = [C.c_void_p]
+    lib.svb_band_create.restype = C.c_void_p
+    lib.svb_band_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
+    lib.svb_band_destroy.argtypes = [C.c_void_p]
     lib.svb_tap.restype = C.c_int64
     lib.svb_tap.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
     lib.svb_host_alloc.restype = C.c_void_p
@@ -130,6 +138,8 @@ def load():
         "svb_synth_pair": [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp],
         "svb_point_cloud_bgra": [vp, vp, vp, vp, vp, vp, vp],
         "svb_stage_bgra_to_gray": [vp, vp, vp],
+        "svb_band_process": [vp, vp, vp, C.c_int, vp, vp],
+        "svb_band_get_stats": [vp, C.POINTER(BandStats)],
         "svb_image_read": [C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "svb_calib_load_yaml": [C.c_char_p, C.POINTER(Calibration)],
         "svb_stereo_rectify": [C.POINTER(Calibration), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp],
@@ -245,6 +255,39 @@ class PinnedArray:
             self.array = None
             load().svb_host_free(self.ptr)
             self.ptr = None
+
+
+class BandGroup:
+    """One frame split into row bands over several GPUs (svb_band_*): Elas::process semantics, P2P halo exchange."""
+
+    def __init__(self, params, width, height, devices):
+        self.lib = load()
+        self.W, self.H = width, height
+        arr = (C.c_int * len(devices))(*devices)
+        self.h = self.lib.svb_band_create(C.byref(params), width, height, arr, len(devices))
+        if not self.h:
+            raise SvbError(-1, self.lib.svb_last_error().decode())
+
+    def process(self, I1, I2, D1=None, D2=None):
+        """D1 / D2 may be preallocated (e.g. PinnedArray views, so that the transfers run at full PCIe rate)."""
+        I1 = np.ascontiguousarray(I1, np.uint8)
+        I2 = np.ascontiguousarray(I2, np.uint8)
+        D1 = np.zeros((self.H, self.W), np.float32) if D1 is None else D1
+        D2 = np.zeros((self.H, self.W), np.float32) if D2 is None else D2
+        rc = self.lib.svb_band_process(self.h, _ptr(I1), _ptr(I2), self.W, _ptr(D1), _ptr(D2))
+        if rc != 0:
+            raise SvbError(rc, self.lib.svb_last_error().decode())
+        return D1, D2
+
+    def stats(self):
+        s = BandStats()
+        self.lib.svb_band_get_stats(self.h, C.byref(s))
+        return {k: getattr(s, k) for k, _ in BandStats._fields_}
+
+    def close(self):
+        if self.h:
+            self.lib.svb_band_destroy(self.h)
+            self.h = None
 
 
 class Context:

@@ -26,6 +26,7 @@ struct DenseArgs {
     const uint32_t *grid[2];
     float *D[2];
     int W, H, maxT, gw, gh, gwords, grid_size, disp_max, match_texture, plane_radius;
+    int row0;  // first image row of the launch (0, or the start of this device's band)
     unsigned grid_magic;  // ceil(2^32 / grid_size)
     int P[8];
 };
@@ -70,7 +71,7 @@ __device__ __forceinline__ uint32_t range_mask(int lo, int hi, int base) {
 template <int SIDE, int RADIUS>
 __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = blockIdx.y;
+    const int v = a.row0 + blockIdx.y;
     const int f = blockIdx.z >> 1;
     const int W = a.W, H = a.H;
     const size_t N = (size_t)W * H;
@@ -198,7 +199,13 @@ __global__ void __launch_bounds__(128) k_dense(const DenseArgs a) {
 int launch_dense(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, const int32_t *owner1, const int32_t *owner2,
                  const PlaneRec *rec1, const PlaneRec *rec2, const uint32_t *grid1, const uint32_t *grid2, float *D1, float *D2, int nf,
                  cudaStream_t s) {
-    if (nf <= 0) return SVB_OK;
+    return launch_dense_rows(d, p, desc1, desc2, owner1, owner2, rec1, rec2, grid1, grid2, D1, D2, nf, 0, d.H, s);
+}
+
+int launch_dense_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, const int32_t *owner1, const int32_t *owner2,
+                      const PlaneRec *rec1, const PlaneRec *rec2, const uint32_t *grid1, const uint32_t *grid2, float *D1, float *D2, int nf,
+                      int row0, int row1, cudaStream_t s) {
+    if (nf <= 0 || row1 <= row0) return SVB_OK;
     DenseArgs a;
     a.desc[0] = desc1;
     a.desc[1] = desc2;
@@ -222,7 +229,8 @@ int launch_dense(const Dims &d, const svb_params &p, const uint8_t *desc1, const
     a.match_texture = p.match_texture;
     a.plane_radius = d.plane_radius;
     for (int i = 0; i < 8; i++) a.P[i] = d.P[i];
-    dim3 grid((d.W + 127) / 128, d.H, nf * 2);
+    a.row0 = row0;
+    dim3 grid((d.W + 127) / 128, row1 - row0, nf * 2);
     if (d.plane_radius == 2)
         k_dense<2><<<grid, 128, 0, s>>>(a);
     else if (d.plane_radius == 3)

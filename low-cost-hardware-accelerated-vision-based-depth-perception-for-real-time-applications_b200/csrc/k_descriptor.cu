@@ -29,14 +29,14 @@ constexpr int NT = 256;
 
 __device__ __forceinline__ int sat_u8(int x) { return min(max(x, 0), 255); }
 
-__global__ void __launch_bounds__(NT) k_descriptor(const uint8_t *__restrict__ img, uint8_t *__restrict__ desc, int W, int H) {
+__global__ void __launch_bounds__(NT) k_descriptor(const uint8_t *__restrict__ img, uint8_t *__restrict__ desc, int W, int H, int row0, int row1) {
     __shared__ uint8_t sI[TH + 6][TW + 6 + 2];
     __shared__ uint8_t sDu[TH + 4][TW + 4];
     __shared__ uint8_t sDv[TH + 2][TW + 2 + 2];
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TW;
-    const int y0 = blockIdx.y * TH;
+    const int y0 = row0 + blockIdx.y * TH;  // only rows row0 .. row1-1 are produced (row-band split; the whole image otherwise)
     const size_t N = (size_t)W * H;
     const uint8_t *I = img + (size_t)blockIdx.z * N;
     uint4 *out = reinterpret_cast<uint4 *>(desc + (size_t)blockIdx.z * N * 16);
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(NT) k_descriptor(const uint8_t *__restrict__ i
     for (int i = tid; i < TH * TW; i += NT) {
         int ty = i / TW, tx = i - ty * TW;
         int u = x0 + tx, v = y0 + ty;
-        if (u >= W || v >= H) continue;
+        if (u >= W || v >= row1) continue;
         uint4 q = make_uint4(0u, 0u, 0u, 0u);
         if (u >= 3 && u < W - 3 && v >= 3 && v < H - 3) {
             const int a = ty + 2, b = tx + 2;  // du(v,u) = sDu[a][b]
@@ -94,9 +94,13 @@ __global__ void __launch_bounds__(NT) k_descriptor(const uint8_t *__restrict__ i
 }  // namespace
 
 int launch_descriptor(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, cudaStream_t s) {
-    if (nimg <= 0) return SVB_OK;
-    dim3 grid((d.W + TW - 1) / TW, (d.H + TH - 1) / TH, nimg);
-    k_descriptor<<<grid, NT, 0, s>>>(img, desc, d.W, d.H);
+    return launch_descriptor_rows(d, img, desc, nimg, 0, d.H, s);
+}
+
+int launch_descriptor_rows(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, int row0, int row1, cudaStream_t s) {
+    if (nimg <= 0 || row1 <= row0) return SVB_OK;
+    dim3 grid((d.W + TW - 1) / TW, (row1 - row0 + TH - 1) / TH, nimg);
+    k_descriptor<<<grid, NT, 0, s>>>(img, desc, d.W, d.H, row0, row1);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

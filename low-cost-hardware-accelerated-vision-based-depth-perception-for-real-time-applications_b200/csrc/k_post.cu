@@ -12,10 +12,10 @@ namespace {
 // ---- L/R check ------------------------------------------------------------------------------------
 // grid: (ceil(W/256), H, nf).  Out of place: the reference works on copies of both maps (elas.cpp:956-959).
 __global__ void __launch_bounds__(256) k_lr_check(const float *__restrict__ D1in, const float *__restrict__ D2in, float *__restrict__ D1out,
-                                                 float *__restrict__ D2out, int W, int H, float lr_threshold) {
+                                                 float *__restrict__ D2out, int W, int H, float lr_threshold, int row0) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= W) return;
-    const size_t base = ((size_t)blockIdx.z * H + blockIdx.y) * W;
+    const size_t base = ((size_t)blockIdx.z * H + row0 + blockIdx.y) * W;
     const float d1 = D1in[base + u];
     const float d2 = D2in[base + u];
     const float fw = (float)W;
@@ -112,11 +112,11 @@ __global__ void __launch_bounds__(GAP_WARPS * 32) k_gap_rows(float *__restrict__
 // its warps handles GC_COLS / GC_WARPS columns, and the strip is written back.  Every invalid pixel only depends on
 // the nearest valid pixels above and below in the state BEFORE the pass (fills never create a boundary for another
 // gap, elas.cpp:1220-1293), so the sequential walk and this formulation agree exactly.
-constexpr int GC_COLS = 16;
 constexpr int GC_WARPS = 8;
 
+// GC_COLS (runtime: 16, or 8 for very tall frames so that the strip still fits in shared memory) columns per CTA
 __global__ void __launch_bounds__(GC_WARPS * 32) k_gap_cols_strip(float *__restrict__ D_all, int W, int H, int gap_width, int add_corners,
-                                                                  int Hpad) {
+                                                                  int Hpad, int GC_COLS) {
     extern __shared__ float s_gc[];  // [H][GC_COLS + 1] floats, then GC_WARPS * Hpad ints
     float *strip = s_gc;
     int *prev_all = reinterpret_cast<int *>(s_gc + (size_t)H * (GC_COLS + 1));
@@ -341,9 +341,14 @@ __global__ void __launch_bounds__(128) k_median_v(const float *__restrict__ tmp_
 
 int launch_lr_check(const Dims &d, const svb_params &p, const float *D1in, const float *D2in, float *D1out, float *D2out, int nf,
                     cudaStream_t s) {
-    if (nf <= 0) return SVB_OK;
-    dim3 grid((d.W + 255) / 256, d.H, nf);
-    k_lr_check<<<grid, 256, 0, s>>>(D1in, D2in, D1out, D2out, d.W, d.H, (float)p.lr_threshold);
+    return launch_lr_check_rows(d, p, D1in, D2in, D1out, D2out, nf, 0, d.H, s);
+}
+
+int launch_lr_check_rows(const Dims &d, const svb_params &p, const float *D1in, const float *D2in, float *D1out, float *D2out, int nf, int row0,
+                         int row1, cudaStream_t s) {
+    if (nf <= 0 || row1 <= row0) return SVB_OK;
+    dim3 grid((d.W + 255) / 256, row1 - row0, nf);
+    k_lr_check<<<grid, 256, 0, s>>>(D1in, D2in, D1out, D2out, d.W, d.H, (float)p.lr_threshold, row0);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }
@@ -365,7 +370,12 @@ int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStrea
         SVB_LAUNCH_CHECK();
     }
     const int Hpad = (d.H + 31) & ~31;
-    const size_t smem = (size_t)d.H * (GC_COLS + 1) * sizeof(float) + (size_t)GC_WARPS * Hpad * sizeof(int);
+    int GC_COLS = 16;
+    size_t smem = (size_t)d.H * (GC_COLS + 1) * sizeof(float) + (size_t)GC_WARPS * Hpad * sizeof(int);
+    if (smem > 200 * 1024) {
+        GC_COLS = 8;
+        smem = (size_t)d.H * (GC_COLS + 1) * sizeof(float) + (size_t)GC_WARPS * Hpad * sizeof(int);
+    }
     if (smem <= 200 * 1024) {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(k_gap_cols_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -375,7 +385,7 @@ int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStrea
             }
         }
         dim3 grid((d.W + GC_COLS - 1) / GC_COLS, nimg);
-        k_gap_cols_strip<<<grid, GC_WARPS * 32, smem, s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners, Hpad);
+        k_gap_cols_strip<<<grid, GC_WARPS * 32, smem, s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners, Hpad, GC_COLS);
         SVB_LAUNCH_CHECK();
         return SVB_OK;
     }

@@ -188,7 +188,7 @@ __device__ __forceinline__ int f2u_as_int_x86(float x) {
 __global__ void __launch_bounds__(128) k_raster(const int32_t *__restrict__ support_all, const int32_t *__restrict__ tri1_all,
                                                const int32_t *__restrict__ tri2_all, const int32_t *__restrict__ ntri_all,
                                                const int32_t *__restrict__ trioff_all, int32_t *__restrict__ owner1_all,
-                                               int32_t *__restrict__ owner2_all, int W, int H, int maxS) {
+                                               int32_t *__restrict__ owner2_all, int W, int H, int maxS, int row0, int row1) {
     const int f = blockIdx.z, side = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(128) k_raster(const int32_t *__restrict__ supp
             const float fu = (float)u;
             const int v_1 = f2u_as_int_x86(__fadd_rn(__fmul_rn(AC_a, fu), AC_b));
             const int v_2 = f2u_as_int_x86(__fadd_rn(__fmul_rn(la, fu), lb));
-            const int v_lo = max(min(v_1, v_2), 0), v_hi = min(max(v_1, v_2), H);
+            // rows are clipped to [row0, row1): the whole image, or this device's band in the row-band split
+            const int v_lo = max(max(min(v_1, v_2), 0), row0), v_hi = min(min(max(v_1, v_2), H), row1);
             for (int v = v_lo; v < v_hi; v++) atomicMax(owner + (size_t)v * W + u, i);
         }
     }
@@ -289,17 +290,31 @@ int launch_grid_expand(const Dims &d, const svb_params &p, const uint32_t *grid,
 
 int launch_raster(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,
                   int32_t *owner1, int32_t *owner2, int nf, int max_tri, cudaStream_t s) {
-    if (nf <= 0) return SVB_OK;
+    return launch_raster_rows(d, support, tri1, tri2, ntri, trioff, owner1, owner2, nf, max_tri, 0, d.H, s);
+}
+
+int launch_raster_rows(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,
+                       int32_t *owner1, int32_t *owner2, int nf, int max_tri, int row0, int row1, cudaStream_t s) {
+    if (nf <= 0 || row1 <= row0) return SVB_OK;
     if (max_tri > d.maxT) max_tri = d.maxT;
-    cudaError_t e = cudaMemsetAsync(owner1, 0xFF, (size_t)nf * d.N * sizeof(int32_t), s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(owner2, 0xFF, (size_t)nf * d.N * sizeof(int32_t), s);
+    cudaError_t e = cudaSuccess;
+    if (row0 == 0 && row1 == d.H) {
+        e = cudaMemsetAsync(owner1, 0xFF, (size_t)nf * d.N * sizeof(int32_t), s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(owner2, 0xFF, (size_t)nf * d.N * sizeof(int32_t), s);
+    } else {
+        for (int f = 0; f < nf && e == cudaSuccess; f++) {
+            const size_t off = (size_t)f * d.N + (size_t)row0 * d.W, cnt = (size_t)(row1 - row0) * d.W * sizeof(int32_t);
+            e = cudaMemsetAsync(owner1 + off, 0xFF, cnt, s);
+            if (e == cudaSuccess) e = cudaMemsetAsync(owner2 + off, 0xFF, cnt, s);
+        }
+    }
     if (e != cudaSuccess) {
         set_error("cudaMemsetAsync(owner): %s", cudaGetErrorString(e));
         return SVB_ERR_CUDA;
     }
     if (max_tri <= 0) return SVB_OK;
     dim3 grid((max_tri + 3) / 4, 2, nf);
-    k_raster<<<grid, 128, 0, s>>>(support, tri1, tri2, ntri, trioff, owner1, owner2, d.W, d.H, d.maxS);
+    k_raster<<<grid, 128, 0, s>>>(support, tri1, tri2, ntri, trioff, owner1, owner2, d.W, d.H, d.maxS, row0, row1);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

@@ -122,16 +122,17 @@ __device__ __forceinline__ int match_pass(const uint4 *__restrict__ own, const u
 __global__ void __launch_bounds__(SM_WARPS * 32) k_support_match(const uint8_t *__restrict__ desc1, const uint8_t *__restrict__ desc2,
                                                                  int16_t *__restrict__ dcan_raw, int W, int H, int cw, int ch, int step,
                                                                  int disp_min, int disp_max, int support_texture, float support_threshold,
-                                                                 int lr_threshold) {
+                                                                 int lr_threshold, int vc0, int vc1) {
+    // lattice rows vc0 .. vc1-1 (1 .. ch-1 for a whole frame; a sub-range in the row-band split)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int pu = (cw - 1 + PATCH_U - 1) / PATCH_U, pv = (ch - 1 + PATCH_V - 1) / PATCH_V;
+    const int pu = (cw - 1 + PATCH_U - 1) / PATCH_U, pv = (vc1 - vc0 + PATCH_V - 1) / PATCH_V;
     const int patch = blockIdx.x * SM_WARPS + wid;
     if (patch >= pu * pv) return;  // warp-uniform
     const int prow = patch / pu, pcol = patch - prow * pu;
     const int f = blockIdx.y;
     const int uc = 1 + pcol * PATCH_U + (lane & (PATCH_U - 1));
-    const int vc = 1 + prow * PATCH_V + (lane / PATCH_U);
-    const bool has = uc < cw && vc < ch;
+    const int vc = vc0 + prow * PATCH_V + (lane / PATCH_U);
+    const bool has = uc < cw && vc < vc1;
     const int u = uc * step, v = vc * step;
     const size_t fo = (size_t)f * W * H;
     const uint4 *d1 = reinterpret_cast<const uint4 *>(desc1) + fo;
@@ -362,22 +363,30 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(const int16_t *__
 
 }  // namespace
 
-int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int nf,
-                         cudaStream_t s) {
+int launch_dcan_border(const Dims &d, int16_t *dcan_raw, int nf, cudaStream_t s) {
     if (nf <= 0) return SVB_OK;
-    {
-        int m = d.cw > d.ch ? d.cw : d.ch;
-        dim3 grid((m + 127) / 128, nf);
-        k_dcan_border<<<grid, 128, 0, s>>>(dcan_raw, d.cw, d.ch);
-        SVB_LAUNCH_CHECK();
-    }
-    if (d.cw < 2 || d.ch < 2) return SVB_OK;
-    const int patches = ((d.cw - 1 + PATCH_U - 1) / PATCH_U) * ((d.ch - 1 + PATCH_V - 1) / PATCH_V);
-    dim3 grid((patches + SM_WARPS - 1) / SM_WARPS, nf);
-    k_support_match<<<grid, SM_WARPS * 32, 0, s>>>(desc1, desc2, dcan_raw, d.W, d.H, d.cw, d.ch, d.step, p.disp_min, p.disp_max,
-                                                   p.support_texture, p.support_threshold, p.lr_threshold);
+    int m = d.cw > d.ch ? d.cw : d.ch;
+    dim3 grid((m + 127) / 128, nf);
+    k_dcan_border<<<grid, 128, 0, s>>>(dcan_raw, d.cw, d.ch);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
+}
+
+int launch_support_match_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int nf, int vc0,
+                              int vc1, cudaStream_t s) {
+    if (nf <= 0 || d.cw < 2 || vc1 <= vc0) return SVB_OK;
+    const int patches = ((d.cw - 1 + PATCH_U - 1) / PATCH_U) * ((vc1 - vc0 + PATCH_V - 1) / PATCH_V);
+    dim3 grid((patches + SM_WARPS - 1) / SM_WARPS, nf);
+    k_support_match<<<grid, SM_WARPS * 32, 0, s>>>(desc1, desc2, dcan_raw, d.W, d.H, d.cw, d.ch, d.step, p.disp_min, p.disp_max,
+                                                   p.support_texture, p.support_threshold, p.lr_threshold, vc0, vc1);
+    SVB_LAUNCH_CHECK();
+    return SVB_OK;
+}
+
+int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int nf,
+                         cudaStream_t s) {
+    SVB_TRY(launch_dcan_border(d, dcan_raw, nf, s));
+    return launch_support_match_rows(d, p, desc1, desc2, dcan_raw, nf, 1, d.ch, s);
 }
 
 int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dcan_raw, int16_t *dcan, int32_t *support, int32_t *nsupport,

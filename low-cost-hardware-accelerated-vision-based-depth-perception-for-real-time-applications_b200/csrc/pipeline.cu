@@ -81,84 +81,11 @@ static const char *kStageNames[ST_COUNT] = {"descriptor", "support_match", "supp
                                             "planes",     "grid",          "raster",         "dense_match", "lr_check",
                                             "remove_small_segments", "gap_interpolation", "adaptive_mean", "median", "reproject"};
 
-constexpr int LANES = 3;
-
-struct Lane {
-    cudaStream_t own_stream = nullptr;  // created with the lane
-    cudaStream_t stream = nullptr;      // the stream the lane's work is issued on (own_stream, or lane 0's in single-stream mode)
-    cudaEvent_t ev_a = nullptr, ev_done = nullptr;
-    // device
-    uint8_t *img[2] = {nullptr, nullptr};
-    uint8_t *desc[2] = {nullptr, nullptr};
-    int16_t *dcan_raw = nullptr, *dcan = nullptr;
-    int32_t *support = nullptr, *nsupport = nullptr;
-    int32_t *tri[2] = {nullptr, nullptr};
-    int32_t *ntri = nullptr;    // [2*chunk] triangle counts (2f + side), then [chunk] first triangle of frame f in tri[]
-    int32_t *trioff = nullptr;  // = ntri + 2*chunk
-    PlaneRec *rec[2] = {nullptr, nullptr};
-    uint32_t *grid_tmp = nullptr, *grid[2] = {nullptr, nullptr};
-    int32_t *owner[2] = {nullptr, nullptr};
-    float *Draw = nullptr;  // [2][chunk][N]
-    float *Dlr = nullptr;   // [2][chunk][N]
-    float *Dtmp = nullptr;  // [2][chunk][N]
-    int32_t *labels = nullptr, *sizes = nullptr;  // [2][chunk][N]
-    uint8_t *dmap = nullptr;
-    // pinned host
-    int32_t *h_support = nullptr, *h_nsupport = nullptr, *h_tri[2] = {nullptr, nullptr}, *h_ntri = nullptr;
-};
-
-// CUDA events bracketing every stage of one chunk (stage timing): [i] is recorded in front of stage i, [ST_COUNT] after
-// the last stage, a_end behind the D2H that ends stage A.
-struct StageEvents {
-    cudaEvent_t ev[ST_COUNT + 1] = {};
-    cudaEvent_t a_end = nullptr;
-    bool a_done = false, b_done = false;
-};
-
-struct Tap {
-    std::string name;
-    void *dev = nullptr;
-    size_t bytes = 0;
-};
-
 }  // namespace svb
 
-using namespace svb;
+#include "pipeline_internal.h"
 
-struct svb_context {
-    svb_params p;
-    Dims d;
-    int chunk = 1;
-    int device = 0;
-    int mean_mode = SVB_MEAN_SERIAL_QUANTISED;
-    Lane lanes[LANES];
-    std::unique_ptr<ThreadPool> pool;
-    std::vector<DelaunayScratch> scratch;
-    Calib calib;
-    bool have_calib = false;
-    // tap mode (single frame)
-    bool tap_mode = false;
-    std::vector<Tap> taps;
-    float *planes_ref[2] = {nullptr, nullptr};  // [maxT][6], tap mode only
-    std::vector<int32_t> inject_tri[2];
-    bool inject[2] = {false, false};
-    // generatePointCloud path: BGRA staging on the device
-    uint8_t *bgra[2] = {nullptr, nullptr};
-    cudaEvent_t ev_pc[4] = {nullptr, nullptr, nullptr, nullptr};
-    // resident batch stores
-    uint8_t *in_img[2] = {nullptr, nullptr};
-    size_t in_frames = 0;
-    float *out_D1 = nullptr;
-    size_t out_D1_frames = 0;
-    double *out_points = nullptr;
-    size_t out_points_frames = 0;
-    // stats
-    svb_stats stats;
-    bool stage_timing = false;
-    bool single_stream = false;
-    std::vector<StageEvents> stage_ev;  // one set per chunk of the call in flight
-    std::mutex mu;
-};
+using namespace svb;
 
 namespace {
 
@@ -334,7 +261,8 @@ int stage_a(svb_context *c, Lane &L, const uint8_t *img1, const uint8_t *img2, i
 }
 
 // ---- host stage ----------------------------------------------------------------------------------------
-int stage_host(svb_context *c, Lane &L, int nf) {
+}  // namespace
+int svb::stage_host(svb_context *c, Lane &L, int nf) {
     const Dims &d = c->d;
     SVB_CUDA(cudaEventSynchronize(L.ev_a));
     const auto t0 = std::chrono::steady_clock::now();
@@ -388,6 +316,7 @@ int stage_host(svb_context *c, Lane &L, int nf) {
     return SVB_OK;
 }
 
+namespace {
 // ---- stage B: triangles (pinned host) -> disparity / points -------------------------------------------
 // out_D1 / out_points may be null.  The final maps stay in L.Dlr ([0] = left, [1] = right).
 int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, StageEvents *se) {

@@ -1,0 +1,96 @@
+// Internal structures of the pipeline, shared by pipeline.cu and band_split.cu.  Nothing here crosses the C-ABI.
+#pragma once
+
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "host_delaunay.h"
+#include "svb_internal.h"
+#include "thread_pool.h"
+
+namespace svb {
+
+constexpr int LANES = 3;
+
+struct Lane {
+    cudaStream_t own_stream = nullptr;  // created with the lane
+    cudaStream_t stream = nullptr;      // the stream the lane's work is issued on (own_stream, or lane 0's in single-stream mode)
+    cudaEvent_t ev_a = nullptr, ev_done = nullptr;
+    // device
+    uint8_t *img[2] = {nullptr, nullptr};
+    uint8_t *desc[2] = {nullptr, nullptr};
+    int16_t *dcan_raw = nullptr, *dcan = nullptr;
+    int32_t *support = nullptr, *nsupport = nullptr;
+    int32_t *tri[2] = {nullptr, nullptr};
+    int32_t *ntri = nullptr;    // [2*chunk] triangle counts (2f + side), then [chunk] first triangle of frame f in tri[]
+    int32_t *trioff = nullptr;  // = ntri + 2*chunk
+    PlaneRec *rec[2] = {nullptr, nullptr};
+    uint32_t *grid_tmp = nullptr, *grid[2] = {nullptr, nullptr};
+    int32_t *owner[2] = {nullptr, nullptr};
+    float *Draw = nullptr;  // [2][chunk][N]
+    float *Dlr = nullptr;   // [2][chunk][N]
+    float *Dtmp = nullptr;  // [2][chunk][N]
+    int32_t *labels = nullptr, *sizes = nullptr;  // [2][chunk][N]
+    uint8_t *dmap = nullptr;
+    // pinned host
+    int32_t *h_support = nullptr, *h_nsupport = nullptr, *h_tri[2] = {nullptr, nullptr}, *h_ntri = nullptr;
+};
+
+// CUDA events bracketing every stage of one chunk (stage timing): [i] is recorded in front of stage i, [ST_COUNT] after
+// the last stage, a_end behind the D2H that ends stage A.
+struct StageEvents {
+    cudaEvent_t ev[ST_COUNT + 1] = {};
+    cudaEvent_t a_end = nullptr;
+    bool a_done = false, b_done = false;
+};
+
+struct Tap {
+    std::string name;
+    void *dev = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace svb
+
+struct svb_context {
+    svb_params p;
+    svb::Dims d;
+    int chunk = 1;
+    int device = 0;
+    int mean_mode = SVB_MEAN_SERIAL_QUANTISED;
+    svb::Lane lanes[svb::LANES];
+    std::unique_ptr<svb::ThreadPool> pool;
+    std::vector<svb::DelaunayScratch> scratch;
+    svb::Calib calib;
+    bool have_calib = false;
+    // tap mode (single frame)
+    bool tap_mode = false;
+    std::vector<svb::Tap> taps;
+    float *planes_ref[2] = {nullptr, nullptr};  // [maxT][6], tap mode only
+    std::vector<int32_t> inject_tri[2];
+    bool inject[2] = {false, false};
+    // generatePointCloud path: BGRA staging on the device
+    uint8_t *bgra[2] = {nullptr, nullptr};
+    cudaEvent_t ev_pc[4] = {nullptr, nullptr, nullptr, nullptr};
+    // resident batch stores
+    uint8_t *in_img[2] = {nullptr, nullptr};
+    size_t in_frames = 0;
+    float *out_D1 = nullptr;
+    size_t out_D1_frames = 0;
+    double *out_points = nullptr;
+    size_t out_points_frames = 0;
+    // stats
+    svb_stats stats;
+    bool stage_timing = false;
+    bool single_stream = false;
+    std::vector<svb::StageEvents> stage_ev;  // one set per chunk of the call in flight
+    std::mutex mu;
+};
+
+
+namespace svb {
+// host Delaunay stage of one chunk whose support lists have arrived in lane L's pinned buffers (pipeline.cu)
+int stage_host(svb_context *c, Lane &L, int nf);
+}  // namespace svb

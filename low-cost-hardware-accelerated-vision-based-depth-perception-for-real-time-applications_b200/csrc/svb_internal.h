@@ -81,9 +81,14 @@ enum StageId {
 // ---- kernel launchers (each one is batched: `nimg`/`nf` independent images or frames) ----------
 // k_descriptor.cu
 int launch_descriptor(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, cudaStream_t s);
+// *_rows variants restrict a stage to image rows [row0, row1) / lattice rows [vc0, vc1): the row-band split (band_split.cu)
+int launch_descriptor_rows(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, int row0, int row1, cudaStream_t s);
 // k_support.cu
 int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int nf,
                          cudaStream_t s);
+int launch_dcan_border(const Dims &d, int16_t *dcan_raw, int nf, cudaStream_t s);
+int launch_support_match_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int nf, int vc0,
+                              int vc1, cudaStream_t s);
 // h_support / h_nsupport: device-accessible (mapped pinned) host copies written by the kernel itself, may be null
 int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dcan_raw, int16_t *dcan, int32_t *support, int32_t *nsupport,
                           int32_t *h_support, int32_t *h_nsupport, int nf, cudaStream_t s);
@@ -96,13 +101,20 @@ int launch_grid(const Dims &d, const svb_params &p, const int32_t *support, cons
 int launch_grid_expand(const Dims &d, const svb_params &p, const uint32_t *grid, int32_t *grid_ref, cudaStream_t s);
 int launch_raster(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,
                   int32_t *owner1, int32_t *owner2, int nf, int max_tri, cudaStream_t s);
+int launch_raster_rows(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,
+                       int32_t *owner1, int32_t *owner2, int nf, int max_tri, int row0, int row1, cudaStream_t s);
 // k_dense.cu
 int launch_dense(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, const int32_t *owner1, const int32_t *owner2,
                  const PlaneRec *rec1, const PlaneRec *rec2, const uint32_t *grid1, const uint32_t *grid2, float *D1, float *D2, int nf,
                  cudaStream_t s);
+int launch_dense_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, const int32_t *owner1, const int32_t *owner2,
+                      const PlaneRec *rec1, const PlaneRec *rec2, const uint32_t *grid1, const uint32_t *grid2, float *D1, float *D2, int nf,
+                      int row0, int row1, cudaStream_t s);
 // k_post.cu
 int launch_lr_check(const Dims &d, const svb_params &p, const float *D1in, const float *D2in, float *D1out, float *D2out, int nf,
                     cudaStream_t s);
+int launch_lr_check_rows(const Dims &d, const svb_params &p, const float *D1in, const float *D2in, float *D1out, float *D2out, int nf, int row0,
+                         int row1, cudaStream_t s);
 int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s);
 int launch_adaptive_mean(const Dims &d, int mean_mode, float *D, float *tmp, int nimg, cudaStream_t s);
 int launch_median(const Dims &d, float *D, float *tmp, int nimg, cudaStream_t s);
