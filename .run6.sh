@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_band_split.py -m gpu -x -q > gpurun_out/pytest_band.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_band.log
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "subsampling" > gpurun_out/pytest_sub.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest_sub.log

@@ -301,6 +301,10 @@ class Context:
         if not self.h:
             raise SvbError(-1, self.lib.svb_last_error().decode())
         step = params.candidate_stepsize
+        if params.subsampling:
+            step += step % 2  # elas.cpp:376-378
+        # disparity maps are (W/2) x (H/2) with subsampling (elas.h:81-83,157-160)
+        self.Dw, self.Dh = (width // 2, height // 2) if params.subsampling else (width, height)
         self.cw = (width + step - 1) // step
         self.ch = (height + step - 1) // step
         self.gw = -(-width // params.grid_size)
@@ -356,8 +360,8 @@ class Context:
         I1 = np.ascontiguousarray(I1, np.uint8)
         I2 = np.ascontiguousarray(I2, np.uint8)
         assert I1.shape == (self.H, self.W) and I2.shape == (self.H, self.W)
-        D1 = np.zeros((self.H, self.W), np.float32)
-        D2 = np.zeros((self.H, self.W), np.float32)
+        D1 = np.zeros((self.Dh, self.Dw), np.float32)
+        D2 = np.zeros((self.Dh, self.Dw), np.float32)
         self._chk(self.lib.svb_process(self.h, _ptr(I1), _ptr(I2), self.W, _ptr(D1), _ptr(D2)))
         return D1, D2
 
@@ -373,8 +377,8 @@ class Context:
         "planes2": (np.float32, lambda s: (-1, 6)),
         "grid1": (np.int32, lambda s: (s.gh, s.gw, s.p.disp_max + 2)),
         "grid2": (np.int32, lambda s: (s.gh, s.gw, s.p.disp_max + 2)),
-        "owner1": (np.int32, lambda s: (s.H, s.W)),
-        "owner2": (np.int32, lambda s: (s.H, s.W)),
+        "owner1": (np.int32, lambda s: (s.Dh, s.Dw)),
+        "owner2": (np.int32, lambda s: (s.Dh, s.Dw)),
     }
 
     def tap(self, name):
@@ -382,7 +386,7 @@ class Context:
             dt, shp = self._TAP_SPECS[name]
             shape = shp(self)
         else:
-            dt, shape = np.float32, (self.H, self.W)
+            dt, shape = np.float32, (self.Dh, self.Dw)
         cap = max(self.W * self.H * 16, self.gw * self.gh * (self.p.disp_max + 2) * 4, 1 << 20)
         buf = np.zeros(cap, np.uint8)
         n = self.lib.svb_tap(self.h, name.encode(), _ptr(buf), cap)
@@ -425,7 +429,7 @@ class Context:
         tri = np.ascontiguousarray(tri, np.int32)
         desc1 = np.ascontiguousarray(desc1, np.uint8)
         desc2 = np.ascontiguousarray(desc2, np.uint8)
-        D = np.zeros((self.H, self.W), np.float32)
+        D = np.zeros((self.Dh, self.Dw), np.float32)
         self._chk(self.lib.svb_stage_disparity(self.h, _ptr(support), len(support), _ptr(tri), len(tri), _ptr(desc1), _ptr(desc2), int(right),
                                                _ptr(D)))
         return D
@@ -500,7 +504,7 @@ class Context:
         self._chk(self.lib.svb_batch_run_host(self.h, _ptr(left), _ptr(right), n, flags, _ptr(D1_out), _ptr(points_out)))
 
     def batch_disparity(self, frame):
-        out = np.zeros((self.H, self.W), np.float32)
+        out = np.zeros((self.Dh, self.Dw), np.float32)
         self._chk(self.lib.svb_batch_download_disparity(self.h, frame, _ptr(out)))
         return out
 

@@ -66,6 +66,11 @@ svb_band_group *svb_band_create(const svb_params *params, int width, int height,
         delete g;
         return nullptr;
     }
+    if (g->d.sub) {
+        set_error("svb_band_create: subsampling is not supported by the row-band split");
+        delete g;
+        return nullptr;
+    }
     if (height < 16 * n_devices) {
         set_error("svb_band_create: %d rows are too few for %d bands", height, n_devices);
         delete g;

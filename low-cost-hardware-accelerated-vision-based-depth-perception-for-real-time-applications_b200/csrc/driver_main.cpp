@@ -11,8 +11,8 @@
 // Option letters, long names and the "-x=val" / "-x val" / "--name=val" spellings follow the popt table of :768-784.
 // Extension (not in the reference): -B N processes the sequence in batches of N frames through the frame-batch
 // pipeline and reports the aggregate rate.
-// Out of scope here and rejected with a message: -p 1 (OpenGL viewer), -t 1 (YOLO object tracking); -f != 1 and -s 1
-// need the resize / subsampling paths that are not built yet.
+// Out of scope here and rejected with a message: -p 1 (OpenGL viewer), -t 1 (YOLO object tracking); -f != 1
+// needs the resize path that is not built yet.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -252,8 +252,8 @@ int main(int argc, const char **argv) {
     printf("** Object tracking disabled\n");
     printf("KITTI Path: %s \n", o.kitti_path.c_str());
     if (o.draw_points) fprintf(stderr, "the OpenGL viewer is outside this program's scope (-p 1 ignored)\n");
-    if (o.scale_factor != 1.f || o.subsample || o.extrapolate != 1) {
-        fprintf(stderr, "scale_factor != 1, subsampling = 1 and extrapolate_point_cloud != 1 are not built yet (DESIGN.md 1)\n");
+    if (o.scale_factor != 1.f || o.extrapolate != 1) {
+        fprintf(stderr, "scale_factor != 1 and extrapolate_point_cloud != 1 are not built yet (DESIGN.md 1)\n");
         return 1;
     }
     unsigned max_files = 0;
@@ -266,6 +266,7 @@ int main(int argc, const char **argv) {
     const size_t N = (size_t)W * H;
     svb_params p;
     svb_default_params(SVB_PIPELINE, &p);  // generateDisparityMap()'s preset (stereo_vision.cu:315-319)
+    p.subsampling = o.subsample ? 1 : 0;    // -s 1: half-resolution matching (the map fills the first quarter of the float buffer)
     printf("Post Process only left = %d, Subsampling = %d\n", p.postprocess_only_left, p.subsampling);
     svb_context *ctx = svb_create(&p, W, H, 1, -1);
     svb_calibration cal;

@@ -120,7 +120,7 @@ bool env_flag(const char *name) {
 }
 
 // externalInit() (stereo_vision.cu:506-572) without OpenCV / YOLO / GL
-void external_init(int width, int height, bool graphics, bool display, bool trackObjects, float scale, const char *yaml) {
+void external_init(int width, int height, bool graphics, bool display, bool trackObjects, float scale, const char *yaml, bool subsampling) {
     g.initialised = true;
     g.width = width;
     g.height = height;
@@ -152,6 +152,10 @@ void external_init(int width, int height, bool graphics, bool display, bool trac
     // generateDisparityMap()'s preset (stereo_vision.cu:315-319)
     svb_params p;
     svb_default_params(SVB_PIPELINE, &p);
+    // `static int res = printf(..., param.subsampling = subsample)` latches the flag of the first frame (stereo_vision.cu:316-317).
+    // The half-size map then occupies the first quarter of the full-size float buffer that is converted and projected
+    // (leftdpf is width x height, :312-324): reproduced as is.
+    p.subsampling = subsampling ? 1 : 0;
     printf("Post Process only left = %d, Subsampling = %d\n", p.postprocess_only_left, p.subsampling);
     g.ctx = svb_create(&p, width, height, 1, -1);
     if (!g.ctx) {
@@ -176,14 +180,13 @@ sv_double3 *generatePointCloud(unsigned char *left, unsigned char *right, char *
     (void)YOLO_CFG;
     (void)YOLO_WEIGHTS;
     (void)YOLO_CLASSES;
-    if (!g.initialised) external_init(width, height, graphics, display, objectTracking, (float)scale, CAMERA_CALIBRATION_YAML);
     // sv.py passes 14 of the 16 arguments (sv.py:180): the last two are whatever the registers held
     if (!env_flag("SVB_TRUST_TAIL_ARGS")) {
         removeSky = false;
         subsampling = false;
     }
     (void)removeSky;  // dmapOLD.copyTo(dmapOLD, sky_mask) copies the map onto itself: no effect in the reference either
-    if (subsampling) fprintf(stderr, "generatePointCloud: subsampling is not implemented on this path; running at full resolution\n");
+    if (!g.initialised) external_init(width, height, graphics, display, objectTracking, (float)scale, CAMERA_CALIBRATION_YAML, subsampling);
     const auto t0 = std::chrono::steady_clock::now();
     if (!g.failed && left && right) {
         if (width != g.width || height != g.height) {

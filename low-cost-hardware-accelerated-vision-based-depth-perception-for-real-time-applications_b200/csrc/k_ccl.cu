@@ -173,18 +173,21 @@ __global__ void __launch_bounds__(128) k_ccl_prune(float *__restrict__ D_all, co
 
 int launch_remove_small_segments(const Dims &d, const svb_params &p, float *D, int32_t *labels, int32_t *sizes, int nimg, cudaStream_t s) {
     if (nimg <= 0) return SVB_OK;
-    dim3 grid((d.W + 127) / 128, d.H, nimg);
-    k_ccl_init<<<grid, 128, 0, s>>>(D, labels, sizes, d.W, d.H, p.speckle_sim_threshold);
+    const int W = d.Dw, H = d.Dh;
+    // elas.cpp:1017-1022: at half resolution a speckle is sqrt(speckle_size) * 2 pixels
+    const int min_size = d.sub ? (int)(sqrtf((float)p.speckle_size) * 2) : p.speckle_size;
+    dim3 grid((W + 127) / 128, H, nimg);
+    k_ccl_init<<<grid, 128, 0, s>>>(D, labels, sizes, W, H, p.speckle_sim_threshold);
     SVB_LAUNCH_CHECK();
-    if (d.H > 1) {
-        dim3 gm((d.W + 127) / 128, d.H - 1, nimg);
-        k_ccl_merge<<<gm, 128, 0, s>>>(D, labels, d.W, d.H, p.speckle_sim_threshold);
+    if (H > 1) {
+        dim3 gm((W + 127) / 128, H - 1, nimg);
+        k_ccl_merge<<<gm, 128, 0, s>>>(D, labels, W, H, p.speckle_sim_threshold);
         SVB_LAUNCH_CHECK();
     }
-    dim3 gc((d.W + 127) / 128, (d.H + CNT_ROWS - 1) / CNT_ROWS, nimg);
-    k_ccl_count<<<gc, 32 * CNT_ROWS, 0, s>>>(labels, sizes, d.W, d.H);
+    dim3 gc((W + 127) / 128, (H + CNT_ROWS - 1) / CNT_ROWS, nimg);
+    k_ccl_count<<<gc, 32 * CNT_ROWS, 0, s>>>(labels, sizes, W, H);
     SVB_LAUNCH_CHECK();
-    k_ccl_prune<<<grid, 128, 0, s>>>(D, labels, sizes, d.W, d.H, p.speckle_size);
+    k_ccl_prune<<<grid, 128, 0, s>>>(D, labels, sizes, W, H, min_size);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

@@ -26,7 +26,8 @@ struct DenseArgs {
     const uint32_t *grid[2];
     float *D[2];
     int W, H, maxT, gw, gh, gwords, grid_size, disp_max, match_texture, plane_radius;
-    int row0;  // first image row of the launch (0, or the start of this device's band)
+    int row0;  // first map row of the launch (0, or the start of this device's band)
+    int Dw, DN, shift;  // disparity map width / size and log2 of the pixel step (1 with subsampling: map pixel (x,y) = image (2x,2y))
     unsigned grid_magic;  // ceil(2^32 / grid_size)
     int P[8];
 };
@@ -70,14 +71,15 @@ __device__ __forceinline__ uint32_t range_mask(int lo, int hi, int base) {
 // front); RADIUS == 0: generic radius from the arguments.
 template <int SIDE, int RADIUS>
 __device__ __forceinline__ void dense_body(const DenseArgs &a) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = a.row0 + blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;  // map pixel
+    const int y = a.row0 + blockIdx.y;
+    const int u = x << a.shift, v = y << a.shift;         // image pixel (elas.cpp:707-711: d_addr = (u/2, v/2) when subsampling)
     const int f = blockIdx.z >> 1;
     const int W = a.W, H = a.H;
     const size_t N = (size_t)W * H;
-    const bool in = u < W;
-    const size_t pix = (size_t)v * W + (in ? u : 0);
-    float *D = a.D[SIDE] + (size_t)f * N;
+    const bool in = x < a.Dw;
+    const size_t pix = (size_t)y * a.Dw + (in ? x : 0);
+    float *D = a.D[SIDE] + (size_t)f * a.DN;
 
     const int row = max(min(v, H - 3), 2);  // elas.cpp:718
     const uint4 *own = reinterpret_cast<const uint4 *>(a.desc[SIDE]) + (size_t)f * N + (size_t)row * W;
@@ -90,7 +92,7 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     uint4 c = make_uint4(0, 0, 0, 0);
     int o = -1;
     if (in) {
-        o = a.owner[SIDE][(size_t)f * N + pix];
+        o = a.owner[SIDE][(size_t)f * a.DN + pix];
         if (o >= 0 && u >= 2 && u < W - 2) {  // elas.cpp:714
             c = __ldg(own + u);
             const uint4 k128 = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
@@ -230,7 +232,15 @@ int launch_dense_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, 
     a.plane_radius = d.plane_radius;
     for (int i = 0; i < 8; i++) a.P[i] = d.P[i];
     a.row0 = row0;
-    dim3 grid((d.W + 127) / 128, row1 - row0, nf * 2);
+    a.Dw = d.Dw;
+    a.DN = d.DN;
+    a.shift = d.sub ? 1 : 0;
+    if (d.sub && (row0 != 0 || row1 != d.H)) {
+        set_error("row-band dense matching with subsampling is not supported");
+        return SVB_ERR_UNSUPPORTED;
+    }
+    const int rows = d.sub ? d.Dh : row1 - row0;
+    dim3 grid((d.Dw + 127) / 128, rows, nf * 2);
     if (d.plane_radius == 2)
         k_dense<2><<<grid, 128, 0, s>>>(a);
     else if (d.plane_radius == 3)

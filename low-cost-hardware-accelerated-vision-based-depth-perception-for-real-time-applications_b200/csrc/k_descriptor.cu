@@ -29,7 +29,7 @@ constexpr int NT = 256;
 
 __device__ __forceinline__ int sat_u8(int x) { return min(max(x, 0), 255); }
 
-__global__ void __launch_bounds__(NT) k_descriptor(const uint8_t *__restrict__ img, uint8_t *__restrict__ desc, int W, int H, int row0, int row1) {
+__global__ void __launch_bounds__(NT) k_descriptor(const uint8_t *__restrict__ img, uint8_t *__restrict__ desc, int W, int H, int row0, int row1, int half) {
     __shared__ uint8_t sI[TH + 6][TW + 6 + 2];
     __shared__ uint8_t sDu[TH + 4][TW + 4];
     __shared__ uint8_t sDv[TH + 2][TW + 2 + 2];
@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(NT) k_descriptor(const uint8_t *__restrict__ i
         int u = x0 + tx, v = y0 + ty;
         if (u >= W || v >= row1) continue;
         uint4 q = make_uint4(0u, 0u, 0u, 0u);
-        if (u >= 3 && u < W - 3 && v >= 3 && v < H - 3) {
+        // half resolution (descriptor.cpp:50-93): only rows v = 4, 6, ... < H-3 are produced, every other row is zero
+        if (u >= 3 && u < W - 3 && v >= 3 && v < H - 3 && (!half || (v >= 4 && (v & 1) == 0))) {
             const int a = ty + 2, b = tx + 2;  // du(v,u) = sDu[a][b]
             const int e = ty + 1, f = tx + 1;  // dv(v,u) = sDv[e][f]
             uint32_t c0 = sDu[a][b];
@@ -100,7 +101,7 @@ int launch_descriptor(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg
 int launch_descriptor_rows(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, int row0, int row1, cudaStream_t s) {
     if (nimg <= 0 || row1 <= row0) return SVB_OK;
     dim3 grid((d.W + TW - 1) / TW, (row1 - row0 + TH - 1) / TH, nimg);
-    k_descriptor<<<grid, NT, 0, s>>>(img, desc, d.W, d.H, row0, row1);
+    k_descriptor<<<grid, NT, 0, s>>>(img, desc, d.W, d.H, row0, row1, d.sub);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

@@ -12,7 +12,7 @@ namespace {
 // ---- L/R check ------------------------------------------------------------------------------------
 // grid: (ceil(W/256), H, nf).  Out of place: the reference works on copies of both maps (elas.cpp:956-959).
 __global__ void __launch_bounds__(256) k_lr_check(const float *__restrict__ D1in, const float *__restrict__ D2in, float *__restrict__ D1out,
-                                                 float *__restrict__ D2out, int W, int H, float lr_threshold, int row0) {
+                                                 float *__restrict__ D2out, int W, int H, float lr_threshold, int row0, int half) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= W) return;
     const size_t base = ((size_t)blockIdx.z * H + row0 + blockIdx.y) * W;
@@ -20,12 +20,13 @@ __global__ void __launch_bounds__(256) k_lr_check(const float *__restrict__ D1in
     const float d2 = D2in[base + u];
     const float fw = (float)W;
     float o1 = -10.f, o2 = -10.f;
-    const float uw1 = __fsub_rn((float)u, d1);
+    // subsampling (elas.cpp:972-975): the maps are half size, the disparities are not: warp by d/2
+    const float uw1 = __fsub_rn((float)u, half ? __fdiv_rn(d1, 2.f) : d1);
     if (d1 >= 0.f && uw1 >= 0.f && uw1 < fw) {
         const float other = D2in[base + (int)uw1];
         o1 = (fabsf(__fsub_rn(other, d1)) > lr_threshold) ? -10.f : d1;
     }
-    const float uw2 = __fadd_rn((float)u, d2);
+    const float uw2 = __fadd_rn((float)u, half ? __fdiv_rn(d2, 2.f) : d2);
     if (d2 >= 0.f && uw2 >= 0.f && uw2 < fw) {
         const float other = D1in[base + (int)uw2];
         o2 = (fabsf(__fsub_rn(other, d2)) > lr_threshold) ? -10.f : d2;
@@ -114,9 +115,10 @@ __global__ void __launch_bounds__(GAP_WARPS * 32) k_gap_rows(float *__restrict__
 // gap, elas.cpp:1220-1293), so the sequential walk and this formulation agree exactly.
 constexpr int GC_WARPS = 8;
 
-// GC_COLS (runtime: 16, or 8 for very tall frames so that the strip still fits in shared memory) columns per CTA
+// GC_COLS columns per CTA: 16, or 8 for very tall frames so that the strip still fits in shared memory
+template <int GC_COLS>
 __global__ void __launch_bounds__(GC_WARPS * 32) k_gap_cols_strip(float *__restrict__ D_all, int W, int H, int gap_width, int add_corners,
-                                                                  int Hpad, int GC_COLS) {
+                                                                  int Hpad) {
     extern __shared__ float s_gc[];  // [H][GC_COLS + 1] floats, then GC_WARPS * Hpad ints
     float *strip = s_gc;
     int *prev_all = reinterpret_cast<int *>(s_gc + (size_t)H * (GC_COLS + 1));
@@ -272,6 +274,80 @@ __global__ void __launch_bounds__(128) k_mean_v(const float *__restrict__ tmp_al
     if (r0 + 3 >= 4 && r0 + 3 <= H - 4 && mean8<MODE, 3>(x, &r)) D_all[img + (size_t)(r0 + 3) * W + u] = r;
 }
 
+// Half-resolution variant (subsampling, elas.cpp:1334-1400): 4 taps c-2 .. c+1, ring slots = coordinate mod 4, the four
+// terms are added in slot order ((t0 + t1) + t2) + t3.  x[0..6] = values at coordinates c0-2 .. c0+4, c0 % 4 == 0.
+template <int MODE, int J>
+__device__ __forceinline__ bool mean4(const float (&x)[7], float *out) {
+    const float xc = x[J + 2];
+    float wsl[4], fsl[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        // window element i sits at coordinate c0 - 2 + J + i, i.e. slot (J + i + 2) mod 4
+        const int slot = (J + i + 2) & 3;
+        const float w = mean_weight<MODE>(x[J + i], xc);
+        wsl[slot] = w;
+        fsl[slot] = __fmul_rn(x[J + i], w);
+    }
+    const float weight_sum = __fadd_rn(__fadd_rn(__fadd_rn(wsl[0], wsl[1]), wsl[2]), wsl[3]);
+    const float factor_sum = __fadd_rn(__fadd_rn(__fadd_rn(fsl[0], fsl[1]), fsl[2]), fsl[3]);
+    if (weight_sum > 0.f) {
+        const float d = __fdiv_rn(factor_sum, weight_sum);
+        if (d >= 0.f) {
+            *out = d;
+            return true;
+        }
+    }
+    return false;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_mean4_h(const float *__restrict__ D_all, float *__restrict__ tmp_all, int W, int H) {
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c0 >= W) return;
+    const int v = blockIdx.y;
+    const size_t base = ((size_t)blockIdx.z * H + v) * W;
+    const float *row = D_all + base;
+    float x[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        const int cc = c0 - 2 + k;
+        const float val = (cc >= 0 && cc < W) ? row[cc] : -10.f;
+        x[k] = val < 0.f ? -10.f : val;
+    }
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[j] = x[j + 2] < 0.f ? -10.f : 0.f;
+    if (v >= 3 && v < H - 3) {  // centre c = u - 1 for u = 3 .. W-1
+        float r;
+        if (c0 + 0 >= 2 && c0 + 0 <= W - 2 && mean4<MODE, 0>(x, &r)) out[0] = r;
+        if (c0 + 1 >= 2 && c0 + 1 <= W - 2 && mean4<MODE, 1>(x, &r)) out[1] = r;
+        if (c0 + 2 >= 2 && c0 + 2 <= W - 2 && mean4<MODE, 2>(x, &r)) out[2] = r;
+        if (c0 + 3 >= 2 && c0 + 3 <= W - 2 && mean4<MODE, 3>(x, &r)) out[3] = r;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (c0 + j < W) tmp_all[base + c0 + j] = out[j];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_mean4_v(const float *__restrict__ tmp_all, float *__restrict__ D_all, int W, int H) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < 3 || u >= W - 3) return;
+    const int r0 = blockIdx.y * 4;
+    const size_t img = (size_t)blockIdx.z * H * W;
+    float x[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        const int rr = r0 - 2 + k;
+        x[k] = (rr >= 0 && rr < H) ? tmp_all[img + (size_t)rr * W + u] : -10.f;
+    }
+    float r;
+    if (r0 + 0 >= 2 && r0 + 0 <= H - 2 && mean4<MODE, 0>(x, &r)) D_all[img + (size_t)(r0 + 0) * W + u] = r;
+    if (r0 + 1 >= 2 && r0 + 1 <= H - 2 && mean4<MODE, 1>(x, &r)) D_all[img + (size_t)(r0 + 1) * W + u] = r;
+    if (r0 + 2 >= 2 && r0 + 2 <= H - 2 && mean4<MODE, 2>(x, &r)) D_all[img + (size_t)(r0 + 2) * W + u] = r;
+    if (r0 + 3 >= 2 && r0 + 3 <= H - 2 && mean4<MODE, 3>(x, &r)) D_all[img + (size_t)(r0 + 3) * W + u] = r;
+}
+
 // ---- median -------------------------------------------------------------------------------------------
 // Median of 7 by a 13-exchange selection network (the reference sorts with an insertion sort, elas.cpp:1519-1528;
 // the median is a selection, so any correct method gives the same value; the inputs are never NaN).
@@ -347,17 +423,23 @@ int launch_lr_check(const Dims &d, const svb_params &p, const float *D1in, const
 int launch_lr_check_rows(const Dims &d, const svb_params &p, const float *D1in, const float *D2in, float *D1out, float *D2out, int nf, int row0,
                          int row1, cudaStream_t s) {
     if (nf <= 0 || row1 <= row0) return SVB_OK;
-    dim3 grid((d.W + 255) / 256, row1 - row0, nf);
-    k_lr_check<<<grid, 256, 0, s>>>(D1in, D2in, D1out, D2out, d.W, d.H, (float)p.lr_threshold, row0);
+    if (d.sub) {
+        row0 = 0;
+        row1 = d.Dh;
+    }
+    dim3 grid((d.Dw + 255) / 256, row1 - row0, nf);
+    k_lr_check<<<grid, 256, 0, s>>>(D1in, D2in, D1out, D2out, d.Dw, d.Dh, (float)p.lr_threshold, row0, d.sub);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }
 
 int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s) {
     if (nimg <= 0) return SVB_OK;
-    const int Wpad = (d.W + 31) & ~31;
+    const int W = d.Dw, H = d.Dh;
+    const int gap_width = d.sub ? p.ipol_gap_width / 2 + 1 : p.ipol_gap_width;  // elas.cpp:1131-1135
+    const int Wpad = (W + 31) & ~31;
     {
-        dim3 grid((d.H + GAP_WARPS - 1) / GAP_WARPS, nimg);
+        dim3 grid((H + GAP_WARPS - 1) / GAP_WARPS, nimg);
         const size_t smem_rows = (size_t)GAP_WARPS * Wpad * sizeof(int);
         if (smem_rows > 48 * 1024) {  // 4K-wide rows: opt in to large dynamic shared memory
             cudaError_t e = cudaFuncSetAttribute(k_gap_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows);
@@ -366,32 +448,36 @@ int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStrea
                 return SVB_ERR_CUDA;
             }
         }
-        k_gap_rows<<<grid, GAP_WARPS * 32, smem_rows, s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners, Wpad);
+        k_gap_rows<<<grid, GAP_WARPS * 32, smem_rows, s>>>(D, W, H, gap_width, p.add_corners, Wpad);
         SVB_LAUNCH_CHECK();
     }
-    const int Hpad = (d.H + 31) & ~31;
+    const int Hpad = (H + 31) & ~31;
     int GC_COLS = 16;
-    size_t smem = (size_t)d.H * (GC_COLS + 1) * sizeof(float) + (size_t)GC_WARPS * Hpad * sizeof(int);
+    size_t smem = (size_t)H * (GC_COLS + 1) * sizeof(float) + (size_t)GC_WARPS * Hpad * sizeof(int);
     if (smem > 200 * 1024) {
         GC_COLS = 8;
-        smem = (size_t)d.H * (GC_COLS + 1) * sizeof(float) + (size_t)GC_WARPS * Hpad * sizeof(int);
+        smem = (size_t)H * (GC_COLS + 1) * sizeof(float) + (size_t)GC_WARPS * Hpad * sizeof(int);
     }
     if (smem <= 200 * 1024) {
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(k_gap_cols_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = GC_COLS == 16 ? cudaFuncSetAttribute(k_gap_cols_strip<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                          : cudaFuncSetAttribute(k_gap_cols_strip<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) {
                 set_error("cudaFuncSetAttribute(k_gap_cols_strip): %s", cudaGetErrorString(e));
                 return SVB_ERR_CUDA;
             }
         }
-        dim3 grid((d.W + GC_COLS - 1) / GC_COLS, nimg);
-        k_gap_cols_strip<<<grid, GC_WARPS * 32, smem, s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners, Hpad, GC_COLS);
+        dim3 grid((W + GC_COLS - 1) / GC_COLS, nimg);
+        if (GC_COLS == 16)
+            k_gap_cols_strip<16><<<grid, GC_WARPS * 32, smem, s>>>(D, W, H, gap_width, p.add_corners, Hpad);
+        else
+            k_gap_cols_strip<8><<<grid, GC_WARPS * 32, smem, s>>>(D, W, H, gap_width, p.add_corners, Hpad);
         SVB_LAUNCH_CHECK();
         return SVB_OK;
     }
     {
-        dim3 grid((d.W + 127) / 128, nimg);
-        k_gap_cols<<<grid, 128, 0, s>>>(D, d.W, d.H, p.ipol_gap_width, p.add_corners);
+        dim3 grid((W + 127) / 128, nimg);
+        k_gap_cols<<<grid, 128, 0, s>>>(D, W, H, gap_width, p.add_corners);
         SVB_LAUNCH_CHECK();
     }
     return SVB_OK;
@@ -399,17 +485,32 @@ int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStrea
 
 int launch_adaptive_mean(const Dims &d, int mean_mode, float *D, float *tmp, int nimg, cudaStream_t s) {
     if (nimg <= 0) return SVB_OK;
-    const dim3 gh(((d.W + 3) / 4 + 127) / 128, d.H, nimg);
-    const dim3 gv((d.W + 127) / 128, (d.H + 3) / 4, nimg);
-    if (mean_mode == SVB_MEAN_TRUE_ABS) {
-        k_mean_h<1><<<gh, 128, 0, s>>>(D, tmp, d.W, d.H);
+    const int W = d.Dw, H = d.Dh;
+    const dim3 gh(((W + 3) / 4 + 127) / 128, H, nimg);
+    const dim3 gv((W + 127) / 128, (H + 3) / 4, nimg);
+    const bool true_abs = mean_mode == SVB_MEAN_TRUE_ABS;
+    if (d.sub) {
+        if (true_abs) {
+            k_mean4_h<1><<<gh, 128, 0, s>>>(D, tmp, W, H);
+            SVB_LAUNCH_CHECK();
+            k_mean4_v<1><<<gv, 128, 0, s>>>(tmp, D, W, H);
+        } else {
+            k_mean4_h<0><<<gh, 128, 0, s>>>(D, tmp, W, H);
+            SVB_LAUNCH_CHECK();
+            k_mean4_v<0><<<gv, 128, 0, s>>>(tmp, D, W, H);
+        }
         SVB_LAUNCH_CHECK();
-        k_mean_v<1><<<gv, 128, 0, s>>>(tmp, D, d.W, d.H);
+        return SVB_OK;
+    }
+    if (true_abs) {
+        k_mean_h<1><<<gh, 128, 0, s>>>(D, tmp, W, H);
+        SVB_LAUNCH_CHECK();
+        k_mean_v<1><<<gv, 128, 0, s>>>(tmp, D, W, H);
         SVB_LAUNCH_CHECK();
     } else {
-        k_mean_h<0><<<gh, 128, 0, s>>>(D, tmp, d.W, d.H);
+        k_mean_h<0><<<gh, 128, 0, s>>>(D, tmp, W, H);
         SVB_LAUNCH_CHECK();
-        k_mean_v<0><<<gv, 128, 0, s>>>(tmp, D, d.W, d.H);
+        k_mean_v<0><<<gv, 128, 0, s>>>(tmp, D, W, H);
         SVB_LAUNCH_CHECK();
     }
     return SVB_OK;
@@ -417,11 +518,12 @@ int launch_adaptive_mean(const Dims &d, int mean_mode, float *D, float *tmp, int
 
 int launch_median(const Dims &d, float *D, float *tmp, int nimg, cudaStream_t s) {
     if (nimg <= 0) return SVB_OK;
-    const dim3 gh(((d.W + 3) / 4 + 127) / 128, d.H, nimg);
-    const dim3 gv((d.W + 127) / 128, (d.H + 3) / 4, nimg);
-    k_median_h<<<gh, 128, 0, s>>>(D, tmp, d.W, d.H);
+    const int W = d.Dw, H = d.Dh;
+    const dim3 gh(((W + 3) / 4 + 127) / 128, H, nimg);
+    const dim3 gv((W + 127) / 128, (H + 3) / 4, nimg);
+    k_median_h<<<gh, 128, 0, s>>>(D, tmp, W, H);
     SVB_LAUNCH_CHECK();
-    k_median_v<<<gv, 128, 0, s>>>(tmp, D, d.W, d.H);
+    k_median_v<<<gv, 128, 0, s>>>(tmp, D, W, H);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

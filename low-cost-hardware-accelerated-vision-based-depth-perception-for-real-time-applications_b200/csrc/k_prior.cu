@@ -188,14 +188,14 @@ __device__ __forceinline__ int f2u_as_int_x86(float x) {
 __global__ void __launch_bounds__(128) k_raster(const int32_t *__restrict__ support_all, const int32_t *__restrict__ tri1_all,
                                                const int32_t *__restrict__ tri2_all, const int32_t *__restrict__ ntri_all,
                                                const int32_t *__restrict__ trioff_all, int32_t *__restrict__ owner1_all,
-                                               int32_t *__restrict__ owner2_all, int W, int H, int maxS, int row0, int row1) {
+                                               int32_t *__restrict__ owner2_all, int W, int H, int maxS, int row0, int row1, int sub, int Dw, int Dh) {
     const int f = blockIdx.z, side = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (i >= ntri_all[2 * f + side]) return;
     const int32_t *support = support_all + (size_t)f * maxS * 3;
     const int32_t *tri = (side ? tri2_all : tri1_all) + ((size_t)trioff_all[f] + i) * 3;
-    int32_t *owner = (side ? owner2_all : owner1_all) + (size_t)f * W * H;
+    int32_t *owner = (side ? owner2_all : owner1_all) + (size_t)f * Dw * Dh;  // owner map has the disparity map's size
 
     float tu[3], tv[3];
 #pragma unroll
@@ -235,13 +235,20 @@ __global__ void __launch_bounds__(128) k_raster(const int32_t *__restrict__ supp
         if (i0 == i1) continue;
         const float la = part ? BC_a : AB_a, lb = part ? BC_b : AB_b;
         const int u_lo = max(i0, 0), u_hi = min(i1, W);
-        for (int u = u_lo + lane; u < u_hi; u += 32) {
+        // subsampling (elas.cpp:915-934): only even columns and even rows are matched; pixel (u, v) lives at (u/2, v/2)
+        const int ustep = sub ? 2 : 1;
+        for (int u = ((u_lo + ustep - 1) & ~(ustep - 1)) + lane * ustep; u < u_hi; u += 32 * ustep) {
             const float fu = (float)u;
             const int v_1 = f2u_as_int_x86(__fadd_rn(__fmul_rn(AC_a, fu), AC_b));
             const int v_2 = f2u_as_int_x86(__fadd_rn(__fmul_rn(la, fu), lb));
             // rows are clipped to [row0, row1): the whole image, or this device's band in the row-band split
             const int v_lo = max(max(min(v_1, v_2), 0), row0), v_hi = min(min(max(v_1, v_2), H), row1);
-            for (int v = v_lo; v < v_hi; v++) atomicMax(owner + (size_t)v * W + u, i);
+            if (!sub) {
+                for (int v = v_lo; v < v_hi; v++) atomicMax(owner + (size_t)v * W + u, i);
+            } else if ((u >> 1) < Dw) {
+                for (int v = (v_lo + 1) & ~1; v < v_hi; v += 2)
+                    if ((v >> 1) < Dh) atomicMax(owner + (size_t)(v >> 1) * Dw + (u >> 1), i);
+            }
         }
     }
 }
@@ -299,8 +306,11 @@ int launch_raster_rows(const Dims &d, const int32_t *support, const int32_t *tri
     if (max_tri > d.maxT) max_tri = d.maxT;
     cudaError_t e = cudaSuccess;
     if (row0 == 0 && row1 == d.H) {
-        e = cudaMemsetAsync(owner1, 0xFF, (size_t)nf * d.N * sizeof(int32_t), s);
-        if (e == cudaSuccess) e = cudaMemsetAsync(owner2, 0xFF, (size_t)nf * d.N * sizeof(int32_t), s);
+        e = cudaMemsetAsync(owner1, 0xFF, (size_t)nf * d.DN * sizeof(int32_t), s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(owner2, 0xFF, (size_t)nf * d.DN * sizeof(int32_t), s);
+    } else if (d.sub) {
+        set_error("row-band raster with subsampling is not supported");
+        return SVB_ERR_UNSUPPORTED;
     } else {
         for (int f = 0; f < nf && e == cudaSuccess; f++) {
             const size_t off = (size_t)f * d.N + (size_t)row0 * d.W, cnt = (size_t)(row1 - row0) * d.W * sizeof(int32_t);
@@ -314,7 +324,7 @@ int launch_raster_rows(const Dims &d, const int32_t *support, const int32_t *tri
     }
     if (max_tri <= 0) return SVB_OK;
     dim3 grid((max_tri + 3) / 4, 2, nf);
-    k_raster<<<grid, 128, 0, s>>>(support, tri1, tri2, ntri, trioff, owner1, owner2, d.W, d.H, d.maxS, row0, row1);
+    k_raster<<<grid, 128, 0, s>>>(support, tri1, tri2, ntri, trioff, owner1, owner2, d.W, d.H, d.maxS, row0, row1, d.sub, d.Dw, d.Dh);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

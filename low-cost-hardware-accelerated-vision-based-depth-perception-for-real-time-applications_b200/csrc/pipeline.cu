@@ -41,10 +41,6 @@ int make_dims(const svb_params &p, int W, int H, Dims *out) {
         set_error("unsupported image size %dx%d", W, H);
         return SVB_ERR_ARG;
     }
-    if (p.subsampling) {
-        set_error("subsampling=1 is not implemented yet (SURVEY.md 8f rank 3)");
-        return SVB_ERR_UNSUPPORTED;
-    }
     if (p.disp_max < 0 || p.disp_max > 4095 || p.grid_size < 1 || p.candidate_stepsize < 1) {
         set_error("invalid parameters (disp_max=%d grid_size=%d candidate_stepsize=%d)", p.disp_max, p.grid_size, p.candidate_stepsize);
         return SVB_ERR_ARG;
@@ -56,7 +52,12 @@ int make_dims(const svb_params &p, int W, int H, Dims *out) {
     d.W = W;
     d.H = H;
     d.N = W * H;
+    d.sub = p.subsampling ? 1 : 0;
+    d.Dw = d.sub ? W / 2 : W;
+    d.Dh = d.sub ? H / 2 : H;
+    d.DN = d.Dw * d.Dh;
     d.step = p.candidate_stepsize;
+    if (d.sub) d.step += d.step % 2;  // elas.cpp:376-378: at half resolution only every second descriptor row exists
     d.cw = (W + d.step - 1) / d.step;  // elas.cpp:383-386
     d.ch = (H + d.step - 1) / d.step;
     d.gw = (int)ceil((float)W / (float)p.grid_size);  // elas.cpp:88-89
@@ -119,7 +120,13 @@ int lane_create(svb_context *c, Lane &L) {
     SVB_CUDA(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
     for (int s = 0; s < 2; s++) {
         SVB_TRY(dev_alloc(&L.img[s], C * N));
-        SVB_TRY(dev_alloc(&L.desc[s], C * N * 16));
+        {
+            // zero-filled guard bands of (disp_max + W + 1024) descriptors in front of and behind the descriptor arena
+            const size_t pad = ((size_t)c->p.disp_max + d.W + 1024) * 16;
+            SVB_TRY(dev_alloc(&L.desc_base[s], C * N * 16 + 2 * pad));
+            SVB_CUDA(cudaMemset(L.desc_base[s], 0, C * N * 16 + 2 * pad));
+            L.desc[s] = L.desc_base[s] + pad;
+        }
         SVB_TRY(dev_alloc(&L.tri[s], C * d.maxT * 3));
         SVB_TRY(dev_alloc(&L.rec[s], C * d.maxT));
         SVB_TRY(dev_alloc(&L.grid[s], C * d.gw * d.gh * d.gwords));
@@ -135,6 +142,7 @@ int lane_create(svb_context *c, Lane &L) {
     SVB_TRY(dev_alloc(&L.grid_tmp, C * 2 * d.gw * d.gh * d.gwords));
     SVB_TRY(dev_alloc(&L.Draw, 2 * C * N));
     SVB_TRY(dev_alloc(&L.Dlr, 2 * C * N));
+    SVB_CUDA(cudaMemset(L.Dlr, 0, 2 * C * N * sizeof(float)));  // with subsampling only the first DN floats of a map are ever written
     SVB_TRY(dev_alloc(&L.Dtmp, 2 * C * N));
     SVB_TRY(dev_alloc(&L.labels, 2 * C * N));
     SVB_TRY(dev_alloc(&L.sizes, 2 * C * N));
@@ -148,7 +156,7 @@ int lane_create(svb_context *c, Lane &L) {
 void lane_destroy(Lane &L) {
     for (int s = 0; s < 2; s++) {
         cudaFree(L.img[s]);
-        cudaFree(L.desc[s]);
+        cudaFree(L.desc_base[s]);
         cudaFree(L.tri[s]);
         cudaFree(L.rec[s]);
         cudaFree(L.grid[s]);
@@ -322,7 +330,7 @@ namespace {
 int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, StageEvents *se) {
     const Dims &d = c->d;
     const svb_params &p = c->p;
-    const size_t N = (size_t)d.N, C = (size_t)c->chunk;
+    const size_t N = (size_t)d.N, C = (size_t)c->chunk, DN = (size_t)d.DN;
     StageTimer T(L, se);
     int max_tri = 0, max_support = 0;
     for (int i = 0; i < 2 * nf; i++) max_tri = L.h_ntri[i] > max_tri ? L.h_ntri[i] : max_tri;
@@ -350,10 +358,10 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, 
     const bool need_d2 = both || c->tap_mode || (out_D1 == nullptr && out_points == nullptr);
     SVB_TRY(launch_lr_check(d, p, D1raw, D2raw, D1, need_d2 ? D2 : nullptr, nf, L.stream));
     if (c->tap_mode && nf == 1) {
-        SVB_TRY(tap_store(c, "D1raw", D1raw, N * 4, L.stream));
-        SVB_TRY(tap_store(c, "D2raw", D2raw, N * 4, L.stream));
-        SVB_TRY(tap_store(c, "D1lr", D1, N * 4, L.stream));
-        SVB_TRY(tap_store(c, "D2lr", D2, N * 4, L.stream));
+        SVB_TRY(tap_store(c, "D1raw", D1raw, DN * 4, L.stream));
+        SVB_TRY(tap_store(c, "D2raw", D2raw, DN * 4, L.stream));
+        SVB_TRY(tap_store(c, "D1lr", D1, DN * 4, L.stream));
+        SVB_TRY(tap_store(c, "D2lr", D2, DN * 4, L.stream));
     }
     // post-processing chain; when both maps are processed they are handled as 2*nf independent images, which
     // needs the left and right blocks to be adjacent: true when nf == chunk, otherwise run the sides separately
@@ -361,33 +369,33 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, 
     SVB_TRY(T.mark(ST_SEGMENTS));
     for (int s = 0; s < passes; s++) SVB_TRY(launch_remove_small_segments(d, p, s ? D2 : D1, L.labels, L.sizes, nf, L.stream));
     if (c->tap_mode && nf == 1) {
-        SVB_TRY(tap_store(c, "D1seg", D1, N * 4, L.stream));
-        if (both) SVB_TRY(tap_store(c, "D2seg", D2, N * 4, L.stream));
+        SVB_TRY(tap_store(c, "D1seg", D1, DN * 4, L.stream));
+        if (both) SVB_TRY(tap_store(c, "D2seg", D2, DN * 4, L.stream));
     }
     SVB_TRY(T.mark(ST_GAP));
     for (int s = 0; s < passes; s++) SVB_TRY(launch_gap(d, p, s ? D2 : D1, nf, L.stream));
     if (c->tap_mode && nf == 1) {
-        SVB_TRY(tap_store(c, "D1gap", D1, N * 4, L.stream));
-        if (both) SVB_TRY(tap_store(c, "D2gap", D2, N * 4, L.stream));
+        SVB_TRY(tap_store(c, "D1gap", D1, DN * 4, L.stream));
+        if (both) SVB_TRY(tap_store(c, "D2gap", D2, DN * 4, L.stream));
     }
     SVB_TRY(T.mark(ST_MEAN));
     if (p.filter_adaptive_mean) {
         for (int s = 0; s < passes; s++) SVB_TRY(launch_adaptive_mean(d, c->mean_mode, s ? D2 : D1, L.Dtmp, nf, L.stream));
         if (c->tap_mode && nf == 1) {
-            SVB_TRY(tap_store(c, "D1mean", D1, N * 4, L.stream));
-            if (both) SVB_TRY(tap_store(c, "D2mean", D2, N * 4, L.stream));
+            SVB_TRY(tap_store(c, "D1mean", D1, DN * 4, L.stream));
+            if (both) SVB_TRY(tap_store(c, "D2mean", D2, DN * 4, L.stream));
         }
     }
     SVB_TRY(T.mark(ST_MEDIAN));
     if (p.filter_median) {
         for (int s = 0; s < passes; s++) SVB_TRY(launch_median(d, s ? D2 : D1, L.Dtmp, nf, L.stream));
         if (c->tap_mode && nf == 1) {
-            SVB_TRY(tap_store(c, "D1med", D1, N * 4, L.stream));
-            if (both) SVB_TRY(tap_store(c, "D2med", D2, N * 4, L.stream));
+            SVB_TRY(tap_store(c, "D1med", D1, DN * 4, L.stream));
+            if (both) SVB_TRY(tap_store(c, "D2med", D2, DN * 4, L.stream));
         }
     }
     SVB_TRY(T.mark(ST_REPROJECT));
-    if (out_D1) SVB_CUDA(cudaMemcpyAsync(out_D1, D1, N * 4 * nf, cudaMemcpyDeviceToDevice, L.stream));
+    if (out_D1) SVB_CUDA(cudaMemcpyAsync(out_D1, D1, DN * 4 * nf, cudaMemcpyDeviceToDevice, L.stream));
     if (out_points) SVB_TRY(launch_reproject(d, c->calib, D1, L.dmap, out_points, nf, L.stream));
     SVB_TRY(T.mark(ST_COUNT));
     if (se) se->b_done = true;
@@ -647,8 +655,8 @@ int svb_process(svb_context *c, const uint8_t *I1, const uint8_t *I2, int stride
         SVB_TRY(tap_store(c, "tri2", L.tri[1], (size_t)L.h_ntri[1] * 12, L.stream));
         SVB_TRY(tap_store(c, "planes1", c->planes_ref[0], (size_t)L.h_ntri[0] * 24, L.stream));
         SVB_TRY(tap_store(c, "planes2", c->planes_ref[1], (size_t)L.h_ntri[1] * 24, L.stream));
-        SVB_TRY(tap_store(c, "owner1", L.owner[0], N * 4, L.stream));
-        SVB_TRY(tap_store(c, "owner2", L.owner[1], N * 4, L.stream));
+        SVB_TRY(tap_store(c, "owner1", L.owner[0], (size_t)d.DN * 4, L.stream));
+        SVB_TRY(tap_store(c, "owner2", L.owner[1], (size_t)d.DN * 4, L.stream));
         // grids in the reference's list layout
         const size_t gbytes = (size_t)d.gw * d.gh * (c->p.disp_max + 2) * 4;
         for (int s = 0; s < 2; s++) {
@@ -661,8 +669,9 @@ int svb_process(svb_context *c, const uint8_t *I1, const uint8_t *I2, int stride
             SVB_TRY(r);
         }
     }
-    SVB_CUDA(cudaMemcpyAsync(D1, L.Dlr, N * 4, cudaMemcpyDeviceToHost, L.stream));
-    SVB_CUDA(cudaMemcpyAsync(D2, L.Dlr + C * N, N * 4, cudaMemcpyDeviceToHost, L.stream));
+    // D1 / D2 are (W/2) x (H/2) with subsampling (elas.h:157-160)
+    SVB_CUDA(cudaMemcpyAsync(D1, L.Dlr, (size_t)d.DN * 4, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(D2, L.Dlr + C * N, (size_t)d.DN * 4, cudaMemcpyDeviceToHost, L.stream));
     SVB_CUDA(cudaStreamSynchronize(L.stream));
     stage_events_collect(c);
     c->stats.kernel_launches = g_launch_counter;
@@ -796,7 +805,7 @@ int svb_stage_disparity(svb_context *c, const int32_t *support, int n, const int
     SVB_TRY(launch_raster(d, L.support, L.tri[0], L.tri[1], L.ntri, L.trioff, L.owner[0], L.owner[1], 1, m, L.stream));
     SVB_TRY(launch_dense(d, c->p, L.desc[0], L.desc[1], L.owner[0], L.owner[1], L.rec[0], L.rec[1], L.grid[0], L.grid[1], L.Draw, L.Draw + C * N,
                          1, L.stream));
-    SVB_CUDA(cudaMemcpyAsync(D, right_image ? L.Draw + C * N : L.Draw, N * 4, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(D, right_image ? L.Draw + C * N : L.Draw, (size_t)d.DN * 4, cudaMemcpyDeviceToHost, L.stream));
     SVB_CUDA(cudaStreamSynchronize(L.stream));
     return SVB_OK;
 }
@@ -805,11 +814,12 @@ int svb_stage_lr_check(svb_context *c, float *D1, float *D2) {
     STAGE_PROLOG();
     if (!D1 || !D2) return SVB_ERR_ARG;
     const size_t C = (size_t)c->chunk;
-    SVB_CUDA(cudaMemcpyAsync(L.Draw, D1, N * 4, cudaMemcpyHostToDevice, L.stream));
-    SVB_CUDA(cudaMemcpyAsync(L.Draw + C * N, D2, N * 4, cudaMemcpyHostToDevice, L.stream));
+    const size_t DB = (size_t)d.DN * 4;
+    SVB_CUDA(cudaMemcpyAsync(L.Draw, D1, DB, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(L.Draw + C * N, D2, DB, cudaMemcpyHostToDevice, L.stream));
     SVB_TRY(launch_lr_check(d, c->p, L.Draw, L.Draw + C * N, L.Dlr, L.Dlr + C * N, 1, L.stream));
-    SVB_CUDA(cudaMemcpyAsync(D1, L.Dlr, N * 4, cudaMemcpyDeviceToHost, L.stream));
-    SVB_CUDA(cudaMemcpyAsync(D2, L.Dlr + C * N, N * 4, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(D1, L.Dlr, DB, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(D2, L.Dlr + C * N, DB, cudaMemcpyDeviceToHost, L.stream));
     SVB_CUDA(cudaStreamSynchronize(L.stream));
     return SVB_OK;
 }
@@ -817,12 +827,12 @@ int svb_stage_lr_check(svb_context *c, float *D1, float *D2) {
 static int stage_inplace(svb_context *c, float *D, int which) {
     STAGE_PROLOG();
     if (!D) return SVB_ERR_ARG;
-    SVB_CUDA(cudaMemcpyAsync(L.Dlr, D, N * 4, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(L.Dlr, D, (size_t)d.DN * 4, cudaMemcpyHostToDevice, L.stream));
     if (which == 0) SVB_TRY(launch_remove_small_segments(d, c->p, L.Dlr, L.labels, L.sizes, 1, L.stream));
     if (which == 1) SVB_TRY(launch_gap(d, c->p, L.Dlr, 1, L.stream));
     if (which == 2) SVB_TRY(launch_adaptive_mean(d, c->mean_mode, L.Dlr, L.Dtmp, 1, L.stream));
     if (which == 3) SVB_TRY(launch_median(d, L.Dlr, L.Dtmp, 1, L.stream));
-    SVB_CUDA(cudaMemcpyAsync(D, L.Dlr, N * 4, cudaMemcpyDeviceToHost, L.stream));
+    SVB_CUDA(cudaMemcpyAsync(D, L.Dlr, (size_t)d.DN * 4, cudaMemcpyDeviceToHost, L.stream));
     SVB_CUDA(cudaStreamSynchronize(L.stream));
     return SVB_OK;
 }
@@ -896,12 +906,17 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
     const int C = c->chunk;
     const bool from_host = h_left != nullptr;
     const bool want_D = (flags & SVB_OUT_DISPARITY) != 0, want_P = (flags & SVB_OUT_POINTS) != 0;
+    const size_t DN = (size_t)d.DN;
+    if (want_P && d.sub) {
+        set_error("batch: point clouds with subsampling are only defined for the single-frame generatePointCloud path");
+        return SVB_ERR_UNSUPPORTED;
+    }
     if (!want_D && !want_P) {
         set_error("batch: flags select no output");
         return SVB_ERR_ARG;
     }
     stats_reset(c);
-    if (want_D) SVB_TRY(ensure_store((void **)&c->out_D1, &c->out_D1_frames, n_frames, N * 4));
+    if (want_D) SVB_TRY(ensure_store((void **)&c->out_D1, &c->out_D1_frames, n_frames, DN * 4));
     if (want_P) SVB_TRY(ensure_store((void **)&c->out_points, &c->out_points_frames, n_frames, N * 24));
     const int nchunks = (n_frames + C - 1) / C;
     SVB_TRY(stage_events_prepare(c, nchunks));
@@ -929,10 +944,10 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
         Lane &L = c->lanes[k % LANES];
         const int nf = frames_of(k);
         SVB_TRY(stage_host(c, L, nf));
-        const size_t off = (size_t)k * C * N;
-        SVB_TRY(stage_b(c, L, nf, want_D ? c->out_D1 + off : nullptr, want_P ? c->out_points + off * 3 : nullptr, stage_events_of(c, k)));
+        const size_t off = (size_t)k * C * N, offD = (size_t)k * C * DN;
+        SVB_TRY(stage_b(c, L, nf, want_D ? c->out_D1 + offD : nullptr, want_P ? c->out_points + off * 3 : nullptr, stage_events_of(c, k)));
         if (from_host) {
-            if (want_D && h_D1) SVB_CUDA(cudaMemcpyAsync(h_D1 + off, c->out_D1 + off, nf * N * 4, cudaMemcpyDeviceToHost, L.stream));
+            if (want_D && h_D1) SVB_CUDA(cudaMemcpyAsync(h_D1 + offD, c->out_D1 + offD, nf * DN * 4, cudaMemcpyDeviceToHost, L.stream));
             if (want_P && h_points)
                 SVB_CUDA(cudaMemcpyAsync(h_points + off * 3, c->out_points + off * 3, nf * N * 24, cudaMemcpyDeviceToHost, L.stream));
         }
@@ -977,7 +992,7 @@ int svb_batch_run_host(svb_context *c, const uint8_t *left, const uint8_t *right
 int svb_batch_download_disparity(svb_context *c, int frame, float *out) {
     if (!c || !out || frame < 0 || (size_t)frame >= c->out_D1_frames || !c->out_D1) return SVB_ERR_ARG;
     SVB_CUDA(cudaSetDevice(c->device));
-    SVB_CUDA(cudaMemcpy(out, c->out_D1 + (size_t)frame * c->d.N, (size_t)c->d.N * 4, cudaMemcpyDeviceToHost));
+    SVB_CUDA(cudaMemcpy(out, c->out_D1 + (size_t)frame * c->d.DN, (size_t)c->d.DN * 4, cudaMemcpyDeviceToHost));
     return SVB_OK;
 }
 

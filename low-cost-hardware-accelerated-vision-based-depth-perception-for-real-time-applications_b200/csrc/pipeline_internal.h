@@ -20,7 +20,8 @@ struct Lane {
     cudaEvent_t ev_a = nullptr, ev_done = nullptr;
     // device
     uint8_t *img[2] = {nullptr, nullptr};
-    uint8_t *desc[2] = {nullptr, nullptr};
+    uint8_t *desc[2] = {nullptr, nullptr};       // = desc_base + padding: the dense matcher's unguarded loads may run a few
+    uint8_t *desc_base[2] = {nullptr, nullptr};  //   hundred descriptors past either end of the arena (k_dense.cu)
     int16_t *dcan_raw = nullptr, *dcan = nullptr;
     int32_t *support = nullptr, *nsupport = nullptr;
     int32_t *tri[2] = {nullptr, nullptr};

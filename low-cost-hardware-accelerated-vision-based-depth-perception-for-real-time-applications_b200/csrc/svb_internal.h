@@ -43,6 +43,8 @@ extern thread_local long long g_launch_counter;  // kernels launched by this lib
 // ---- geometry derived from (params, width, height) ---------------------------------------------
 struct Dims {
     int W, H, N;          // image size, N = W*H
+    int sub;              // param.subsampling: disparities only for even (u, v), maps are (W/2) x (H/2) (elas.h:81-83)
+    int Dw, Dh, DN;       // disparity map size: W x H, or W/2 x H/2 with subsampling; DN = Dw*Dh
     int step, cw, ch;     // candidate grid (elas.cpp:376-386)
     int gw, gh, gwords;   // disparity grid cells (elas.cpp:88-89) and 32-bit words per cell bitmask
     int maxS;             // capacity of the support list  ((cw-1)*(ch-1) + 6 corner points)
@@ -82,7 +84,7 @@ enum StageId {
 // k_descriptor.cu
 int launch_descriptor(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, cudaStream_t s);
 // *_rows variants restrict a stage to image rows [row0, row1) / lattice rows [vc0, vc1): the row-band split (band_split.cu)
-int launch_descriptor_rows(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, int row0, int row1, cudaStream_t s);
+int launch_descriptor_rows(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, int row0, int row1, cudaStream_t s);  // d.sub: even rows only
 // k_support.cu
 int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int nf,
                          cudaStream_t s);

@@ -15,6 +15,14 @@ def cmp_exact(a, b):
     return {"equal": n == 0, "mismatch": n, "size": int(a.size)}
 
 
+def half(a, ctx):
+    """The oracle is handed full-size buffers; with subsampling it fills the first (W/2)*(H/2) floats (elas.h:157-160)."""
+    a = np.asarray(a)
+    if a.shape == (ctx.Dh, ctx.Dw):
+        return a
+    return a.reshape(-1)[: ctx.Dh * ctx.Dw].reshape(ctx.Dh, ctx.Dw)
+
+
 def staged_parity(ctx, ref, p, L, R, inject=True):
     """Full-pipeline run in tap mode against the oracle's staged run.  With inject=True the oracle's triangle lists
     are injected so that every GPU stage is judged on identical inputs (stage isolation); with inject=False the
@@ -38,19 +46,22 @@ def staged_parity(ctx, ref, p, L, R, inject=True):
     for nm in names:
         got = ctx.tap(nm)
         want = t[nm]
+        if nm.startswith("D"):
+            want = half(want, ctx)
         if nm in ("planes1", "planes2"):
             out[nm] = cmp_exact(got.view(np.uint32), np.ascontiguousarray(want).view(np.uint32))
         else:
             out[nm] = cmp_exact(got, want)
-    out["D1"] = cmp_exact(D1, t["D1"])
-    out["D2"] = cmp_exact(D2, t["D2"])
+    D1_ref, D2_ref = half(t["D1"], ctx), half(t["D2"], ctx)
+    out["D1"] = cmp_exact(D1, D1_ref)
+    out["D2"] = cmp_exact(D2, D2_ref)
     # float tolerance statistics for the filtered map (north_star: <= 1e-3 px on >= 99.9 % of valid pixels, same invalid mask)
-    v_ref = t["D1"] >= 0
+    v_ref = D1_ref >= 0
     v_got = D1 >= 0
     out["D1_mask_equal"] = bool(np.array_equal(v_ref, v_got))
     both = v_ref & v_got
     if both.any():
-        err = np.abs(D1[both] - t["D1"][both])
+        err = np.abs(D1[both] - D1_ref[both])
         out["D1_frac_within_1e-3"] = float((err <= 1e-3).mean())
         out["D1_max_err"] = float(err.max())
     ctx.inject_triangles(0, None)

@@ -119,6 +119,29 @@ def test_point_cloud_bgra_stage(svb, golden, kitti_gray, golden_meta):
         ctx.close()
 
 
+def test_point_cloud_with_subsampling_reproduces_the_driver(svb, ref, kitti_gray, golden_meta):
+    """generateDisparityMap() hands Elas a full-size zeroed float buffer; with subsampling the half-size map lands in its
+    first quarter and the WHOLE buffer is converted and projected (stereo_vision.cu:312-324).  Reproduced as is."""
+    L, R = kitti_gray["L7"], kitti_gray["R7"]
+    H, W = L.shape
+    ctx = svb.Context(svb.default_params(svb.PIPELINE, subsampling=1), W, H)
+    try:
+        Q = np.array(golden_meta["Q"])
+        ctx.set_calibration(Q)
+        pts, dmap, D1, _ = ctx.point_cloud_bgra(gray_to_bgra(L), gray_to_bgra(R))
+        R1, _, _ = ref.process(ref.pipeline_params(subsampling=1), L, R)  # the oracle is given a zeroed W x H buffer as well
+        flat = np.zeros(H * W, np.float32)
+        n = (H // 2) * (W // 2)
+        flat[:n] = R1.reshape(-1)[:n]
+        assert np.array_equal(D1.reshape(-1), flat)
+        dm_o, pts_o = parity.reproject_oracle(flat.reshape(H, W), Q, np.eye(3), np.zeros(3))
+        assert np.array_equal(dmap, dm_o)
+        fin = np.isfinite(pts_o).all(1)
+        assert fin.any() and np.allclose(pts[fin], pts_o[fin], rtol=1e-12, atol=0)
+    finally:
+        ctx.close()
+
+
 def test_bgra_to_gray_matches_cv2(svb):
     with open(os.path.join(GOLDEN, "calib_golden.json")) as f:
         probe = json.load(f)["gray_probe"]

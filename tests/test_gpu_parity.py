@@ -119,6 +119,36 @@ def test_4k_disp512_single_gpu_parity(svb, ref):
         ctx.close()
 
 
+@pytest.mark.parametrize("W,H,setting", [(1242, 375, "pipeline"), (1242, 375, "robotics"), (640, 241, "middlebury"), (1241, 376, "pipeline")])
+def test_subsampling_parity(svb, ref, kitti_gray, W, H, setting):
+    """subsampling = 1 (elas.h:81-83): descriptors on even rows only, lattice step 6, disparities for even (u, v) only in
+    (W/2) x (H/2) maps, d/2 warps in the L/R check, 28-pixel speckles, gap width/2+1, 4-tap adaptive mean -- stage by
+    stage against the oracle, odd and even image sizes."""
+    if (W, H) == (1242, 375):
+        L, R = kitti_gray["L0"], kitti_gray["R0"]
+    else:
+        L, R = svb.synth_pair(21, W, H, 1)
+    over = {"subsampling": 1}
+    if setting == "pipeline":
+        p, p_ref = svb.default_params(svb.PIPELINE, **over), ref.pipeline_params(subsampling=1)
+    elif setting == "robotics":
+        p, p_ref = svb.default_params(svb.ROBOTICS, **over), ref.params(0, **over)
+    else:
+        p, p_ref = svb.default_params(svb.MIDDLEBURY, **over), ref.params(1, **over)
+    ctx = svb.Context(p, W, H)
+    try:
+        assert (ctx.Dw, ctx.Dh) == (W // 2, H // 2)
+        res, t, (D1, D2) = parity.staged_parity(ctx, ref, p_ref, L, R, inject=False)
+        assert_all_equal(res)
+        assert_float_bar(res)
+        assert D1.shape == (H // 2, W // 2) and (D1 >= 0).mean() > 0.3
+        # Elas::process of the oracle in one go gives the same half-size maps
+        R1, R2, _ = ref.process(p_ref, L, R)
+        assert np.array_equal(D1, parity.half(R1, ctx)) and np.array_equal(D2, parity.half(R2, ctx))
+    finally:
+        ctx.close()
+
+
 def test_few_support_points_leaves_outputs_untouched(svb, ref):
     """elas.cpp:64-69: a textureless pair yields < 3 support points; D1/D2 stay as the caller passed them."""
     W, H = 320, 120
