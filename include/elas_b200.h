@@ -160,6 +160,9 @@ int svb_batch_run_host(svb_context *ctx, const uint8_t *left, const uint8_t *rig
  * is 0 everywhere, like the reference's untouched zero-initialised map, and SVB_ERR_FEW_SUPPORT is returned. */
 int svb_point_cloud_bgra(svb_context *ctx, const uint8_t *left_bgra, const uint8_t *right_bgra, double *points_out, uint8_t *dmap_out,
                          float *D1_out, double *times_ms);
+/* cv::resize(src, dst, dsize) with the default INTER_LINEAR on 8-bit BGRA (stereo_vision.cu:599-600,665,676: frames are
+ * resized to out_img_size = input size / scale_factor).  Host buffers; OpenCV's fixed-point arithmetic restated exactly. */
+int svb_resize_bgra(const uint8_t *src, int src_width, int src_height, uint8_t *dst, int dst_width, int dst_height);
 /* cv::cvtColor(BGRA2GRAY) on its own (stereo_vision.cu:346-347) */
 int svb_stage_bgra_to_gray(svb_context *ctx, const uint8_t *bgra, uint8_t *gray_out);
 

@@ -140,6 +140,7 @@ def load():
         "svb_stage_bgra_to_gray": [vp, vp, vp],
         "svb_band_process": [vp, vp, vp, C.c_int, vp, vp],
         "svb_band_get_stats": [vp, C.POINTER(BandStats)],
+        "svb_resize_bgra": [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int],
         "svb_image_read": [C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "svb_calib_load_yaml": [C.c_char_p, C.POINTER(Calibration)],
         "svb_stereo_rectify": [C.POINTER(Calibration), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp],
@@ -201,6 +202,18 @@ def image_read(path):
     if rc != 0:
         raise SvbError(rc, lib.svb_last_error().decode())
     return buf
+
+
+def resize_bgra(img, dsize):
+    """cv::resize(img, dsize) with INTER_LINEAR on 8-bit BGRA, on the GPU (stereo_vision.cu:599-600,665,676)."""
+    lib = load()
+    img = np.ascontiguousarray(img, np.uint8)
+    assert img.ndim == 3 and img.shape[2] == 4
+    out = np.zeros((dsize[1], dsize[0], 4), np.uint8)
+    rc = lib.svb_resize_bgra(_ptr(img), img.shape[1], img.shape[0], _ptr(out), dsize[0], dsize[1])
+    if rc != 0:
+        raise SvbError(rc, lib.svb_last_error().decode())
+    return out
 
 
 def load_calibration(path):

@@ -11,8 +11,7 @@
 // Option letters, long names and the "-x=val" / "-x val" / "--name=val" spellings follow the popt table of :768-784.
 // Extension (not in the reference): -B N processes the sequence in batches of N frames through the frame-batch
 // pipeline and reports the aggregate rate.
-// Out of scope here and rejected with a message: -p 1 (OpenGL viewer), -t 1 (YOLO object tracking); -f != 1
-// needs the resize path that is not built yet.
+// Out of scope here and ignored / rejected with a message: -p 1 (OpenGL viewer), -t 1 (YOLO object tracking), -e != 1.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -252,8 +251,12 @@ int main(int argc, const char **argv) {
     printf("** Object tracking disabled\n");
     printf("KITTI Path: %s \n", o.kitti_path.c_str());
     if (o.draw_points) fprintf(stderr, "the OpenGL viewer is outside this program's scope (-p 1 ignored)\n");
-    if (o.scale_factor != 1.f || o.extrapolate != 1) {
-        fprintf(stderr, "scale_factor != 1 and extrapolate_point_cloud != 1 are not built yet (DESIGN.md 1)\n");
+    if (o.extrapolate != 1 || !(o.scale_factor > 0.f)) {
+        fprintf(stderr, "extrapolate_point_cloud != 1 is not built (DESIGN.md 1); scale_factor must be positive\n");
+        return 1;
+    }
+    if (o.batch > 0 && o.scale_factor != 1.f) {
+        fprintf(stderr, "-B (batch extension) runs at scale_factor 1 only\n");
         return 1;
     }
     unsigned max_files = 0;
@@ -262,7 +265,9 @@ int main(int argc, const char **argv) {
     if (o.batch > 0) return batch_loop(o, max_files);
 
     // imageLoop() (stereo_vision.cu:645-697): one frame at a time, the body generatePointCloud() also runs
-    const int W = o.width, H = o.height;
+    // stereo_vision.cu:817-822: calibration size = input size, every frame is resized to out size = input / scale_factor
+    const int inW = o.width, inH = o.height;
+    const int W = (int)(inW / o.scale_factor), H = (int)(inH / o.scale_factor);
     const size_t N = (size_t)W * H;
     svb_params p;
     svb_default_params(SVB_PIPELINE, &p);  // generateDisparityMap()'s preset (stereo_vision.cu:315-319)
@@ -271,7 +276,8 @@ int main(int argc, const char **argv) {
     svb_context *ctx = svb_create(&p, W, H, 1, -1);
     svb_calibration cal;
     double Q[16];
-    if (!ctx || svb_calib_load_yaml(o.calib.c_str(), &cal) != SVB_OK || svb_stereo_rectify(&cal, W, H, W, H, 1.0, 0.0, 0, 0, 0, 0, Q) != SVB_OK) {
+    if (!ctx || svb_calib_load_yaml(o.calib.c_str(), &cal) != SVB_OK ||
+        svb_stereo_rectify(&cal, inW, inH, W, H, o.scale_factor, 0.0, 0, 0, 0, 0, Q) != SVB_OK) {
         fprintf(stderr, "%s\n", svb_last_error());
         return 1;
     }
@@ -281,12 +287,23 @@ int main(int argc, const char **argv) {
     svb_set_calibration(ctx, Q, cal.XR, cal.XT);
     printf("CUDA Init done\n");
     double *points = (double *)svb_host_alloc(N * 24);
-    std::vector<uint8_t> left, right, dmap(N);
+    std::vector<uint8_t> left, right, left_in, right_in, dmap(N);
+    const bool resize = W != inW || H != inH;
     double FPS = 0;
     for (unsigned i = 0; i < max_files; i++) {
-        if (!load_bgra(frame_path(o.kitti_path, "image_02", i), W, H, &left) || !load_bgra(frame_path(o.kitti_path, "image_03", i), W, H, &right))
+        if (!load_bgra(frame_path(o.kitti_path, "image_02", i), inW, inH, resize ? &left_in : &left) ||
+            !load_bgra(frame_path(o.kitti_path, "image_03", i), inW, inH, resize ? &right_in : &right))
             break;
         const auto t0 = std::chrono::steady_clock::now();  // start_timer(t_start) after imread (:664)
+        if (resize) {  // resize(left_img, left_img_OLD, out_img_size) (:665,676)
+            left.resize(N * 4);
+            right.resize(N * 4);
+            if (svb_resize_bgra(left_in.data(), inW, inH, left.data(), W, H) != SVB_OK ||
+                svb_resize_bgra(right_in.data(), inW, inH, right.data(), W, H) != SVB_OK) {
+                fprintf(stderr, "%s\n", svb_last_error());
+                return 1;
+            }
+        }
         double times[2] = {0, 0};
         const int rc = svb_point_cloud_bgra(ctx, left.data(), right.data(), points, dmap.data(), nullptr, times);
         if (rc == SVB_ERR_FEW_SUPPORT)

@@ -4,6 +4,10 @@
 // OpenCV's 8-bit path is fixed point: gray = (B*3735 + G*19235 + R*9798 + 16384) >> 15 (BT.601 weights scaled by 2^15,
 // round to nearest); pinned against python cv2 4.13 on random pixels (tests/golden/calib_golden.json: gray_probe).
 // Memory-bound: 4 B read + 1 B written per pixel; a thread converts 4 pixels (one 16-byte load, one 4-byte store).
+#include <math.h>
+
+#include <vector>
+
 #include "svb_internal.h"
 
 namespace svb {
@@ -38,3 +42,104 @@ int launch_bgra_to_gray(const uint8_t *bgra, uint8_t *gray, int n, cudaStream_t 
 }
 
 }  // namespace svb
+
+// ---- cv::resize(INTER_LINEAR) for 8-bit BGRA ---------------------------------------------------------------------
+// Replaces the resize() calls of the sequence driver (src/parallel_includes/main/stereo_vision.cu:599-600,665,676: input
+// frames are shrunk / enlarged by scale_factor before matching).  OpenCV's 8-bit bilinear path is fixed point and is
+// restated exactly (pinned against python cv2 4.13 for scale factors 0.5 .. 3.0, tests/test_gpu_dropin.py):
+//   fx = float((dx + 0.5) * scale_x - 0.5), sx = floor(fx), fx -= sx; columns are clamped WITH their weight
+//   (sx < 0 -> sx = 0, fx = 0; sx >= sw-1 -> sx = sw-1, fx = 0), rows only clamp the index and keep the weight;
+//   weights = round(w * 2048) as int16; horizontal pass in int32, vertical pass
+//   dst = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.
+namespace svb {
+namespace {
+
+struct ResizeTab {
+    int idx;
+    short w0, w1;
+};
+
+__global__ void __launch_bounds__(256) k_resize_linear_bgra(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const ResizeTab *__restrict__ xt,
+                                                            const ResizeTab *__restrict__ yt, int sw, int sh, int dw, int dh) {
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int dy = blockIdx.y;
+    if (dx >= dw) return;
+    const ResizeTab tx = xt[dx], ty = yt[dy];
+    const int x0 = tx.idx, x1 = min(tx.idx + 1, sw - 1);
+    const int y0 = min(max(ty.idx, 0), sh - 1), y1 = min(max(ty.idx + 1, 0), sh - 1);
+    const uint32_t *r0 = reinterpret_cast<const uint32_t *>(src) + (size_t)y0 * sw;
+    const uint32_t *r1 = reinterpret_cast<const uint32_t *>(src) + (size_t)y1 * sw;
+    const uint32_t p00 = r0[x0], p01 = r0[x1], p10 = r1[x0], p11 = r1[x1];
+    uint32_t out = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int sft = 8 * c;
+        const int S0 = (int)((p00 >> sft) & 0xFF) * tx.w0 + (int)((p01 >> sft) & 0xFF) * tx.w1;
+        const int S1 = (int)((p10 >> sft) & 0xFF) * tx.w0 + (int)((p11 >> sft) & 0xFF) * tx.w1;
+        int v = (((ty.w0 * (S0 >> 4)) >> 16) + ((ty.w1 * (S1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+        out |= (uint32_t)v << sft;
+    }
+    reinterpret_cast<uint32_t *>(dst)[(size_t)dy * dw + dx] = out;
+}
+
+void make_table(std::vector<ResizeTab> &t, int dn, int sn, bool clamp_weight) {
+    const double scale = 1.0 / ((double)dn / sn);
+    t.resize(dn);
+    for (int d = 0; d < dn; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= s;
+        if (clamp_weight) {
+            if (s < 0) {
+                f = 0;
+                s = 0;
+            }
+            if (s >= sn - 1) {
+                f = 0;
+                s = sn - 1;
+            }
+        }
+        t[d].idx = s;
+        t[d].w0 = (short)lrintf((1.f - f) * 2048.f);
+        t[d].w1 = (short)lrintf(f * 2048.f);
+    }
+}
+
+}  // namespace
+}  // namespace svb
+
+extern "C" int svb_resize_bgra(const uint8_t *src, int src_width, int src_height, uint8_t *dst, int dst_width, int dst_height) {
+    using namespace svb;
+    if (!src || !dst || src_width < 1 || src_height < 1 || dst_width < 1 || dst_height < 1) return SVB_ERR_ARG;
+    std::vector<ResizeTab> xt, yt;
+    make_table(xt, dst_width, src_width, true);
+    make_table(yt, dst_height, src_height, false);
+    uint8_t *d_src = nullptr, *d_dst = nullptr;
+    ResizeTab *d_xt = nullptr, *d_yt = nullptr;
+    const size_t sb = (size_t)src_width * src_height * 4, db = (size_t)dst_width * dst_height * 4;
+    int rc = SVB_OK;
+    cudaError_t e = cudaMalloc(&d_src, sb);
+    if (e == cudaSuccess) e = cudaMalloc(&d_dst, db);
+    if (e == cudaSuccess) e = cudaMalloc(&d_xt, xt.size() * sizeof(ResizeTab));
+    if (e == cudaSuccess) e = cudaMalloc(&d_yt, yt.size() * sizeof(ResizeTab));
+    if (e == cudaSuccess) e = cudaMemcpy(d_src, src, sb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_xt, xt.data(), xt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_yt, yt.data(), yt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        dim3 grid((dst_width + 255) / 256, dst_height);
+        k_resize_linear_bgra<<<grid, 256>>>(d_src, d_dst, d_xt, d_yt, src_width, src_height, dst_width, dst_height);
+        g_launch_counter++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(dst, d_dst, db, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+        set_error("svb_resize_bgra: %s", cudaGetErrorString(e));
+        rc = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SVB_ERR_NO_DEVICE : SVB_ERR_CUDA;
+    }
+    cudaFree(d_src);
+    cudaFree(d_dst);
+    cudaFree(d_xt);
+    cudaFree(d_yt);
+    return rc;
+}

@@ -66,8 +66,31 @@ def test_batch_extension(tmp_path, kitti_gray):
     assert re.search(r"^AVG_FPS=[0-9.]+$", r.stdout, re.M) and "(BATCH frames=2)" in r.stdout
 
 
+def test_scale_factor(tmp_path, kitti_gray, ref):
+    """-f 2.0 (test.sh sweeps it): frames are resized like cv::resize does, K1/K2 are divided by the factor and the
+    rectification targets the smaller size; the u8 map equals the oracle's on cv2-resized inputs."""
+    with open(os.path.join(GOLDEN, "calib_golden.json")) as f:
+        case = [c for c in json.load(f)["cases"] if c["name"] == "data/calibration/kitti_2011_09_26.yml" and c["size"] == [1242, 375]
+                and c["alpha"] == 0.0][0]
+    seq = tmp_path / "seq"
+    make_sequence(str(seq), kitti_gray)
+    write_yaml(tmp_path / "k.yml", case)
+    dump = tmp_path / "dump"
+    os.makedirs(dump)
+    r = subprocess.run([EXE, "-k", str(seq), "-p=0", "-f=2.0", "-c", str(tmp_path / "k.yml"), "-o", str(dump)], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "(187, 621)" in r.stdout
+    L = cv2.resize(np.stack([kitti_gray["L0"]] * 3, -1), (621, 187))[..., 0]
+    R = cv2.resize(np.stack([kitti_gray["R0"]] * 3, -1), (621, 187))[..., 0]
+    D1, _, _ = ref.process(ref.pipeline_params(), L, R)
+    want = np.clip(np.rint(D1 * np.float32(4.0)), 0, 255).astype(np.uint8)
+    got = cv2.imread(str(dump / "0000000000_disp.pgm"), cv2.IMREAD_GRAYSCALE)
+    assert np.array_equal(got, want)
+
+
 def test_unsupported_options_fail_loudly(tmp_path):
-    r = subprocess.run([EXE, "-k", str(tmp_path), "-p", "0", "-f", "2.0"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    r = subprocess.run([EXE, "-k", str(tmp_path), "-p", "0", "-e", "2"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "not built" in r.stderr
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "Usage" in r.stderr

@@ -142,6 +142,18 @@ def test_point_cloud_with_subsampling_reproduces_the_driver(svb, ref, kitti_gray
         ctx.close()
 
 
+def test_resize_matches_cv2(svb):
+    """cv::resize INTER_LINEAR (8-bit, fixed point) for the scale factors the reference's test.sh sweeps (0.5 .. 3.0)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for sw, sh in ((1242, 375), (333, 127)):
+        img = rng.integers(0, 256, (sh, sw, 4), dtype=np.uint8)
+        img[: sh // 3] = (np.arange(sw) % 256).astype(np.uint8)[None, :, None]
+        for scale in (0.5, 0.75, 1.0, 1.5, 2.0, 2.5, 3.0):
+            dsize = (int(sw / scale), int(sh / scale))
+            assert np.array_equal(svb.resize_bgra(img, dsize), cv2.resize(img, dsize)), (sw, sh, scale)
+
+
 def test_bgra_to_gray_matches_cv2(svb):
     with open(os.path.join(GOLDEN, "calib_golden.json")) as f:
         probe = json.load(f)["gray_probe"]
