@@ -45,14 +45,20 @@ __device__ void unite(int32_t *labels, int a, int b) {
     }
 }
 
-// grid: (ceil(W/128), H, nimg)   labels are indices local to the image; invalid pixels get label -1
+// Every per-pixel kernel below lets a thread walk RPB consecutive rows of its column: 8x fewer, 8x longer CTAs than
+// one pixel per thread (the one-pixel form was bound by CTA launch rate and exposed load latency: ~1.2 TB/s effective).
+constexpr int RPB = 8;
+
+// grid: (ceil(W/128), ceil(H/RPB), nimg)   labels are indices local to the image; invalid pixels get label -1
 __global__ void __launch_bounds__(128) k_ccl_init(const float *__restrict__ D_all, int32_t *__restrict__ labels_all, int32_t *__restrict__ sizes_all,
                                                  int W, int H, float thr) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = blockIdx.y;
     const size_t img = (size_t)blockIdx.z * W * H;
     const int lane = threadIdx.x & 31;
     const bool in = u < W;
+    const int v_end = min((int)(blockIdx.y + 1) * RPB, H);
+#pragma unroll 4
+  for (int v = blockIdx.y * RPB; v < v_end; v++) {
     const int idx = v * W + u;
     const float d = in ? D_all[img + idx] : -10.f;
     const float dl = __shfl_up_sync(0xFFFFFFFFu, d, 1);
@@ -60,7 +66,7 @@ __global__ void __launch_bounds__(128) k_ccl_init(const float *__restrict__ D_al
     // linked to the left neighbour?
     const bool link = in && u > 0 && similar(d, dleft, thr);
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, link);
-    if (!in) return;
+    if (!in) continue;
     // run start inside this warp: the nearest lane at or below `lane` whose link bit is clear
     const unsigned clear_below = ~bal & ((2u << lane) - 1u);  // lanes <= lane with no left link (lane 31: all bits)
     const unsigned mask = (lane == 31) ? ~bal : clear_below;
@@ -76,25 +82,29 @@ __global__ void __launch_bounds__(128) k_ccl_init(const float *__restrict__ D_al
     }
     labels_all[img + idx] = label;
     if (label == idx) sizes_all[img + idx] = 0;  // only run starts can end up as roots (a root is its segment's minimum index)
+  }
 }
 
 // Vertical edges.  An edge (u,v)-(u,v-1) is skipped when the edge one column to the left already unites the same two
 // runs: both pixels are linked to their left neighbours and those neighbours are vertically similar.
 __global__ void __launch_bounds__(128) k_ccl_merge(const float *__restrict__ D_all, int32_t *__restrict__ labels_all, int W, int H, float thr) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = blockIdx.y + 1;
     if (u >= W) return;
     const size_t img = (size_t)blockIdx.z * W * H;
-    const int idx = v * W + u;
-    const float d = D_all[img + idx];
-    const float du = D_all[img + idx - W];
-    if (!similar(d, du, thr)) return;
-    if (u > 0) {
-        const float dl = D_all[img + idx - 1];
-        const float dul = D_all[img + idx - W - 1];
-        if (similar(d, dl, thr) && similar(du, dul, thr) && similar(dl, dul, thr)) return;
+    const int v0 = max((int)blockIdx.y * RPB, 1), v_end = min((int)(blockIdx.y + 1) * RPB, H);
+    if (v0 >= v_end) return;
+    // the row above is carried in registers from one step to the next
+    float du = D_all[img + (size_t)(v0 - 1) * W + u];
+    float dul = u > 0 ? D_all[img + (size_t)(v0 - 1) * W + u - 1] : -10.f;
+    for (int v = v0; v < v_end; v++) {
+        const int idx = v * W + u;
+        const float d = D_all[img + idx];
+        const float dl = u > 0 ? D_all[img + idx - 1] : -10.f;
+        if (similar(d, du, thr) && !(u > 0 && similar(d, dl, thr) && similar(du, dul, thr) && similar(dl, dul, thr)))
+            unite(labels_all + img, idx, idx - W);
+        du = d;
+        dul = dl;
     }
-    unite(labels_all + img, idx, idx - W);
 }
 
 // Flatten labels to roots and count segment sizes.  A CTA covers a 128 x 8 pixel tile; equal roots are first combined
@@ -157,15 +167,18 @@ __global__ void __launch_bounds__(32 * CNT_ROWS) k_ccl_count(int32_t *__restrict
 __global__ void __launch_bounds__(128) k_ccl_prune(float *__restrict__ D_all, const int32_t *__restrict__ labels_all,
                                                   const int32_t *__restrict__ sizes_all, int W, int H, int min_size) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = blockIdx.y;
     if (u >= W) return;
     const size_t img = (size_t)blockIdx.z * W * H;
-    const int idx = v * W + u;
-    const int r = labels_all[img + idx];
-    if (r < 0) {
-        if (1 < min_size) D_all[img + idx] = -10.f;
-    } else if (sizes_all[img + r] < min_size) {
-        D_all[img + idx] = -10.f;
+    const int v_end = min((int)(blockIdx.y + 1) * RPB, H);
+#pragma unroll 4
+    for (int v = blockIdx.y * RPB; v < v_end; v++) {
+        const int idx = v * W + u;
+        const int r = labels_all[img + idx];
+        if (r < 0) {
+            if (1 < min_size) D_all[img + idx] = -10.f;
+        } else if (sizes_all[img + r] < min_size) {
+            D_all[img + idx] = -10.f;
+        }
     }
 }
 
@@ -176,12 +189,11 @@ int launch_remove_small_segments(const Dims &d, const svb_params &p, float *D, i
     const int W = d.Dw, H = d.Dh;
     // elas.cpp:1017-1022: at half resolution a speckle is sqrt(speckle_size) * 2 pixels
     const int min_size = d.sub ? (int)(sqrtf((float)p.speckle_size) * 2) : p.speckle_size;
-    dim3 grid((W + 127) / 128, H, nimg);
+    dim3 grid((W + 127) / 128, (H + RPB - 1) / RPB, nimg);
     k_ccl_init<<<grid, 128, 0, s>>>(D, labels, sizes, W, H, p.speckle_sim_threshold);
     SVB_LAUNCH_CHECK();
     if (H > 1) {
-        dim3 gm((W + 127) / 128, H - 1, nimg);
-        k_ccl_merge<<<gm, 128, 0, s>>>(D, labels, W, H, p.speckle_sim_threshold);
+        k_ccl_merge<<<grid, 128, 0, s>>>(D, labels, W, H, p.speckle_sim_threshold);
         SVB_LAUNCH_CHECK();
     }
     dim3 gc((W + 127) / 128, (H + CNT_ROWS - 1) / CNT_ROWS, nimg);

@@ -11,28 +11,35 @@ namespace {
 
 // ---- L/R check ------------------------------------------------------------------------------------
 // grid: (ceil(W/256), H, nf).  Out of place: the reference works on copies of both maps (elas.cpp:956-959).
+constexpr int LR_ROWS = 8;  // rows per thread: fewer, longer CTAs and 8 independent loads in flight per thread
+
+// grid: (ceil(W/256), ceil(rows/LR_ROWS), nf)
 __global__ void __launch_bounds__(256) k_lr_check(const float *__restrict__ D1in, const float *__restrict__ D2in, float *__restrict__ D1out,
-                                                 float *__restrict__ D2out, int W, int H, float lr_threshold, int row0, int half) {
+                                                 float *__restrict__ D2out, int W, int H, float lr_threshold, int row0, int row1, int half) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= W) return;
-    const size_t base = ((size_t)blockIdx.z * H + row0 + blockIdx.y) * W;
-    const float d1 = D1in[base + u];
-    const float d2 = D2in[base + u];
     const float fw = (float)W;
-    float o1 = -10.f, o2 = -10.f;
-    // subsampling (elas.cpp:972-975): the maps are half size, the disparities are not: warp by d/2
-    const float uw1 = __fsub_rn((float)u, half ? __fdiv_rn(d1, 2.f) : d1);
-    if (d1 >= 0.f && uw1 >= 0.f && uw1 < fw) {
-        const float other = D2in[base + (int)uw1];
-        o1 = (fabsf(__fsub_rn(other, d1)) > lr_threshold) ? -10.f : d1;
+    const int v_end = min(row0 + (int)(blockIdx.y + 1) * LR_ROWS, row1);
+#pragma unroll 4
+    for (int v = row0 + blockIdx.y * LR_ROWS; v < v_end; v++) {
+        const size_t base = ((size_t)blockIdx.z * H + v) * W;
+        const float d1 = D1in[base + u];
+        const float d2 = D2in[base + u];
+        float o1 = -10.f, o2 = -10.f;
+        // subsampling (elas.cpp:972-975): the maps are half size, the disparities are not: warp by d/2
+        const float uw1 = __fsub_rn((float)u, half ? __fdiv_rn(d1, 2.f) : d1);
+        if (d1 >= 0.f && uw1 >= 0.f && uw1 < fw) {
+            const float other = D2in[base + (int)uw1];
+            o1 = (fabsf(__fsub_rn(other, d1)) > lr_threshold) ? -10.f : d1;
+        }
+        const float uw2 = __fadd_rn((float)u, half ? __fdiv_rn(d2, 2.f) : d2);
+        if (d2 >= 0.f && uw2 >= 0.f && uw2 < fw) {
+            const float other = D1in[base + (int)uw2];
+            o2 = (fabsf(__fsub_rn(other, d2)) > lr_threshold) ? -10.f : d2;
+        }
+        D1out[base + u] = o1;
+        if (D2out) D2out[base + u] = o2;
     }
-    const float uw2 = __fadd_rn((float)u, half ? __fdiv_rn(d2, 2.f) : d2);
-    if (d2 >= 0.f && uw2 >= 0.f && uw2 < fw) {
-        const float other = D1in[base + (int)uw2];
-        o2 = (fabsf(__fsub_rn(other, d2)) > lr_threshold) ? -10.f : d2;
-    }
-    D1out[base + u] = o1;
-    if (D2out) D2out[base + u] = o2;
 }
 
 // ---- gap interpolation, row pass --------------------------------------------------------------------
@@ -427,8 +434,8 @@ int launch_lr_check_rows(const Dims &d, const svb_params &p, const float *D1in, 
         row0 = 0;
         row1 = d.Dh;
     }
-    dim3 grid((d.Dw + 255) / 256, row1 - row0, nf);
-    k_lr_check<<<grid, 256, 0, s>>>(D1in, D2in, D1out, D2out, d.Dw, d.Dh, (float)p.lr_threshold, row0, d.sub);
+    dim3 grid((d.Dw + 255) / 256, (row1 - row0 + LR_ROWS - 1) / LR_ROWS, nf);
+    k_lr_check<<<grid, 256, 0, s>>>(D1in, D2in, D1out, D2out, d.Dw, d.Dh, (float)p.lr_threshold, row0, row1, d.sub);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }
