@@ -88,17 +88,18 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     // d <= disp_max even where the warped column leaves the row: loads never need a guard, only the result does.
     const uint4 *po = reinterpret_cast<const uint4 *>(a.desc[SIDE ^ 1]) + (size_t)f * N + (size_t)row * W + u;
 
-    bool active = false;
-    uint4 c = make_uint4(0, 0, 0, 0);
-    int o = -1;
-    if (in) {
-        o = a.owner[SIDE][(size_t)f * a.DN + pix];
-        if (o >= 0 && u >= 2 && u < W - 2) {  // elas.cpp:714
-            c = __ldg(own + u);
-            const uint4 k128 = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
-            active = (int)sad16(c, k128) >= a.match_texture;  // elas.cpp:731-736
-        }
-    }
+    // Three independent loads are issued up front (owner index, own descriptor, first 128 candidate bits of the grid
+    // cell), so that the prologue waits for ONE memory round trip before the plane record instead of four chained ones.
+    const int uc = in ? min(u, W - 1) : W - 1;
+    const int gx = a.grid_size == 1 ? uc : (int)__umulhi((unsigned)uc, a.grid_magic);  // u / grid_size by reciprocal (exact for u < 2^16)
+    const int gy = a.grid_size == 1 ? v : (int)__umulhi((unsigned)v, a.grid_magic);    // u, v >= 0: equals the float floor (elas.cpp:744-745)
+    const uint32_t *cell = a.grid[SIDE] + ((size_t)f * a.gw * a.gh + (size_t)gy * a.gw + gx) * a.gwords;
+    const int o = in ? __ldg(a.owner[SIDE] + (size_t)f * a.DN + pix) : -1;
+    const uint4 c = __ldg(own + uc);
+    uint4 m4_first = __ldg(reinterpret_cast<const uint4 *>(cell));
+    const uint4 k128 = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+    // elas.cpp:714 (column range) and :731-736 (texture)
+    const bool active = in && o >= 0 && u >= 2 && u < W - 2 && (int)sad16(c, k128) >= a.match_texture;
     int d_plane = 0, dmin = 1, dmax = 0;  // empty band for inactive lanes
     unsigned prior_on = 0u;
     if (active) {
@@ -116,14 +117,11 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
 
     unsigned key = 0xFFFFFFFFu;
     // (i) grid candidates outside the band, ascending (elas.cpp:759-767 / 778-786)
-    // u / grid_size by a host-computed reciprocal (exact for u < 2^16: u * (magic * g - 2^32) < 2^32)
-    const int uc = in ? u : W - 1;
-    const int gx = a.grid_size == 1 ? uc : (int)__umulhi((unsigned)uc, a.grid_magic), gy = v / a.grid_size;  // u, v >= 0: equals the float floor
-    const uint32_t *cell = a.grid[SIDE] + ((size_t)f * a.gw * a.gh + (size_t)gy * a.gw + gx) * a.gwords;
     // gwords is a multiple of 4 (make_dims): a cell is read as 16-byte vectors, and a group of four words (128
     // disparities) without any candidate in the whole warp is skipped with one vote
     for (int w4 = 0; w4 < a.gwords; w4 += 4) {
-        const uint4 m4 = active ? __ldg(reinterpret_cast<const uint4 *>(cell + w4)) : make_uint4(0, 0, 0, 0);
+        uint4 m4 = w4 == 0 ? m4_first : __ldg(reinterpret_cast<const uint4 *>(cell + w4));
+        if (!active) m4 = make_uint4(0, 0, 0, 0);
         if (!__any_sync(0xFFFFFFFFu, (m4.x | m4.y | m4.z | m4.w) != 0u)) continue;
 #pragma unroll
         for (int j = 0; j < 4; j++) {

@@ -1,6 +1,6 @@
 // Context, device arenas, the frame-batch pipeline and every svb_* entry point of include/elas_b200.h.
 //
-// One svb_context owns LANES independent lanes; a lane holds the device arenas for `chunk` frames, one CUDA
+// One svb_context owns n_lanes (default 3) independent lanes; a lane holds the device arenas for `chunk` frames, one CUDA
 // stream and pinned staging buffers.  A batch is cut into chunks that go round-robin over the lanes:
 //     stage A (GPU)  descriptor -> support matching -> lattice filters/compaction -> D2H support list
 //     host stage     Delaunay triangulation (worker pool, one job per frame and side)
@@ -10,6 +10,7 @@
 // Frames never interact, so there is no collective anywhere.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -511,7 +512,13 @@ svb_context *svb_create(const svb_params *params, int width, int height, int chu
         delete c;
         return nullptr;
     }
-    for (int i = 0; i < LANES; i++)
+    {
+        const char *e = getenv("SVB_LANES");
+        const int n = e ? atoi(e) : 3;
+        c->n_lanes = n < 1 ? 1 : (n > MAX_LANES ? MAX_LANES : n);
+        if (c->chunk == 1) c->n_lanes = 1;  // single-frame contexts never pipeline
+    }
+    for (int i = 0; i < c->n_lanes; i++)
         if (lane_create(c, c->lanes[i]) != SVB_OK) {
             svb_destroy(c);
             return nullptr;
@@ -531,7 +538,8 @@ void svb_destroy(svb_context *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < LANES; i++) lane_destroy(c->lanes[i]);
+    for (int i = 0; i < MAX_LANES; i++)
+        if (c->lanes[i].own_stream) lane_destroy(c->lanes[i]);
     for (auto &t : c->taps) cudaFree(t.dev);
     for (auto &se : c->stage_ev) {
         for (int i = 0; i <= ST_COUNT; i++)
@@ -575,7 +583,7 @@ int svb_set_single_stream(svb_context *c, int on) {
     SVB_CUDA(cudaSetDevice(c->device));
     SVB_CUDA(cudaDeviceSynchronize());
     c->single_stream = on != 0;
-    for (int i = 0; i < LANES; i++) c->lanes[i].stream = c->single_stream ? c->lanes[0].own_stream : c->lanes[i].own_stream;
+    for (int i = 0; i < c->n_lanes; i++) c->lanes[i].stream = c->single_stream ? c->lanes[0].own_stream : c->lanes[i].own_stream;
     return SVB_OK;
 }
 
@@ -925,6 +933,7 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
     SVB_CUDA(cudaEventCreate(&ev1));
     SVB_CUDA(cudaDeviceSynchronize());
     SVB_CUDA(cudaEventRecord(ev0, c->lanes[0].stream));
+    const int LANES = c->n_lanes;
     for (int l = 1; l < LANES; l++) SVB_CUDA(cudaStreamWaitEvent(c->lanes[l].stream, ev0, 0));
 
     auto frames_of = [&](int k) { return (k + 1) * C <= n_frames ? C : n_frames - k * C; };

@@ -12,7 +12,7 @@
 
 namespace svb {
 
-constexpr int LANES = 3;
+constexpr int MAX_LANES = 6;  // arenas in flight; the context uses n_lanes of them (default 3, SVB_LANES overrides)
 
 struct Lane {
     cudaStream_t own_stream = nullptr;  // created with the lane
@@ -61,7 +61,8 @@ struct svb_context {
     int chunk = 1;
     int device = 0;
     int mean_mode = SVB_MEAN_SERIAL_QUANTISED;
-    svb::Lane lanes[svb::LANES];
+    svb::Lane lanes[svb::MAX_LANES];
+    int n_lanes = 3;
     std::unique_ptr<svb::ThreadPool> pool;
     std::vector<svb::DelaunayScratch> scratch;
     svb::Calib calib;
