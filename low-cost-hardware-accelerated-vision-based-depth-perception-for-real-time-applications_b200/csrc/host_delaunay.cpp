@@ -15,7 +15,14 @@
 //   - output = live non-ghost triangle records in creation order, corners (org, dest, apex)  (:7449-7500)
 // Unlike the reference (float coordinates + adaptive-precision floating point predicates) every predicate here
 // is evaluated exactly in 64-bit integers: |coordinates| < 2^13 keeps orient2d below 2^28 and incircle below 2^56.
-// Triangle records are plain index triples in one flat arena (no pointer pool, no per-call malloc).
+// Triangle records are 32-byte rows {3 neighbour handles, 3 vertices} in one flat arena (no pointer pool, no per-call
+// malloc); a handle is one int (record << 2 | orientation).
+//
+// What is restated and what is merely equivalent: the vertex sort and the median partitions of the reference are
+// randomised, but only two things they produce reach the output -- WHICH of several equal-coordinate vertices
+// survives, and the SETS on either side of every median (subsets of <= 3 come out x-sorted).  So the common
+// duplicate-free case runs an LSD radix sort and a k-d split over presorted rank lists (two branch-free linear passes
+// per level); only an input that does contain duplicates goes through the restated randomised quicksort.
 #include "host_delaunay.h"
 
 #include <algorithm>
@@ -25,101 +32,96 @@ namespace svb {
 
 namespace {
 
-struct Handle {
-    int t;  // triangle record
-    int o;  // orientation 0..2
+// A handle is (record << 2 | orientation); record r occupies R[8r .. 8r+7] = {nbr0, nbr1, nbr2, -, vtx0, vtx1, vtx2, -}.
+struct Pt {
+    int32_t x, y;
 };
 
-const int PLUS1[3] = {1, 2, 0};
-const int MINUS1[3] = {2, 0, 1};
-
 struct Mesh {
-    const int32_t *X;  // valid for index -1 (sentinel) .. n-1
-    const int32_t *Y;
-    int32_t *nbr;  // 3 per record, encoded handle (t << 2 | o)
-    int32_t *vtx;  // 3 per record, vertex id or -1 ("NULL")
+    const Pt *__restrict P;  // coordinates by vertex id (= position in the lexicographic order); index -1 is the "NULL" sentinel
+    int32_t *__restrict R;
     int ntri;
 
-    static int enc(Handle h) { return (h.t << 2) | h.o; }
-    static Handle dec(int e) { return Handle{e >> 2, e & 3}; }
-
-    int org(Handle h) const { return vtx[3 * h.t + PLUS1[h.o]]; }
-    int dest(Handle h) const { return vtx[3 * h.t + MINUS1[h.o]]; }
-    int apex(Handle h) const { return vtx[3 * h.t + h.o]; }
-    void setorg(Handle h, int v) { vtx[3 * h.t + PLUS1[h.o]] = v; }
-    void setdest(Handle h, int v) { vtx[3 * h.t + MINUS1[h.o]] = v; }
-    void setapex(Handle h, int v) { vtx[3 * h.t + h.o] = v; }
-    Handle sym(Handle h) const { return dec(nbr[3 * h.t + h.o]); }
-    static Handle lnext(Handle h) { return Handle{h.t, PLUS1[h.o]}; }
-    static Handle lprev(Handle h) { return Handle{h.t, MINUS1[h.o]}; }
-    void bond(Handle a, Handle b) {
-        nbr[3 * a.t + a.o] = enc(b);
-        nbr[3 * b.t + b.o] = enc(a);
+    static int lnext(int e) { return (e & 3) == 2 ? e - 2 : e + 1; }
+    static int lprev(int e) { return (e & 3) == 0 ? e + 2 : e - 1; }
+    int &nbr(int e) { return R[2 * e - (e & 3)]; }
+    int &vtx(int e) { return R[2 * e - (e & 3) + 4]; }
+    int apex(int e) { return vtx(e); }
+    int org(int e) { return vtx(lnext(e)); }
+    int dest(int e) { return vtx(lprev(e)); }
+    void setapex(int e, int v) { vtx(e) = v; }
+    void setorg(int e, int v) { vtx(lnext(e)) = v; }
+    void setdest(int e, int v) { vtx(lprev(e)) = v; }
+    int sym(int e) { return nbr(e); }
+    void bond(int a, int b) {
+        nbr(a) = b;
+        nbr(b) = a;
     }
     // record 0 is the "outer space" record: its neighbours are itself and its vertices are NULL
-    Handle make() {
+    int make() {
         const int t = ntri++;
-        nbr[3 * t] = nbr[3 * t + 1] = nbr[3 * t + 2] = 0;
-        vtx[3 * t] = vtx[3 * t + 1] = vtx[3 * t + 2] = -1;
-        return Handle{t, 0};
+        int32_t *r = R + 8 * t;
+        r[0] = r[1] = r[2] = r[3] = 0;
+        r[4] = r[5] = r[6] = r[7] = -1;
+        return t << 2;
     }
 
-    // exact orientation: > 0 iff a, b, c are counter-clockwise
-    int64_t ccw(int a, int b, int c) const {
-        return (int64_t)(X[a] - X[c]) * (Y[b] - Y[c]) - (int64_t)(Y[a] - Y[c]) * (X[b] - X[c]);
+    // exact orientation: > 0 iff a, b, c are counter-clockwise.  |coordinate differences| < 2^14: 32-bit exact.
+    static int32_t ccw(Pt a, Pt b, Pt c) { return (a.x - c.x) * (b.y - c.y) - (a.y - c.y) * (b.x - c.x); }
+    int32_t ccw(int a, int b, int c) const { return ccw(P[a], P[b], P[c]); }
+    // exact in-circle: > 0 iff d lies inside the circle through a, b, c (a, b, c counter-clockwise).
+    // lifts and 2x2 minors stay below 2^29 (32-bit), their products below 2^58 (64-bit).
+    static int64_t incircle(Pt a, Pt b, Pt c, Pt d) {
+        const int32_t adx = a.x - d.x, ady = a.y - d.y;
+        const int32_t bdx = b.x - d.x, bdy = b.y - d.y;
+        const int32_t cdx = c.x - d.x, cdy = c.y - d.y;
+        const int32_t alift = adx * adx + ady * ady;
+        const int32_t blift = bdx * bdx + bdy * bdy;
+        const int32_t clift = cdx * cdx + cdy * cdy;
+        return (int64_t)alift * (bdx * cdy - cdx * bdy) + (int64_t)blift * (cdx * ady - adx * cdy) +
+               (int64_t)clift * (adx * bdy - bdx * ady);
     }
-    // exact in-circle: > 0 iff d lies inside the circle through a, b, c (a, b, c counter-clockwise)
-    int64_t incircle(int a, int b, int c, int d) const {
-        const int64_t adx = X[a] - X[d], ady = Y[a] - Y[d];
-        const int64_t bdx = X[b] - X[d], bdy = Y[b] - Y[d];
-        const int64_t cdx = X[c] - X[d], cdy = Y[c] - Y[d];
-        const int64_t alift = adx * adx + ady * ady;
-        const int64_t blift = bdx * bdx + bdy * bdy;
-        const int64_t clift = cdx * cdx + cdy * cdy;
-        return alift * (bdx * cdy - cdx * bdy) + blift * (cdx * ady - adx * cdy) + clift * (adx * bdy - bdx * ady);
-    }
+    int64_t incircle(int a, int b, int c, int d) const { return incircle(P[a], P[b], P[c], P[d]); }
 
-    void merge(Handle &farleft, Handle &innerleft, Handle &innerright, Handle &farright, int axis);
-    void recurse(const int32_t *sorted, int count, int axis, Handle &farleft, Handle &farright);
+    void merge(int &farleft, int &innerleft, int &innerright, int &farright, int axis);
+    void recurse(const int32_t *sorted, int count, int axis, int &farleft, int &farright);
 };
 
 // Knit two adjacent triangulations together (triangle.cpp:5362-5651).
-void Mesh::merge(Handle &farleft, Handle &innerleft, Handle &innerright, Handle &farright, int axis) {
+void Mesh::merge(int &farleft, int &innerleft, int &innerright, int &farright, int axis) {
     int innerleftdest = dest(innerleft), innerleftapex = apex(innerleft);
     int innerrightorg = org(innerright), innerrightapex = apex(innerright);
     if (axis == 1) {
         // horizontal cut: move the extreme handles from leftmost/rightmost to bottommost/topmost vertices
         int farleftpt = org(farleft), farleftapex = apex(farleft);
-        int farrightpt = dest(farright), farrightapex = apex(farright);
-        while (Y[farleftapex] < Y[farleftpt]) {
+        int farrightpt = dest(farright);
+        while (P[farleftapex].y < P[farleftpt].y) {
             farleft = sym(lnext(farleft));
             farleftpt = farleftapex;
             farleftapex = apex(farleft);
         }
-        Handle check = sym(innerleft);
+        int check = sym(innerleft);
         int checkv = apex(check);
-        while (Y[checkv] > Y[innerleftdest]) {
+        while (P[checkv].y > P[innerleftdest].y) {
             innerleft = lnext(check);
             innerleftapex = innerleftdest;
             innerleftdest = checkv;
             check = sym(innerleft);
             checkv = apex(check);
         }
-        while (Y[innerrightapex] < Y[innerrightorg]) {
+        while (P[innerrightapex].y < P[innerrightorg].y) {
             innerright = sym(lnext(innerright));
             innerrightorg = innerrightapex;
             innerrightapex = apex(innerright);
         }
         check = sym(farright);
         checkv = apex(check);
-        while (Y[checkv] > Y[farrightpt]) {
+        while (P[checkv].y > P[farrightpt].y) {
             farright = lnext(check);
-            farrightapex = farrightpt;
             farrightpt = checkv;
             check = sym(farright);
             checkv = apex(check);
         }
-        (void)farrightapex;
     }
     // lower common tangent
     bool changed;
@@ -139,10 +141,10 @@ void Mesh::merge(Handle &farleft, Handle &innerleft, Handle &innerright, Handle 
         }
     } while (changed);
 
-    Handle leftcand = sym(innerleft);
-    Handle rightcand = sym(innerright);
+    int leftcand = sym(innerleft);
+    int rightcand = sym(innerright);
     // bottom bounding record
-    Handle base = make();
+    int base = make();
     bond(base, innerleft);
     base = lnext(base);
     bond(base, innerright);
@@ -154,12 +156,13 @@ void Mesh::merge(Handle &farleft, Handle &innerleft, Handle &innerright, Handle 
 
     int lowerleft = innerleftdest, lowerright = innerrightorg;
     int upperleft = apex(leftcand), upperright = apex(rightcand);
+    Pt pll = P[lowerleft], plr = P[lowerright], pul = P[upperleft], pur = P[upperright];  // coordinates ride along
     while (true) {
-        const bool leftfinished = ccw(upperleft, lowerleft, lowerright) <= 0;
-        const bool rightfinished = ccw(upperright, lowerleft, lowerright) <= 0;
+        const bool leftfinished = ccw(pul, pll, plr) <= 0;
+        const bool rightfinished = ccw(pur, pll, plr) <= 0;
         if (leftfinished && rightfinished) {
             // top bounding record
-            Handle top = make();
+            int top = make();
             setorg(top, lowerleft);
             setdest(top, lowerright);
             bond(top, base);
@@ -169,19 +172,17 @@ void Mesh::merge(Handle &farleft, Handle &innerleft, Handle &innerright, Handle 
             bond(top, leftcand);
             if (axis == 1) {
                 // restore the extreme handles to the leftmost / rightmost vertices
-                int farleftpt = org(farleft), farleftapex = apex(farleft);
+                int farleftpt = org(farleft);
                 int farrightpt = dest(farright), farrightapex = apex(farright);
-                Handle check = sym(farleft);
+                int check = sym(farleft);
                 int checkv = apex(check);
-                while (X[checkv] < X[farleftpt]) {
+                while (P[checkv].x < P[farleftpt].x) {
                     farleft = lprev(check);
-                    farleftapex = farleftpt;
                     farleftpt = checkv;
                     check = sym(farleft);
                     checkv = apex(check);
                 }
-                (void)farleftapex;
-                while (X[farrightapex] > X[farrightpt]) {
+                while (P[farrightapex].x > P[farrightpt].x) {
                     farright = sym(lprev(farright));
                     farrightpt = farrightapex;
                     farrightapex = apex(farright);
@@ -191,86 +192,84 @@ void Mesh::merge(Handle &farleft, Handle &innerleft, Handle &innerright, Handle 
         }
         if (!leftfinished) {
             // would deleting the left candidate edge expose a vertex that violates the Delaunay property?
-            Handle next = sym(lprev(leftcand));
+            int next = sym(lprev(leftcand));
             int nextapex = apex(next);
-            if (nextapex >= 0) {
-                bool bad = incircle(lowerleft, lowerright, upperleft, nextapex) > 0;
-                while (bad) {
-                    // edge flip: the left triangulation gains one bounding record
-                    next = lnext(next);
-                    const Handle topcasing = sym(next);
-                    next = lnext(next);
-                    const Handle sidecasing = sym(next);
-                    bond(next, topcasing);
-                    bond(leftcand, sidecasing);
-                    leftcand = lnext(leftcand);
-                    const Handle outercasing = sym(leftcand);
-                    next = lprev(next);
-                    bond(next, outercasing);
-                    setorg(leftcand, lowerleft);
-                    setdest(leftcand, -1);
-                    setapex(leftcand, nextapex);
-                    setorg(next, -1);
-                    setdest(next, upperleft);
-                    setapex(next, nextapex);
-                    upperleft = nextapex;
-                    next = sidecasing;
-                    nextapex = apex(next);
-                    bad = nextapex >= 0 ? incircle(lowerleft, lowerright, upperleft, nextapex) > 0 : false;
-                }
+            while (nextapex >= 0 && incircle(pll, plr, pul, P[nextapex]) > 0) {
+                // edge flip: the left triangulation gains one bounding record
+                next = lnext(next);
+                const int topcasing = sym(next);
+                next = lnext(next);
+                const int sidecasing = sym(next);
+                bond(next, topcasing);
+                bond(leftcand, sidecasing);
+                leftcand = lnext(leftcand);
+                const int outercasing = sym(leftcand);
+                next = lprev(next);
+                bond(next, outercasing);
+                setorg(leftcand, lowerleft);
+                setdest(leftcand, -1);
+                setapex(leftcand, nextapex);
+                setorg(next, -1);
+                setdest(next, upperleft);
+                setapex(next, nextapex);
+                upperleft = nextapex;
+                pul = P[nextapex];
+                next = sidecasing;
+                nextapex = apex(next);
             }
         }
         if (!rightfinished) {
-            Handle next = sym(lnext(rightcand));
+            int next = sym(lnext(rightcand));
             int nextapex = apex(next);
-            if (nextapex >= 0) {
-                bool bad = incircle(lowerleft, lowerright, upperright, nextapex) > 0;
-                while (bad) {
-                    next = lprev(next);
-                    const Handle topcasing = sym(next);
-                    next = lprev(next);
-                    const Handle sidecasing = sym(next);
-                    bond(next, topcasing);
-                    bond(rightcand, sidecasing);
-                    rightcand = lprev(rightcand);
-                    const Handle outercasing = sym(rightcand);
-                    next = lnext(next);
-                    bond(next, outercasing);
-                    setorg(rightcand, -1);
-                    setdest(rightcand, lowerright);
-                    setapex(rightcand, nextapex);
-                    setorg(next, upperright);
-                    setdest(next, -1);
-                    setapex(next, nextapex);
-                    upperright = nextapex;
-                    next = sidecasing;
-                    nextapex = apex(next);
-                    bad = nextapex >= 0 ? incircle(lowerleft, lowerright, upperright, nextapex) > 0 : false;
-                }
+            while (nextapex >= 0 && incircle(pll, plr, pur, P[nextapex]) > 0) {
+                next = lprev(next);
+                const int topcasing = sym(next);
+                next = lprev(next);
+                const int sidecasing = sym(next);
+                bond(next, topcasing);
+                bond(rightcand, sidecasing);
+                rightcand = lprev(rightcand);
+                const int outercasing = sym(rightcand);
+                next = lnext(next);
+                bond(next, outercasing);
+                setorg(rightcand, -1);
+                setdest(rightcand, lowerright);
+                setapex(rightcand, nextapex);
+                setorg(next, upperright);
+                setdest(next, -1);
+                setapex(next, nextapex);
+                upperright = nextapex;
+                pur = P[nextapex];
+                next = sidecasing;
+                nextapex = apex(next);
             }
         }
-        if (leftfinished || (!rightfinished && incircle(upperleft, lowerleft, lowerright, upperright) > 0)) {
+        if (leftfinished || (!rightfinished && incircle(pul, pll, plr, pur) > 0)) {
             // new edge lowerleft -- upperright
             bond(base, rightcand);
             base = lprev(rightcand);
             setdest(base, lowerleft);
             lowerright = upperright;
+            plr = pur;
             rightcand = sym(base);
             upperright = apex(rightcand);
+            pur = P[upperright];
         } else {
             // new edge upperleft -- lowerright (also taken on a co-circular tie)
             bond(base, leftcand);
             base = lnext(leftcand);
             setorg(base, lowerright);
             lowerleft = upperleft;
+            pll = pul;
             leftcand = sym(base);
             upperleft = apex(leftcand);
+            pul = P[upperleft];
         }
     }
 }
 
 // triangle.cpp:5670-5815
-void Mesh::recurse(const int32_t *s, int count, int axis, Handle &farleft, Handle &farright) {
+void Mesh::recurse(const int32_t *s, int count, int axis, int &farleft, int &farright) {
     if (count == 2) {
         // an edge: two bounding records glued along all three sides
         farleft = make();
@@ -290,7 +289,7 @@ void Mesh::recurse(const int32_t *s, int count, int axis, Handle &farleft, Handl
         return;
     }
     if (count == 3) {
-        Handle mid = make(), t1 = make(), t2 = make(), t3 = make();
+        int mid = make(), t1 = make(), t2 = make(), t3 = make();
         const int64_t area = ccw(s[0], s[1], s[2]);
         if (area == 0) {
             // collinear: two edges, four bounding records
@@ -358,7 +357,7 @@ void Mesh::recurse(const int32_t *s, int count, int axis, Handle &farleft, Handl
         return;
     }
     const int divider = count >> 1;
-    Handle innerleft, innerright;
+    int innerleft, innerright;
     recurse(s, divider, 1 - axis, farleft, innerleft);
     recurse(s + divider, count - divider, 1 - axis, innerright, farright);
     merge(farleft, innerleft, innerright, farright, axis);
@@ -400,69 +399,165 @@ void lex_quicksort(int32_t *a, int n, const LexXY &c, Lcg &rng) {
     if (right < n - 2) lex_quicksort(a + right + 1, n - right - 1, c, rng);
 }
 
-// Alternating-axis partition (triangle.cpp:5307-5325).  Only the SETS on either side of each median matter
-// (keys are distinct after duplicate removal), so a deterministic selection replaces the randomised one.
-void alternate_axes(int32_t *a, int n, int axis, const int32_t *X, const int32_t *Y) {
-    const int divider = n >> 1;
-    if (n <= 3) axis = 0;
-    const int32_t *K0 = axis ? Y : X, *K1 = axis ? X : Y;
-    std::nth_element(a, a + divider, a + n, [K0, K1](int p, int q) { return K0[p] < K0[q] || (K0[p] == K0[q] && K1[p] < K1[q]); });
-    if (n - divider >= 2) {
-        if (divider >= 2) alternate_axes(a, divider, 1 - axis, X, Y);
-        alternate_axes(a + divider, n - divider, 1 - axis, X, Y);
+// Lexicographic order of duplicate-free input: LSD radix sort, 3 passes of 9 bits over key = (x + 8192) << 13 | y.
+// item = key << 32 | index.  Returns false (nothing usable in `a`) when a coordinate is out of range.
+const int RADIX_BITS = 9, RADIX = 1 << RADIX_BITS;
+bool radix_lex_sort(const int32_t *x, const int32_t *y, int n, uint64_t *a, uint64_t *b) {
+    uint32_t hist[3][RADIX];
+    std::memset(hist, 0, sizeof(hist));
+    uint32_t bad = 0;
+    for (int i = 0; i < n; i++) {
+        const uint32_t xb = (uint32_t)(x[i] + 8192), yb = (uint32_t)y[i];
+        bad |= (xb >> 14) | (yb >> 13);
+        const uint32_t key = xb << 13 | yb;
+        a[i] = (uint64_t)key << 32 | (uint32_t)i;
+        hist[0][key & (RADIX - 1)]++;
+        hist[1][(key >> RADIX_BITS) & (RADIX - 1)]++;
+        hist[2][(key >> (2 * RADIX_BITS)) & (RADIX - 1)]++;
     }
+    if (bad) return false;
+    for (int p = 0; p < 3; p++) {
+        uint32_t sum = 0;
+        for (int k = 0; k < RADIX; k++) {
+            const uint32_t c = hist[p][k];
+            hist[p][k] = sum;
+            sum += c;
+        }
+    }
+    for (int p = 0; p < 3; p++) {
+        const int shift = 32 + p * RADIX_BITS;
+        uint32_t *h = hist[p];
+        for (int i = 0; i < n; i++) b[h[(a[i] >> shift) & (RADIX - 1)]++] = a[i];
+        std::swap(a, b);
+    }
+    return true;  // three passes: the result is in the array that was passed as `b`
+}
+
+// Alternating-axis median partition (triangle.cpp:5243-5325) over rank pairs e = xrank << 32 | yrank.  Lx holds the
+// subset in x order, Ly the same subset in y order; splitting along one axis is a cut of that axis' list and a stable
+// (order-preserving) split of the other one.  Subsets of <= 3 are emitted in x order.
+void kd_partition(uint64_t *Lx, uint64_t *Ly, uint64_t *tmp, int n, int axis, int32_t *out) {
+    if (n <= 3) {
+        for (int i = 0; i < n; i++) out[i] = (int32_t)(Lx[i] >> 32);
+        return;
+    }
+    const int divider = n >> 1;
+    int lo = 0, hi = 0;
+    if (axis == 0) {
+        const uint32_t pivot = (uint32_t)(Lx[divider] >> 32);
+        for (int i = 0; i < n; i++) {
+            const uint64_t e = Ly[i];
+            const int low = (uint32_t)(e >> 32) < pivot;
+            Ly[lo] = e;  // lo <= i: never overtakes the read position
+            tmp[hi] = e;
+            lo += low;
+            hi += 1 - low;
+        }
+        std::memcpy(Ly + divider, tmp, sizeof(uint64_t) * hi);
+    } else {
+        const uint32_t pivot = (uint32_t)Ly[divider];
+        for (int i = 0; i < n; i++) {
+            const uint64_t e = Lx[i];
+            const int low = (uint32_t)e < pivot;
+            Lx[lo] = e;
+            tmp[hi] = e;
+            lo += low;
+            hi += 1 - low;
+        }
+        std::memcpy(Lx + divider, tmp, sizeof(uint64_t) * hi);
+    }
+    kd_partition(Lx, Ly, tmp, divider, 1 - axis, out);
+    kd_partition(Lx + divider, Ly + divider, tmp, n - divider, 1 - axis, out + divider);
 }
 
 }  // namespace
 
 int delaunay_xy(const int32_t *x, const int32_t *y, int n, int32_t *tri_out, int cap, DelaunayScratch &scratch) {
     if (n < 3) return 0;
-    // arena: [X sentinel + n][Y sentinel + n][sorted n][nbr 3*R][vtx 3*R],  R <= 1 + 2 records per vertex + merges
+    // arena (int32 units): [5 n uint64: sort ping-pong / Lx, Ly, tmp][{x,y} sentinel + n][vid n][sorted n]
+    //                      [records 8 R],  R <= 1 + 2 records per vertex + merges
     const size_t max_records = 1 + (size_t)4 * n + 16;
-    const size_t need = 2 * (size_t)(n + 1) + n + 6 * max_records;
+    const size_t need = 10 * (size_t)n + 2 * (size_t)(n + 1) + 2 * (size_t)n + 8 * max_records + 2;
     if (scratch.storage.size() < need) scratch.storage.resize(need);
     int32_t *base = scratch.storage.data();
-    int32_t *X = base + 1, *Y = X + n + 1, *sorted = Y + n, *nbr = sorted + n, *vtx = nbr + 3 * max_records;
-    X[-1] = 0;
-    Y[-1] = 0;
-    std::memcpy(X, x, sizeof(int32_t) * n);
-    std::memcpy(Y, y, sizeof(int32_t) * n);
-    for (int i = 0; i < n; i++) sorted[i] = i;
+    base += ((uintptr_t)base & 7) ? 1 : 0;  // 8-byte alignment for the uint64 arrays
+    uint64_t *A = (uint64_t *)base, *B = A + n, *Ly = B + n, *tmp = Ly + n;  // A / B double as the radix buffers
+    Pt *P = (Pt *)(A + 5 * (size_t)n) + 1;
+    int32_t *vid = (int32_t *)(P + n), *sorted = vid + n, *R = sorted + n;
+    P[-1] = Pt{0, 0};
 
-    LexXY cmp{X, Y};
-    Lcg rng;
-    lex_quicksort(sorted, n, cmp, rng);
-    int m = 0;  // drop duplicates, keeping the first of each run (triangle.cpp:5890-5903)
-    for (int j = 1; j < n; j++)
-        if (!(X[sorted[m]] == X[sorted[j]] && Y[sorted[m]] == Y[sorted[j]])) sorted[++m] = sorted[j];
-    m++;
-    if (m < 3) return 0;
-    {
-        const int divider = m >> 1;
-        if (m - divider >= 2) {
-            if (divider >= 2) alternate_axes(sorted, divider, 1, X, Y);
-            alternate_axes(sorted + divider, m - divider, 1, X, Y);
+    // 1. lexicographic order, duplicates dropped (keeping the first of each run, triangle.cpp:5890-5903)
+    int m = 0;
+    bool fast = radix_lex_sort(x, y, n, A, B);
+    if (fast) {
+        const uint64_t *S = B;  // see radix_lex_sort
+        for (int i = 1; i < n; i++)
+            if ((S[i] >> 32) == (S[i - 1] >> 32)) {
+                fast = false;  // which duplicate survives depends on the reference's sort: take the restated path
+                break;
+            }
+        if (fast) {
+            for (int i = 0; i < n; i++) vid[i] = (int32_t)(uint32_t)S[i];
+            m = n;
         }
     }
+    if (!fast) {
+        for (int i = 0; i < n; i++) vid[i] = i;
+        LexXY cmp{x, y};
+        Lcg rng;
+        lex_quicksort(vid, n, cmp, rng);
+        for (int j = 1; j < n; j++)
+            if (!(x[vid[m]] == x[vid[j]] && y[vid[m]] == y[vid[j]])) vid[++m] = vid[j];
+        m++;
+    }
+    if (m < 3) return 0;
+    int ymin = y[vid[0]], ymax = ymin;
+    for (int i = 0; i < m; i++) {
+        P[i] = Pt{x[vid[i]], y[vid[i]]};
+        ymin = std::min(ymin, P[i].y);
+        ymax = std::max(ymax, P[i].y);
+    }
 
+    // 2. rank of every vertex in (y, x) order: a stable sort by y of the x-ordered list
+    uint64_t *Lx = A;
+    if ((int64_t)ymax - ymin + 2 <= (int64_t)(8 * max_records)) {  // the counting array borrows the record arena
+        const int span = ymax - ymin + 1;
+        int32_t *cnt = R;  // free until step 4
+        std::memset(cnt, 0, sizeof(int32_t) * (span + 1));
+        for (int i = 0; i < m; i++) cnt[P[i].y - ymin + 1]++;
+        for (int k = 0; k < span; k++) cnt[k + 1] += cnt[k];
+        for (int i = 0; i < m; i++) {
+            const int pos = cnt[P[i].y - ymin]++;
+            sorted[pos] = i;
+        }
+    } else {
+        for (int i = 0; i < m; i++) sorted[i] = i;
+        std::stable_sort(sorted, sorted + m, [P](int p, int q) { return P[p].y < P[q].y; });
+    }
+    for (int r = 0; r < m; r++) Lx[sorted[r]] = (uint64_t)(uint32_t)sorted[r] << 32 | (uint32_t)r;
+    for (int r = 0; r < m; r++) Ly[r] = Lx[sorted[r]];
+
+    // 3. alternating cuts; `sorted` receives the vertex ids in recursion order
+    kd_partition(Lx, Ly, tmp, m, 0, sorted);
+
+    // 4. divide and conquer
     Mesh mesh;
-    mesh.X = X;
-    mesh.Y = Y;
-    mesh.nbr = nbr;
-    mesh.vtx = vtx;
+    mesh.P = P;
+    mesh.R = R;
     mesh.ntri = 0;
     mesh.make();  // record 0: outer space
-    Handle hullleft, hullright;
+    int hullleft, hullright;
     mesh.recurse(sorted, m, 0, hullleft, hullright);
 
     int count = 0;
     for (int t = 1; t < mesh.ntri; t++) {
-        const int a = vtx[3 * t + 1], b = vtx[3 * t + 2], c = vtx[3 * t];  // org, dest, apex at orientation 0
-        if (a < 0 || b < 0 || c < 0) continue;                            // bounding record (removeghosts, :5817-5859)
+        const int32_t *r = R + 8 * t + 4;
+        const int a = r[1], b = r[2], c = r[0];  // org, dest, apex at orientation 0
+        if ((a | b | c) < 0) continue;           // bounding record (removeghosts, :5817-5859)
         if (count < cap) {
-            tri_out[3 * count] = a;
-            tri_out[3 * count + 1] = b;
-            tri_out[3 * count + 2] = c;
+            tri_out[3 * count] = vid[a];
+            tri_out[3 * count + 1] = vid[b];
+            tri_out[3 * count + 2] = vid[c];
         }
         count++;
     }
@@ -473,7 +568,7 @@ int delaunay_support(const int32_t *support, int n, int right_image, int32_t *tr
     if (n < 3) return 0;
     // coordinates are staged at the tail of the arena, past everything delaunay_xy lays out for n points
     const size_t max_records = 1 + (size_t)4 * n + 16;
-    const size_t need = 2 * (size_t)(n + 1) + n + 6 * max_records;
+    const size_t need = 10 * (size_t)n + 2 * (size_t)(n + 1) + 2 * (size_t)n + 8 * max_records + 2;
     if (scratch.storage.size() < need + 2 * (size_t)n) scratch.storage.resize(need + 2 * (size_t)n);
     int32_t *xs = scratch.storage.data() + need, *ys = xs + n;
     for (int i = 0; i < n; i++) {
