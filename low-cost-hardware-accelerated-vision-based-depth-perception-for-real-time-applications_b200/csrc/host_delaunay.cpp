@@ -16,7 +16,7 @@
 // Unlike the reference (float coordinates + adaptive-precision floating point predicates) every predicate here
 // is evaluated exactly in 64-bit integers: |coordinates| < 2^13 keeps orient2d below 2^28 and incircle below 2^56.
 // Triangle records are 32-byte rows {3 neighbour handles, 3 vertices} in one flat arena (no pointer pool, no per-call
-// malloc); a handle is one int (record << 2 | orientation).
+// malloc); a handle is one int (8 * record + orientation).
 //
 // What is restated and what is merely equivalent: the vertex sort and the median partitions of the reference are
 // randomised, but only two things they produce reach the output -- WHICH of several equal-coordinate vertices
@@ -32,7 +32,8 @@ namespace svb {
 
 namespace {
 
-// A handle is (record << 2 | orientation); record r occupies R[8r .. 8r+7] = {nbr0, nbr1, nbr2, -, vtx0, vtx1, vtx2, -}.
+// Record r occupies R[8r .. 8r+7] = {nbr0, nbr1, nbr2, -, vtx0, vtx1, vtx2, -}; a handle is (8r + orientation), i.e.
+// the index of its own neighbour slot, and its apex sits four ints further.
 struct Pt {
     int32_t x, y;
 };
@@ -44,8 +45,8 @@ struct Mesh {
 
     static int lnext(int e) { return (e & 3) == 2 ? e - 2 : e + 1; }
     static int lprev(int e) { return (e & 3) == 0 ? e + 2 : e - 1; }
-    int &nbr(int e) { return R[2 * e - (e & 3)]; }
-    int &vtx(int e) { return R[2 * e - (e & 3) + 4]; }
+    int &nbr(int e) { return R[e]; }
+    int &vtx(int e) { return R[e + 4]; }
     int apex(int e) { return vtx(e); }
     int org(int e) { return vtx(lnext(e)); }
     int dest(int e) { return vtx(lprev(e)); }
@@ -63,7 +64,7 @@ struct Mesh {
         int32_t *r = R + 8 * t;
         r[0] = r[1] = r[2] = r[3] = 0;
         r[4] = r[5] = r[6] = r[7] = -1;
-        return t << 2;
+        return t << 3;
     }
 
     // exact orientation: > 0 iff a, b, c are counter-clockwise.  |coordinate differences| < 2^14: 32-bit exact.
@@ -433,41 +434,52 @@ bool radix_lex_sort(const int32_t *x, const int32_t *y, int n, uint64_t *a, uint
     return true;  // three passes: the result is in the array that was passed as `b`
 }
 
-// Alternating-axis median partition (triangle.cpp:5243-5325) over rank pairs e = xrank << 32 | yrank.  Lx holds the
-// subset in x order, Ly the same subset in y order; splitting along one axis is a cut of that axis' list and a stable
-// (order-preserving) split of the other one.  Subsets of <= 3 are emitted in x order.
-void kd_partition(uint64_t *Lx, uint64_t *Ly, uint64_t *tmp, int n, int axis, int32_t *out) {
+// Alternating-axis median partition (triangle.cpp:5243-5325) over rank pairs e = xrank << HALF | yrank (32-bit
+// elements while the ranks fit 16 bits, 64-bit ones otherwise).  Lx holds the subset in x order, Ly the same subset in
+// y order; splitting along one axis is a cut of that axis' list and a stable (order-preserving) split of the other
+// one.  Subsets of <= 3 are emitted in x order.
+template <typename E, int HALF>
+void kd_partition(E *Lx, E *Ly, E *tmp, int n, int axis, int32_t *out) {
+    const E LOW = ((E)1 << HALF) - 1;
     if (n <= 3) {
-        for (int i = 0; i < n; i++) out[i] = (int32_t)(Lx[i] >> 32);
+        for (int i = 0; i < n; i++) out[i] = (int32_t)(Lx[i] >> HALF);
         return;
     }
     const int divider = n >> 1;
     int lo = 0, hi = 0;
     if (axis == 0) {
-        const uint32_t pivot = (uint32_t)(Lx[divider] >> 32);
+        const E pivot = Lx[divider] >> HALF;
         for (int i = 0; i < n; i++) {
-            const uint64_t e = Ly[i];
-            const int low = (uint32_t)(e >> 32) < pivot;
+            const E e = Ly[i];
+            const int low = (e >> HALF) < pivot;
             Ly[lo] = e;  // lo <= i: never overtakes the read position
             tmp[hi] = e;
             lo += low;
             hi += 1 - low;
         }
-        std::memcpy(Ly + divider, tmp, sizeof(uint64_t) * hi);
+        for (int i = 0; i < hi; i++) Ly[divider + i] = tmp[i];
     } else {
-        const uint32_t pivot = (uint32_t)Ly[divider];
+        const E pivot = Ly[divider] & LOW;
         for (int i = 0; i < n; i++) {
-            const uint64_t e = Lx[i];
-            const int low = (uint32_t)e < pivot;
+            const E e = Lx[i];
+            const int low = (e & LOW) < pivot;
             Lx[lo] = e;
             tmp[hi] = e;
             lo += low;
             hi += 1 - low;
         }
-        std::memcpy(Lx + divider, tmp, sizeof(uint64_t) * hi);
+        for (int i = 0; i < hi; i++) Lx[divider + i] = tmp[i];
     }
-    kd_partition(Lx, Ly, tmp, divider, 1 - axis, out);
-    kd_partition(Lx + divider, Ly + divider, tmp, n - divider, 1 - axis, out + divider);
+    kd_partition<E, HALF>(Lx, Ly, tmp, divider, 1 - axis, out);
+    kd_partition<E, HALF>(Lx + divider, Ly + divider, tmp, n - divider, 1 - axis, out + divider);
+}
+
+template <typename E, int HALF>
+void kd_order(const int32_t *by_y, int m, void *arena, int32_t *out) {
+    E *Lx = (E *)arena, *Ly = Lx + m, *tmp = Ly + m;
+    for (int r = 0; r < m; r++) Lx[by_y[r]] = (E)(uint32_t)by_y[r] << HALF | (E)(uint32_t)r;
+    for (int r = 0; r < m; r++) Ly[r] = Lx[by_y[r]];
+    kd_partition<E, HALF>(Lx, Ly, tmp, m, 0, out);
 }
 
 }  // namespace
@@ -481,7 +493,7 @@ int delaunay_xy(const int32_t *x, const int32_t *y, int n, int32_t *tri_out, int
     if (scratch.storage.size() < need) scratch.storage.resize(need);
     int32_t *base = scratch.storage.data();
     base += ((uintptr_t)base & 7) ? 1 : 0;  // 8-byte alignment for the uint64 arrays
-    uint64_t *A = (uint64_t *)base, *B = A + n, *Ly = B + n, *tmp = Ly + n;  // A / B double as the radix buffers
+    uint64_t *A = (uint64_t *)base, *B = A + n;  // radix buffers, then the rank lists of step 3
     Pt *P = (Pt *)(A + 5 * (size_t)n) + 1;
     int32_t *vid = (int32_t *)(P + n), *sorted = vid + n, *R = sorted + n;
     P[-1] = Pt{0, 0};
@@ -519,7 +531,7 @@ int delaunay_xy(const int32_t *x, const int32_t *y, int n, int32_t *tri_out, int
     }
 
     // 2. rank of every vertex in (y, x) order: a stable sort by y of the x-ordered list
-    uint64_t *Lx = A;
+    int32_t *by_y = (int32_t *)(A + 3 * (size_t)n);  // the last two of the five uint64 arrays
     if ((int64_t)ymax - ymin + 2 <= (int64_t)(8 * max_records)) {  // the counting array borrows the record arena
         const int span = ymax - ymin + 1;
         int32_t *cnt = R;  // free until step 4
@@ -528,17 +540,18 @@ int delaunay_xy(const int32_t *x, const int32_t *y, int n, int32_t *tri_out, int
         for (int k = 0; k < span; k++) cnt[k + 1] += cnt[k];
         for (int i = 0; i < m; i++) {
             const int pos = cnt[P[i].y - ymin]++;
-            sorted[pos] = i;
+            by_y[pos] = i;
         }
     } else {
-        for (int i = 0; i < m; i++) sorted[i] = i;
-        std::stable_sort(sorted, sorted + m, [P](int p, int q) { return P[p].y < P[q].y; });
+        for (int i = 0; i < m; i++) by_y[i] = i;
+        std::stable_sort(by_y, by_y + m, [P](int p, int q) { return P[p].y < P[q].y; });
     }
-    for (int r = 0; r < m; r++) Lx[sorted[r]] = (uint64_t)(uint32_t)sorted[r] << 32 | (uint32_t)r;
-    for (int r = 0; r < m; r++) Ly[r] = Lx[sorted[r]];
 
     // 3. alternating cuts; `sorted` receives the vertex ids in recursion order
-    kd_partition(Lx, Ly, tmp, m, 0, sorted);
+    if (m <= 65535)
+        kd_order<uint32_t, 16>(by_y, m, A, sorted);
+    else
+        kd_order<uint64_t, 32>(by_y, m, A, sorted);
 
     // 4. divide and conquer
     Mesh mesh;

@@ -15,8 +15,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "host_delaunay.h"
@@ -948,19 +950,83 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
         }
         return stage_a(c, L, c->in_img[0] + off, c->in_img[1] + off, nf, stage_events_of(c, k));
     };
-    for (int k = 0; k < nchunks && k < LANES; k++) SVB_TRY(issue_a(k));
-    for (int k = 0; k < nchunks; k++) {
-        Lane &L = c->lanes[k % LANES];
-        const int nf = frames_of(k);
-        SVB_TRY(stage_host(c, L, nf));
-        const size_t off = (size_t)k * C * N, offD = (size_t)k * C * DN;
-        SVB_TRY(stage_b(c, L, nf, want_D ? c->out_D1 + offD : nullptr, want_P ? c->out_points + off * 3 : nullptr, stage_events_of(c, k)));
-        if (from_host) {
-            if (want_D && h_D1) SVB_CUDA(cudaMemcpyAsync(h_D1 + offD, c->out_D1 + offD, nf * DN * 4, cudaMemcpyDeviceToHost, L.stream));
-            if (want_P && h_points)
-                SVB_CUDA(cudaMemcpyAsync(h_points + off * 3, c->out_points + off * 3, nf * N * 24, cudaMemcpyDeviceToHost, L.stream));
+    // The host stage runs on its own thread, one chunk ahead of the launches: while this thread queues stage B of
+    // chunk k and stage A of chunk k + LANES, the Delaunay workers already triangulate chunk k + 1.  `issued` counts
+    // the chunks whose stage A (and with it the event the host stage waits for) has been queued.
+    struct HostStage {
+        std::mutex mu;
+        std::condition_variable cv;
+        int issued = 0, done = 0, err = SVB_OK;
+        bool stop = false;
+        char msg[1024] = "";  // the error text is thread-local: carried over to the calling thread
+    } hs;
+    std::thread host_thread([&] {
+        cudaSetDevice(c->device);
+        for (int k = 0; k < nchunks; k++) {
+            {
+                std::unique_lock<std::mutex> lk(hs.mu);
+                hs.cv.wait(lk, [&] { return hs.issued > k || hs.stop; });
+                if (hs.stop) return;
+            }
+            const int rc = stage_host(c, c->lanes[k % LANES], frames_of(k));
+            std::lock_guard<std::mutex> lk(hs.mu);
+            if (rc != SVB_OK) {
+                hs.err = rc;
+                snprintf(hs.msg, sizeof(hs.msg), "%s", g_err);
+                hs.done = nchunks;
+                hs.cv.notify_all();
+                return;
+            }
+            hs.done = k + 1;
+            hs.cv.notify_all();
         }
-        if (k + LANES < nchunks) SVB_TRY(issue_a(k + LANES));
+    });
+    auto drive = [&]() -> int {
+        for (int k = 0; k < nchunks && k < LANES; k++) {
+            SVB_TRY(issue_a(k));
+            std::lock_guard<std::mutex> lk(hs.mu);
+            hs.issued = k + 1;
+            hs.cv.notify_all();
+        }
+        for (int k = 0; k < nchunks; k++) {
+            Lane &L = c->lanes[k % LANES];
+            const int nf = frames_of(k);
+            {
+                std::unique_lock<std::mutex> lk(hs.mu);
+                hs.cv.wait(lk, [&] { return hs.done > k; });
+                if (hs.err != SVB_OK) {
+                    set_error("%s", hs.msg);
+                    return hs.err;
+                }
+            }
+            const size_t off = (size_t)k * C * N, offD = (size_t)k * C * DN;
+            SVB_TRY(stage_b(c, L, nf, want_D ? c->out_D1 + offD : nullptr, want_P ? c->out_points + off * 3 : nullptr, stage_events_of(c, k)));
+            if (from_host) {
+                if (want_D && h_D1) SVB_CUDA(cudaMemcpyAsync(h_D1 + offD, c->out_D1 + offD, nf * DN * 4, cudaMemcpyDeviceToHost, L.stream));
+                if (want_P && h_points)
+                    SVB_CUDA(cudaMemcpyAsync(h_points + off * 3, c->out_points + off * 3, nf * N * 24, cudaMemcpyDeviceToHost, L.stream));
+            }
+            if (k + LANES < nchunks) {
+                SVB_TRY(issue_a(k + LANES));
+                std::lock_guard<std::mutex> lk(hs.mu);
+                hs.issued = k + LANES + 1;
+                hs.cv.notify_all();
+            }
+        }
+        return SVB_OK;
+    };
+    const int drive_rc = drive();
+    {
+        std::lock_guard<std::mutex> lk(hs.mu);
+        hs.stop = true;
+        hs.cv.notify_all();
+    }
+    host_thread.join();
+    if (drive_rc != SVB_OK) {
+        cudaDeviceSynchronize();
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        return drive_rc;
     }
     for (int l = 1; l < LANES; l++) {
         SVB_CUDA(cudaEventRecord(c->lanes[l].ev_done, c->lanes[l].stream));
