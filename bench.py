@@ -322,6 +322,14 @@ def main():
     stage_ms = exact_run["stage_ms"]
     value_single_stream = sum_over_ranks(float(args.batch * args.steps)) / (max_over_ranks(exact_run["gpu_ms"]) * 1e-3)
 
+    # ---- pixel-disparity evaluations (SURVEY.md 8d ii): one untimed step with the counting kernels -------------------
+    ctx.set_eval_counting(True)
+    ctx.batch_run(args.batch, flags)
+    n_support_hyp, n_dense_hyp = ctx.eval_counts()
+    ctx.set_eval_counting(False)
+    support_hyp = sum_over_ranks(float(n_support_hyp)) / (args.batch * world)
+    dense_hyp = sum_over_ranks(float(n_dense_hyp)) / (args.batch * world)
+
     # ---- end to end from pinned host buffers ----------------------------------------------------------------
     nb = min(args.e2e_batch, args.batch)
     hl = svb.PinnedArray((nb, H, W), np.uint8)
@@ -370,7 +378,15 @@ def main():
             per_stage[k] = {"us_per_frame": 1e3 * v / (args.batch * args.steps)}
     if top:
         ach = per_stage[top]["GBps"]
-        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernels per launch of `ncu_frames_per_launch` frames, from the
+        # committed `ncu --set full` capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py), scaled to this chunk size
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if top in tj.get("stages", {}):
+                traffic = tj["stages"][top]["dram_bytes_per_launch"] * args.chunk / tj["frames_per_launch"]
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_launch": sb[top] * args.chunk,
                 "avg_launch_ms": kernel_stages[top] / nlaunch_per_stage,
                 "share_of_step": kernel_stages[top] / sum(stage_ms.values()),
@@ -401,6 +417,11 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * N * nb, "d2h_bytes_per_step": (4 + 24) * N * nb,
                     "frames_per_step": nb, "steps": e2e_steps},
             "gpu_launches": int(launches),
+            "pixel_disparity_evals": {
+                "support_hypotheses_per_frame": support_hyp, "dense_hypotheses_per_frame": dense_hyp,
+                "evals_per_s": (support_hyp + dense_hyp) * value, "sad16_per_s": (4.0 * support_hyp + dense_hyp) * value,
+                "note": "hypotheses the reference algorithm evaluates for exactly these frames (support: 4 x 16-byte SAD each, forward + "
+                        "backward pass; dense: one 16-byte SAD each), counted on the device by an untimed step (svb_set_eval_counting)"},
             "roofline": roof,
             "cpu_baseline": cpu,
             "clocks": clocks,

@@ -87,6 +87,13 @@ int svb_set_delaunay_threads(svb_context *ctx, int n_threads);
 /* on: every lane issues its GPU work on ONE stream (kernels never overlap one another, so the per-stage CUDA-event
  * times of svb_stats are exact); off (default): one stream per lane. */
 int svb_set_single_stream(svb_context *ctx, int on);
+/* Measurement aid ("pixel-disparity evaluations"): while on, the two matching kernels also count the
+ * hypotheses the reference algorithm evaluates -- support matching: every d of a candidate's range, forward and
+ * backward (elas.cpp:330, one hypothesis = four 16-byte SADs); dense matching: grid candidates outside the plane band
+ * plus the band, warped column inside the image (elas.cpp:759-793, one 16-byte SAD each).  svb_get_eval_counts returns
+ * the totals since the last call and resets them.  Off by default: the timed kernels carry no counting code. */
+int svb_set_eval_counting(svb_context *ctx, int on);
+int svb_get_eval_counts(svb_context *ctx, uint64_t *support_hypotheses, uint64_t *dense_hypotheses);
 
 /* Elas::process (src/parallel_includes/elas/elas.h:151-160, serial semantics of
  * src/serial_includes/elas/elas.cpp:31-150).  Host buffers; I1/I2 are u8 with `stride` bytes per

@@ -112,6 +112,8 @@ def load():
         "svb_set_delaunay_threads": [vp, C.c_int],
         "svb_set_stage_timing": [vp, C.c_int],
         "svb_set_single_stream": [vp, C.c_int],
+        "svb_set_eval_counting": [vp, C.c_int],
+        "svb_get_eval_counts": [vp, vp, vp],
         "svb_set_tap_mode": [vp, C.c_int],
         "svb_process": [vp, vp, vp, C.c_int, vp, vp],
         "svb_inject_triangles": [vp, C.c_int, vp, C.c_int],
@@ -351,6 +353,15 @@ class Context:
 
     def set_single_stream(self, on=True):
         self._chk(self.lib.svb_set_single_stream(self.h, int(on)))
+
+    def set_eval_counting(self, on=True):
+        self._chk(self.lib.svb_set_eval_counting(self.h, int(on)))
+
+    def eval_counts(self):
+        """(support hypotheses, dense hypotheses) counted since the last call; see svb_set_eval_counting."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._chk(self.lib.svb_get_eval_counts(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def set_delaunay_threads(self, n):
         self._chk(self.lib.svb_set_delaunay_threads(self.h, int(n)))

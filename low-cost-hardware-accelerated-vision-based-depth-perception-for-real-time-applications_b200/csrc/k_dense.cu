@@ -30,6 +30,7 @@ struct DenseArgs {
     int Dw, DN, shift;  // disparity map width / size and log2 of the pixel step (1 with subsampling: map pixel (x,y) = image (2x,2y))
     unsigned grid_magic;  // ceil(2^32 / grid_size)
     int P[8];
+    unsigned long long *evals;  // COUNT variant only: number of evaluated hypotheses (elas.cpp:759-793)
 };
 
 __device__ __forceinline__ unsigned sad16_acc(const uint4 &a, const uint4 &b, unsigned acc) {
@@ -69,8 +70,9 @@ __device__ __forceinline__ uint32_t range_mask(int lo, int hi, int base) {
 //   (elas.cpp:757-794: grid candidates ascending, then the band ascending).  min_val starts at 10000 > any cost.
 // RADIUS > 0: plane radius known at compile time (the band loop is fully unrolled and all of its loads are issued up
 // front); RADIUS == 0: generic radius from the arguments.
-template <int SIDE, int RADIUS>
+template <int SIDE, int RADIUS, bool COUNT>
 __device__ __forceinline__ void dense_body(const DenseArgs &a) {
+    unsigned n_hyp = 0u;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;  // map pixel
     const int y = a.row0 + blockIdx.y;
     const int u = x << a.shift, v = y << a.shift;         // image pixel (elas.cpp:707-711: d_addr = (u/2, v/2) when subsampling)
@@ -128,6 +130,7 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
             const int w = w4 + j;
             uint32_t mine = j == 0 ? m4.x : j == 1 ? m4.y : j == 2 ? m4.z : m4.w;
             if (mine) mine &= ~range_mask(dmin, dmax, w << 5) & range_mask(dlo, dhi, w << 5);
+            if (COUNT) n_hyp += __popc(mine);
             uint32_t uni = __reduce_or_sync(0xFFFFFFFFu, mine);
             while (uni) {
                 // two candidates per trip: both loads are in flight before either SAD chain starts
@@ -160,6 +163,7 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
             okb[k + RADIUS] = (unsigned)(d - lo3) <= span;
             dsb[k + RADIUS] = okb[k + RADIUS] ? d : 0;
             ob[k + RADIUS] = __ldg(desc_at(po, SIDE ? dsb[k + RADIUS] : -dsb[k + RADIUS]));
+            if (COUNT) n_hyp += okb[k + RADIUS] ? 1u : 0u;
         }
 #pragma unroll
         for (int k = -RADIUS; k <= RADIUS; k++) {
@@ -172,6 +176,7 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
         for (int k = -r; k <= r; k++) {
             const int d = (int)((unsigned)d_plane + (unsigned)k);
             const bool ok = (unsigned)(d - lo3) <= span;
+            if (COUNT) n_hyp += ok ? 1u : 0u;
             const int ds = ok ? d : 0;
             const unsigned seed = 16u + ((unsigned)a.P[k < 0 ? -k : k] & prior_on);
             const unsigned cost = sad16_acc(c, __ldg(desc_at(po, SIDE ? ds : -ds)), seed);
@@ -184,14 +189,18 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
         if (active) out = key != 0xFFFFFFFFu ? (float)(key & 0xFFFu) : -1.f;  // elas.cpp:797-800
         D[pix] = out;
     }
+    if (COUNT) {
+        const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, n_hyp);
+        if ((threadIdx.x & 31) == 0 && tot) atomicAdd(a.evals + 1, (unsigned long long)tot);
+    }
 }
 
-template <int RADIUS>
+template <int RADIUS, bool COUNT>
 __global__ void __launch_bounds__(128) k_dense(const DenseArgs a) {
     if (blockIdx.z & 1)
-        dense_body<1, RADIUS>(a);
+        dense_body<1, RADIUS, COUNT>(a);
     else
-        dense_body<0, RADIUS>(a);
+        dense_body<0, RADIUS, COUNT>(a);
 }
 
 }  // namespace
@@ -239,12 +248,20 @@ int launch_dense_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, 
     }
     const int rows = d.sub ? d.Dh : row1 - row0;
     dim3 grid((d.Dw + 127) / 128, rows, nf * 2);
-    if (d.plane_radius == 2)
-        k_dense<2><<<grid, 128, 0, s>>>(a);
+    a.evals = d.evals;
+    if (d.evals) {
+        if (d.plane_radius == 2)
+            k_dense<2, true><<<grid, 128, 0, s>>>(a);
+        else if (d.plane_radius == 3)
+            k_dense<3, true><<<grid, 128, 0, s>>>(a);
+        else
+            k_dense<0, true><<<grid, 128, 0, s>>>(a);
+    } else if (d.plane_radius == 2)
+        k_dense<2, false><<<grid, 128, 0, s>>>(a);
     else if (d.plane_radius == 3)
-        k_dense<3><<<grid, 128, 0, s>>>(a);
+        k_dense<3, false><<<grid, 128, 0, s>>>(a);
     else
-        k_dense<0><<<grid, 128, 0, s>>>(a);
+        k_dense<0, false><<<grid, 128, 0, s>>>(a);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

@@ -48,15 +48,16 @@ __device__ __forceinline__ unsigned sad16_acc(const uint4 &a, const uint4 &b, un
 }
 
 // One pass over the patch: every lane holds one candidate (u, v) of image `own`; returns its disparity or -1.
-template <bool right_image>
+template <bool right_image, bool COUNT>
 __device__ __forceinline__ int match_pass(const uint4 *__restrict__ own, const uint4 *__restrict__ oth, int u, int v, bool has, int W, int H,
-                                          int disp_min, int disp_max, int support_texture, float support_threshold) {
+                                          int disp_min, int disp_max, int support_texture, float support_threshold, unsigned &n_hyp) {
     // candidate validity and disparity range (elas.cpp:279,296-300,318-327)
     bool ok = has && u >= 5 && u <= W - 6 && v >= 5 && v <= H - 6;
     if (ok) ok = (int)texture16(__ldg(own + (size_t)v * W + u)) >= support_texture;
     const int dmin = max(disp_min, 0);
     const int dmax = right_image ? min(disp_max, W - u - 5) : min(disp_max, u - 5);
     ok = ok && (dmax - dmin >= 10);
+    if (COUNT) n_hyp += ok ? (unsigned)(dmax - dmin + 1) : 0u;  // elas.cpp:330: every d of the range is evaluated
     if (!__any_sync(0xFFFFFFFFu, ok)) return -1;
     // matched columns x = u - d (left candidate) or u + d (right candidate)
     const int xlo = ok ? (right_image ? u + dmin : u - dmax) : 0x7FFFFFFF;
@@ -119,10 +120,12 @@ __device__ __forceinline__ int match_pass(const uint4 *__restrict__ own, const u
 }
 
 // grid: (ceil(#patches / SM_WARPS), nf); patches are numbered along the lattice row first
+// COUNT: also add up the evaluated hypotheses (svb_set_eval_counting); the timed kernel is the one without
+template <bool COUNT>
 __global__ void __launch_bounds__(SM_WARPS * 32) k_support_match(const uint8_t *__restrict__ desc1, const uint8_t *__restrict__ desc2,
                                                                  int16_t *__restrict__ dcan_raw, int W, int H, int cw, int ch, int step,
                                                                  int disp_min, int disp_max, int support_texture, float support_threshold,
-                                                                 int lr_threshold, int vc0, int vc1) {
+                                                                 int lr_threshold, int vc0, int vc1, unsigned long long *evals) {
     // lattice rows vc0 .. vc1-1 (1 .. ch-1 for a whole frame; a sub-range in the row-band split)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int pu = (cw - 1 + PATCH_U - 1) / PATCH_U, pv = (vc1 - vc0 + PATCH_V - 1) / PATCH_V;
@@ -139,9 +142,14 @@ __global__ void __launch_bounds__(SM_WARPS * 32) k_support_match(const uint8_t *
     const uint4 *d2 = reinterpret_cast<const uint4 *>(desc2) + fo;
 
     // forward: candidate in the left image, search the right image (elas.cpp:403)
-    const int d = match_pass<false>(d1, d2, u, v, has, W, H, disp_min, disp_max, support_texture, support_threshold);
+    unsigned n_hyp = 0u;
+    const int d = match_pass<false, COUNT>(d1, d2, u, v, has, W, H, disp_min, disp_max, support_texture, support_threshold, n_hyp);
     // backward: the match (u-d, v) as a candidate of the right image, search the left image (elas.cpp:406)
-    const int dback = match_pass<true>(d2, d1, u - d, v, has && d >= 0, W, H, disp_min, disp_max, support_texture, support_threshold);
+    const int dback = match_pass<true, COUNT>(d2, d1, u - d, v, has && d >= 0, W, H, disp_min, disp_max, support_texture, support_threshold, n_hyp);
+    if (COUNT) {
+        const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, n_hyp);
+        if (lane == 0) atomicAdd(evals, (unsigned long long)tot);
+    }
     int result = -1;
     if (d >= 0 && dback >= 0 && abs(d - dback) <= lr_threshold) result = d;  // elas.cpp:404-409
     if (has) dcan_raw[(size_t)f * cw * ch + (size_t)vc * cw + uc] = (int16_t)result;
@@ -377,8 +385,12 @@ int launch_support_match_rows(const Dims &d, const svb_params &p, const uint8_t 
     if (nf <= 0 || d.cw < 2 || vc1 <= vc0) return SVB_OK;
     const int patches = ((d.cw - 1 + PATCH_U - 1) / PATCH_U) * ((vc1 - vc0 + PATCH_V - 1) / PATCH_V);
     dim3 grid((patches + SM_WARPS - 1) / SM_WARPS, nf);
-    k_support_match<<<grid, SM_WARPS * 32, 0, s>>>(desc1, desc2, dcan_raw, d.W, d.H, d.cw, d.ch, d.step, p.disp_min, p.disp_max,
-                                                   p.support_texture, p.support_threshold, p.lr_threshold, vc0, vc1);
+    if (d.evals)
+        k_support_match<true><<<grid, SM_WARPS * 32, 0, s>>>(desc1, desc2, dcan_raw, d.W, d.H, d.cw, d.ch, d.step, p.disp_min, p.disp_max,
+                                                             p.support_texture, p.support_threshold, p.lr_threshold, vc0, vc1, d.evals);
+    else
+        k_support_match<false><<<grid, SM_WARPS * 32, 0, s>>>(desc1, desc2, dcan_raw, d.W, d.H, d.cw, d.ch, d.step, p.disp_min, p.disp_max,
+                                                              p.support_texture, p.support_threshold, p.lr_threshold, vc0, vc1, nullptr);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

@@ -557,6 +557,7 @@ void svb_destroy(svb_context *c) {
         if (c->ev_pc[i]) cudaEventDestroy(c->ev_pc[i]);
     cudaFree(c->out_D1);
     cudaFree(c->out_points);
+    cudaFree(c->d.evals);
     delete c;
 }
 
@@ -586,6 +587,38 @@ int svb_set_single_stream(svb_context *c, int on) {
     SVB_CUDA(cudaDeviceSynchronize());
     c->single_stream = on != 0;
     for (int i = 0; i < c->n_lanes; i++) c->lanes[i].stream = c->single_stream ? c->lanes[0].own_stream : c->lanes[i].own_stream;
+    return SVB_OK;
+}
+
+int svb_set_eval_counting(svb_context *c, int on) {
+    if (!c) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SVB_CUDA(cudaSetDevice(c->device));
+    SVB_CUDA(cudaDeviceSynchronize());
+    if (on && !c->d.evals) {
+        SVB_CUDA(cudaMalloc((void **)&c->d.evals, 2 * sizeof(unsigned long long)));
+        SVB_CUDA(cudaMemset(c->d.evals, 0, 2 * sizeof(unsigned long long)));
+    } else if (!on && c->d.evals) {
+        cudaFree(c->d.evals);
+        c->d.evals = nullptr;
+    }
+    return SVB_OK;
+}
+
+int svb_get_eval_counts(svb_context *c, uint64_t *support_hypotheses, uint64_t *dense_hypotheses) {
+    if (!c) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->d.evals) {
+        set_error("svb_get_eval_counts: counting is off (svb_set_eval_counting)");
+        return SVB_ERR_ARG;
+    }
+    SVB_CUDA(cudaSetDevice(c->device));
+    SVB_CUDA(cudaDeviceSynchronize());
+    unsigned long long h[2] = {0, 0};
+    SVB_CUDA(cudaMemcpy(h, c->d.evals, sizeof(h), cudaMemcpyDeviceToHost));
+    SVB_CUDA(cudaMemset(c->d.evals, 0, sizeof(h)));
+    if (support_hypotheses) *support_hypotheses = h[0];
+    if (dense_hypotheses) *dense_hypotheses = h[1];
     return SVB_OK;
 }
 

@@ -51,6 +51,9 @@ struct Dims {
     int maxT;             // capacity of one triangle list (2*maxS is an upper bound for a planar triangulation)
     int plane_radius;     // elas.cpp:832
     int P[8];             // prior table P[|d - d_plane|] for deltas 0..plane_radius (elas.cpp:831)
+    // optional device counters (svb_set_eval_counting): [0] support-matching hypotheses (64-byte SADs), [1] dense-matching
+    // hypotheses (16-byte SADs), counted the way the reference evaluates them; nullptr = the kernels without counting
+    unsigned long long *evals;
 };
 
 int make_dims(const svb_params &p, int W, int H, Dims *out);

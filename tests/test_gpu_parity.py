@@ -277,12 +277,44 @@ def test_reproject_parity(svb, golden, golden_meta):
             assert np.array_equal(np.isnan(pts), np.isnan(pts_o))
             rel = np.abs(pts[fin] - pts_o[fin]) / np.maximum(np.abs(pts_o[fin]), 1e-300)
             assert rel.max() <= POINT_RTOL
-            assert rel.max() <= 1e-15  # same operation order in f64: equal to the last bit or two
+            assert np.array_equal(pts, pts_o, equal_nan=True)  # same operation order, correctly rounded quotients: bit-identical
+        # general Q (w depends on x and y too) and rows scaled into the exponent ranges where the shared-reciprocal
+        # division falls back to IEEE division (tiny numerators, huge / tiny quotients)
+        Qg = np.array(golden_meta["Q"], np.float64)
+        Qg[3, 0], Qg[3, 1], Qg[3, 3] = 1e-4, -3e-4, 0.37
+        for scale in ((1, 1, 1, 1), (1e-42, 1e-300, 1e200, 1), (1, 1e250, 1, 1e-60), (1e-310, 1, 1, 1e300)):
+            Qs = Qg * np.array(scale, np.float64)[:, None]
+            dm, pts = ctx.reproject(D, Qs, np.array(golden_meta["XR"]), np.array(golden_meta["XT"]))
+            with np.errstate(all="ignore"):
+                dm_o, pts_o = parity.reproject_oracle(D, Qs, golden_meta["XR"], golden_meta["XT"])
+            assert np.array_equal(pts, pts_o, equal_nan=True), scale
         # a map with invalid pixels: d8 = 0 -> w = 0 -> inf / nan exactly like the reference kernel
         D2 = golden["robotics_0_D1"]
         dm, pts = ctx.reproject(D2, np.array(golden_meta["Q"]))
         dm_o, pts_o = parity.reproject_oracle(D2, golden_meta["Q"], np.eye(3), np.zeros(3))
         assert np.array_equal(dm, dm_o)
         assert np.array_equal(np.isfinite(pts), np.isfinite(pts_o))
+        assert np.array_equal(pts, pts_o, equal_nan=True)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("setting,support_m,dense_m", [("ROBOTICS", 4.84, 7.09), ("MIDDLEBURY", 5.89, 11.43)])
+def test_hypothesis_counters_match_instrumented_reference(svb, kitti_gray, setting, support_m, dense_m):
+    """svb_set_eval_counting: the counters behind bench.py's pixel-disparity evals/s.  Known answers = the counts of an
+    instrumented copy of the reference on kitti frame 0 (three significant digits)."""
+    L, R = kitti_gray["L0"], kitti_gray["R0"]
+    ctx = svb.Context(svb.default_params(getattr(svb, setting)), L.shape[1], L.shape[0])
+    try:
+        D_plain = ctx.process(L, R)
+        ctx.set_eval_counting(True)
+        D_counted = ctx.process(L, R)
+        s, d = ctx.eval_counts()
+        assert abs(s / 1e6 - support_m) <= 0.0051, s
+        assert abs(d / 1e6 - dense_m) <= 0.0051, d
+        assert ctx.eval_counts() == (0, 0)  # reading resets
+        for a, b in zip(D_plain, D_counted):  # the counting variants compute the same maps
+            assert np.array_equal(a, b)
+        ctx.set_eval_counting(False)
     finally:
         ctx.close()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Small end-to-end cases for `compute-sanitizer --tool memcheck|racecheck|initcheck python tools/sanitize_case.py`.
-Sizes are tiny on purpose (the sanitizer slows kernels down by 10-100x); every code path of the library runs once:
+"""Small end-to-end cases that touch every code path of the library once (a quick manual check on a GPU box).
+Sizes are tiny on purpose:
 single-frame process (both presets), subsampling, batch pipeline with reprojection, BGRA point cloud, row-band split."""
 import os
 import sys
