@@ -124,6 +124,10 @@ int svb_stage_support(svb_context *ctx, const uint8_t *desc1, const uint8_t *des
 /* Elas::computeDelaunayTriangulation (elas.cpp:442-501) -- the host stage on its own */
 int svb_stage_delaunay(const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out);
 /* Elas::computeDisparityPlanes (elas.cpp:503-575): planes = m x {t1a,t1b,t1c,t2a,t2b,t2c} */
+/* The same stage as the pipeline runs it: vertex order (sort + alternating cuts) on the device, recursion on the host;
+ * *used_device_order = 0 when the device flagged the list (duplicate coordinates, > 4096 points) and the host did it all. */
+int svb_stage_delaunay_pipeline(svb_context *ctx, const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out,
+                                int *used_device_order);
 int svb_stage_planes(svb_context *ctx, const int32_t *support, int n, const int32_t *tri, int m, float *planes);
 /* Elas::createGrid (elas.cpp:577-653): grid = gh*gw*(disp_max+2) int32, reference layout */
 int svb_stage_grid(svb_context *ctx, const int32_t *support, int n, int right_image, int32_t *grid);

@@ -120,6 +120,7 @@ def load():
         "svb_stage_descriptor": [vp, vp, C.c_int, vp],
         "svb_stage_support": [vp, vp, vp, vp, vp, vp, C.c_int, vp],
         "svb_stage_delaunay": [vp, C.c_int, C.c_int, vp, C.c_int, vp],
+        "svb_stage_delaunay_pipeline": [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp],
         "svb_stage_planes": [vp, vp, C.c_int, vp, C.c_int, vp],
         "svb_stage_grid": [vp, vp, C.c_int, C.c_int, vp],
         "svb_stage_disparity": [vp, vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp],
@@ -353,6 +354,17 @@ class Context:
 
     def set_single_stream(self, on=True):
         self._chk(self.lib.svb_set_single_stream(self.h, int(on)))
+
+    def delaunay_pipeline(self, support, right):
+        """The Delaunay stage as the pipeline runs it (vertex order on the device, recursion on the host).
+        Returns (triangles, used_device_order)."""
+        support = np.ascontiguousarray(support, np.int32)
+        n = len(support)
+        cap = 2 * n + 16
+        tri = np.zeros((cap, 3), np.int32)
+        m, used = C.c_int(0), C.c_int(0)
+        self._chk(self.lib.svb_stage_delaunay_pipeline(self.h, _ptr(support), n, int(right), _ptr(tri), cap, C.byref(m), C.byref(used)))
+        return tri[: m.value].copy(), bool(used.value)
 
     def set_eval_counting(self, on=True):
         self._chk(self.lib.svb_set_eval_counting(self.h, int(on)))

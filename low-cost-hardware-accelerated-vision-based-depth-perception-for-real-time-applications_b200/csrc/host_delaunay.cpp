@@ -577,6 +577,47 @@ int delaunay_xy(const int32_t *x, const int32_t *y, int n, int32_t *tri_out, int
     return count;
 }
 
+int delaunay_support_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int32_t *tri_out, int cap,
+                             DelaunayScratch &scratch) {
+    if (n < 3) return 0;
+    // arena (int32 units): [{x,y} sentinel + n][identity sequence n][records 8 R]
+    const size_t max_records = 1 + (size_t)4 * n + 16;
+    const size_t need = 2 * (size_t)(n + 1) + (size_t)n + 8 * max_records + 2;
+    if (scratch.storage.size() < need) scratch.storage.resize(need);
+    int32_t *base = scratch.storage.data();
+    base += ((uintptr_t)base & 7) ? 1 : 0;
+    Pt *P = (Pt *)base + 1;
+    int32_t *seq = (int32_t *)(P + n), *R = seq + n;
+    P[-1] = Pt{0, 0};
+    for (int i = 0; i < n; i++) {
+        const int id = order[i];
+        if ((unsigned)id >= (unsigned)n) return -1;
+        const int32_t *sp = support + 3 * id;
+        P[i] = Pt{right_image ? sp[0] - sp[2] : sp[0], sp[1]};  // elas.cpp:451-461
+        seq[i] = i;
+    }
+    Mesh mesh;
+    mesh.P = P;
+    mesh.R = R;
+    mesh.ntri = 0;
+    mesh.make();  // record 0: outer space
+    int hullleft, hullright;
+    mesh.recurse(seq, n, 0, hullleft, hullright);
+    int count = 0;
+    for (int t = 1; t < mesh.ntri; t++) {
+        const int32_t *r = R + 8 * t + 4;
+        const int a = r[1], b = r[2], c = r[0];
+        if ((a | b | c) < 0) continue;
+        if (count < cap) {
+            tri_out[3 * count] = order[a];
+            tri_out[3 * count + 1] = order[b];
+            tri_out[3 * count + 2] = order[c];
+        }
+        count++;
+    }
+    return count;
+}
+
 int delaunay_support(const int32_t *support, int n, int right_image, int32_t *tri_out, int cap, DelaunayScratch &scratch) {
     if (n < 3) return 0;
     // coordinates are staged at the tail of the arena, past everything delaunay_xy lays out for n points

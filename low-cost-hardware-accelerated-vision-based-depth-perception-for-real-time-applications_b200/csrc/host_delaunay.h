@@ -18,6 +18,12 @@ struct DelaunayScratch {
 // rotation the reference emits.  Returns the number of triangles (which may exceed cap; only cap are stored).
 int delaunay_support(const int32_t *support, int n, int right_image, int32_t *tri_out, int cap, DelaunayScratch &scratch);
 
+// Same, starting from the recursion order computed on the device (k_order.cu): order[i] = index into `support` of the
+// i-th vertex after the lexicographic sort and the alternating-axis partition of a DUPLICATE-FREE point set.
+// Returns -1 if `order` is not usable (the caller then runs delaunay_support).
+int delaunay_support_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int32_t *tri_out, int cap,
+                             DelaunayScratch &scratch);
+
 // Same on explicit integer coordinates.
 int delaunay_xy(const int32_t *x, const int32_t *y, int n, int32_t *tri_out, int cap, DelaunayScratch &scratch);
 

@@ -153,6 +153,9 @@ int lane_create(svb_context *c, Lane &L) {
     SVB_TRY(host_alloc(&L.h_support, C * d.maxS * 3));
     SVB_TRY(host_alloc(&L.h_nsupport, C));
     SVB_TRY(host_alloc(&L.h_ntri, C * 3));
+    SVB_TRY(host_alloc(&L.h_order, C * 2 * d.maxS));
+    SVB_TRY(host_alloc(&L.h_order_ok, C * 2));
+    memset(L.h_order_ok, 0, sizeof(int32_t) * C * 2);
     return SVB_OK;
 }
 
@@ -181,6 +184,8 @@ void lane_destroy(Lane &L) {
     cudaFreeHost(L.h_support);
     cudaFreeHost(L.h_nsupport);
     cudaFreeHost(L.h_ntri);
+    cudaFreeHost(L.h_order);
+    cudaFreeHost(L.h_order_ok);
     if (L.ev_a) cudaEventDestroy(L.ev_a);
     if (L.ev_done) cudaEventDestroy(L.ev_done);
     if (L.own_stream) cudaStreamDestroy(L.own_stream);
@@ -262,6 +267,8 @@ int stage_a(svb_context *c, Lane &L, const uint8_t *img1, const uint8_t *img2, i
     SVB_TRY(T.mark(ST_SUPPORT_FILTER));
     // the kernel writes the lists into the mapped pinned buffers itself: no device-to-host copy is queued
     SVB_TRY(launch_support_filter(d, c->p, L.dcan_raw, L.dcan, L.support, L.nsupport, L.h_support, L.h_nsupport, nf, L.stream));
+    // ... and the order in which the host's divide-and-conquer will meet the vertices (sort + alternating cuts)
+    if (c->gpu_order) SVB_TRY(launch_delaunay_order(d, L.support, L.nsupport, L.h_order, L.h_order_ok, nf, L.stream));
     SVB_TRY(T.mark(ST_D2H_SUPPORT));
     if (se) {
         SVB_CUDA(cudaEventRecord(se->a_end, L.stream));
@@ -310,7 +317,11 @@ int svb::stage_host(svb_context *c, Lane &L, int nf) {
             if (m > cap) m = cap;
             memcpy(out, c->inject_tri[side].data(), sizeof(int32_t) * 3 * m);
         } else if (n >= 3) {
-            m = delaunay_support(L.h_support + (size_t)f * d.maxS * 3, n, side, out, cap, c->scratch[worker]);
+            const int32_t *sup = L.h_support + (size_t)f * d.maxS * 3;
+            m = -1;
+            if (c->gpu_order && L.h_order_ok[2 * f + side] == 1)
+                m = delaunay_support_ordered(sup, n, side, L.h_order + ((size_t)f * 2 + side) * d.maxS, out, cap, c->scratch[worker]);
+            if (m < 0) m = delaunay_support(sup, n, side, out, cap, c->scratch[worker]);
             if (m > cap) m = cap;
         }
         L.h_ntri[2 * f + side] = m;
@@ -515,6 +526,8 @@ svb_context *svb_create(const svb_params *params, int width, int height, int chu
         return nullptr;
     }
     {
+        const char *g = getenv("SVB_GPU_ORDER");
+        if (g && atoi(g) == 0) c->gpu_order = false;
         const char *e = getenv("SVB_LANES");
         const int n = e ? atoi(e) : 3;
         c->n_lanes = n < 1 ? 1 : (n > MAX_LANES ? MAX_LANES : n);
@@ -781,6 +794,32 @@ int svb_stage_delaunay(const int32_t *support, int n, int right_image, int32_t *
     DelaunayScratch scratch;
     const int m = delaunay_support(support, n, right_image, tri, cap, scratch);
     if (n_tri_out) *n_tri_out = m;
+    return SVB_OK;
+}
+
+// Host Delaunay stage exactly as the pipeline runs it: the device orders the vertices (k_order.cu), the host recurses;
+// *used_device_order tells whether the device's order was usable (0: duplicates, > 4096 points, ... -> complete host path).
+int svb_stage_delaunay_pipeline(svb_context *c, const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out,
+                                int *used_device_order) {
+    STAGE_PROLOG();
+    if (!support || !tri || n < 0 || cap < 0 || n > d.maxS) return SVB_ERR_ARG;
+    L.h_nsupport[0] = n;
+    memcpy(L.h_support, support, (size_t)n * 12);
+    SVB_CUDA(cudaMemcpyAsync(L.nsupport, L.h_nsupport, 4, cudaMemcpyHostToDevice, L.stream));
+    if (n) SVB_CUDA(cudaMemcpyAsync(L.support, L.h_support, (size_t)n * 12, cudaMemcpyHostToDevice, L.stream));
+    L.h_order_ok[0] = L.h_order_ok[1] = 0;
+    SVB_TRY(launch_delaunay_order(d, L.support, L.nsupport, L.h_order, L.h_order_ok, 1, L.stream));
+    SVB_CUDA(cudaStreamSynchronize(L.stream));
+    const int side = right_image ? 1 : 0;
+    int m = -1, used = 0;
+    if (L.h_order_ok[side] == 1) {
+        m = delaunay_support_ordered(L.h_support, n, side, L.h_order + (size_t)side * d.maxS, tri, cap, c->scratch[0]);
+        used = m >= 0;
+    }
+    if (m < 0) m = delaunay_support(L.h_support, n, side, tri, cap, c->scratch[0]);
+    L.h_order_ok[0] = L.h_order_ok[1] = 0;
+    if (n_tri_out) *n_tri_out = m;
+    if (used_device_order) *used_device_order = used;
     return SVB_OK;
 }
 

@@ -37,6 +37,8 @@ struct Lane {
     uint8_t *dmap = nullptr;
     // pinned host
     int32_t *h_support = nullptr, *h_nsupport = nullptr, *h_tri[2] = {nullptr, nullptr}, *h_ntri = nullptr;
+    int32_t *h_order = nullptr;     // [chunk][2][maxS] recursion order of the Delaunay stage (k_order.cu), written by the device
+    int32_t *h_order_ok = nullptr;  // [chunk][2] 1 = h_order is valid for that list
 };
 
 // CUDA events bracketing every stage of one chunk (stage timing): [i] is recorded in front of stage i, [ST_COUNT] after
@@ -87,6 +89,7 @@ struct svb_context {
     svb_stats stats;
     bool stage_timing = false;
     bool single_stream = false;
+    bool gpu_order = true;  // SVB_GPU_ORDER=0: the host stage sorts and partitions the vertices itself
     std::vector<svb::StageEvents> stage_ev;  // one set per chunk of the call in flight
     std::mutex mu;
 };

@@ -88,6 +88,8 @@ enum StageId {
 int launch_descriptor(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, cudaStream_t s);
 // *_rows variants restrict a stage to image rows [row0, row1) / lattice rows [vc0, vc1): the row-band split (band_split.cu)
 int launch_descriptor_rows(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, int row0, int row1, cudaStream_t s);  // d.sub: even rows only
+// k_order.cu: recursion order of the host Delaunay stage for every (frame, side); h_order [nf][2][maxS], h_ok [nf][2] (mapped host memory)
+int launch_delaunay_order(const Dims &d, const int32_t *support, const int32_t *nsupport, int32_t *h_order, int32_t *h_ok, int nf, cudaStream_t s);
 // k_support.cu
 int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int nf,
                          cudaStream_t s);

@@ -318,3 +318,33 @@ def test_hypothesis_counters_match_instrumented_reference(svb, kitti_gray, setti
         ctx.set_eval_counting(False)
     finally:
         ctx.close()
+
+
+def test_device_vertex_order_feeds_the_same_triangulation(svb, ref):
+    """k_order.cu + delaunay_support_ordered against the reference's triangulator on random lattices, both sides; lists the
+    device must hand back to the host (duplicate coordinates, more than 4096 points) still give the reference's output."""
+    import test_cabi_host as H
+
+    ctx = svb.Context(svb.default_params(svb.MIDDLEBURY), 1242, 375)
+    try:
+        for seed, n, expect_device in [(1, 3, True), (2, 4, True), (3, 7, True), (4, 50, True), (5, 400, True), (6, 2500, True),
+                                       (8, 4096, True), (7, 6000, False)]:
+            s = H.lattice_support(np.random.default_rng(seed), n)
+            for side in (0, 1):
+                want = ref.delaunay(s, side)
+                got, used = ctx.delaunay_pipeline(s, side)
+                assert np.array_equal(got, want), "seed %d n %d side %d" % (seed, n, side)
+                if side == 0 or not expect_device:
+                    assert used == (expect_device and len(s) <= 4096), (seed, n, side, used)
+        # duplicates in the right image: flagged by the device, resolved by the host like the reference does
+        dup = np.array([(100, 50, 10), (95, 50, 5), (200, 80, 20), (60, 120, 1), (300, 20, 9), (110, 50, 20)], np.int32)
+        got, used = ctx.delaunay_pipeline(dup, 1)
+        assert not used and np.array_equal(got, ref.delaunay(dup, 1))
+        got, used = ctx.delaunay_pipeline(dup, 0)
+        assert used and np.array_equal(got, ref.delaunay(dup, 0))
+        # collinear input: no triangles either way
+        col = np.array([(50, 5 * i, 3) for i in range(1, 30)], np.int32)
+        got, used = ctx.delaunay_pipeline(col, 0)
+        assert used and len(got) == 0
+    finally:
+        ctx.close()
