@@ -174,6 +174,10 @@ int svb_point_cloud_bgra(svb_context *ctx, const uint8_t *left_bgra, const uint8
 /* cv::resize(src, dst, dsize) with the default INTER_LINEAR on 8-bit BGRA (stereo_vision.cu:599-600,665,676: frames are
  * resized to out_img_size = input size / scale_factor).  Host buffers; OpenCV's fixed-point arithmetic restated exactly. */
 int svb_resize_bgra(const uint8_t *src, int src_width, int src_height, uint8_t *dst, int dst_width, int dst_height);
+/* the same cv::resize arithmetic for a single-channel u8 image, and publishPointCloud (stereo_vision.cu:245-265) on a u8
+ * disparity map of any size: what the driver's extrapolate_point_cloud (-e) option needs (resize the map, then project). */
+int svb_resize_gray(const uint8_t *src, int src_width, int src_height, uint8_t *dst, int dst_width, int dst_height);
+int svb_reproject_u8(const uint8_t *dmap, int width, int height, const double *Q16, const double *XR9, const double *XT3, double *points_out);
 /* cv::cvtColor(BGRA2GRAY) on its own (stereo_vision.cu:346-347) */
 int svb_stage_bgra_to_gray(svb_context *ctx, const uint8_t *bgra, uint8_t *gray_out);
 

@@ -144,6 +144,8 @@ def load():
         "svb_band_process": [vp, vp, vp, C.c_int, vp, vp],
         "svb_band_get_stats": [vp, C.POINTER(BandStats)],
         "svb_resize_bgra": [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int],
+        "svb_resize_gray": [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int],
+        "svb_reproject_u8": [vp, C.c_int, C.c_int, vp, vp, vp, vp],
         "svb_image_read": [C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "svb_calib_load_yaml": [C.c_char_p, C.POINTER(Calibration)],
         "svb_stereo_rectify": [C.POINTER(Calibration), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp],
@@ -217,6 +219,33 @@ def resize_bgra(img, dsize):
     if rc != 0:
         raise SvbError(rc, lib.svb_last_error().decode())
     return out
+
+
+def resize_gray(img, dsize):
+    """cv::resize(img, dsize) with INTER_LINEAR on a single-channel 8-bit image (publishPointCloud's map, stereo_vision.cu:249)."""
+    lib = load()
+    img = np.ascontiguousarray(img, np.uint8)
+    assert img.ndim == 2
+    out = np.zeros((dsize[1], dsize[0]), np.uint8)
+    rc = lib.svb_resize_gray(_ptr(img), img.shape[1], img.shape[0], _ptr(out), dsize[0], dsize[1])
+    if rc != 0:
+        raise SvbError(rc, lib.svb_last_error().decode())
+    return out
+
+
+def reproject_u8(dmap, Q, XR=None, XT=None):
+    """projectParallel on a u8 disparity map of any size (stereo_vision.cu:188-212,245-265)."""
+    lib = load()
+    dmap = np.ascontiguousarray(dmap, np.uint8)
+    H, W = dmap.shape
+    Q = np.ascontiguousarray(Q, np.float64).reshape(16)
+    XR = None if XR is None else np.ascontiguousarray(XR, np.float64).reshape(9)
+    XT = None if XT is None else np.ascontiguousarray(XT, np.float64).reshape(3)
+    pts = np.zeros((H * W, 3), np.float64)
+    rc = lib.svb_reproject_u8(_ptr(dmap), W, H, _ptr(Q), None if XR is None else _ptr(XR), None if XT is None else _ptr(XT), _ptr(pts))
+    if rc != 0:
+        raise SvbError(rc, lib.svb_last_error().decode())
+    return pts
 
 
 def load_calibration(path):

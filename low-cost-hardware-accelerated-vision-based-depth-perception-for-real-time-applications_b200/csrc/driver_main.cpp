@@ -251,8 +251,12 @@ int main(int argc, const char **argv) {
     printf("** Object tracking disabled\n");
     printf("KITTI Path: %s \n", o.kitti_path.c_str());
     if (o.draw_points) fprintf(stderr, "the OpenGL viewer is outside this program's scope (-p 1 ignored)\n");
-    if (o.extrapolate != 1 || !(o.scale_factor > 0.f)) {
-        fprintf(stderr, "extrapolate_point_cloud != 1 is not built (DESIGN.md 1); scale_factor must be positive\n");
+    if (o.extrapolate < 1 || !(o.scale_factor > 0.f)) {
+        fprintf(stderr, "extrapolate_point_cloud must be >= 1 and scale_factor positive\n");
+        return 1;
+    }
+    if (o.batch > 0 && o.extrapolate != 1) {
+        fprintf(stderr, "-B (batch extension) runs with extrapolate_point_cloud 1 only\n");
         return 1;
     }
     if (o.batch > 0 && o.scale_factor != 1.f) {
@@ -286,8 +290,16 @@ int main(int argc, const char **argv) {
     }
     svb_set_calibration(ctx, Q, cal.XR, cal.XT);
     printf("CUDA Init done\n");
-    double *points = (double *)svb_host_alloc(N * 24);
-    std::vector<uint8_t> left, right, left_in, right_in, dmap(N);
+    // extrapolate_point_cloud (stereo_vision.cu:523-524,245-265): the u8 map and the left image are resized by the factor and
+    // the larger map is projected with the SAME Q
+    const int PW = W * o.extrapolate, PH = H * o.extrapolate;
+    const size_t PN = (size_t)PW * PH;
+    double *points = (double *)svb_host_alloc(PN * 24);
+    std::vector<uint8_t> left, right, left_in, right_in, dmap(N), dmap_big, color_big;
+    if (o.extrapolate != 1) {
+        dmap_big.resize(PN);
+        color_big.resize(PN * 4);
+    }
     const bool resize = W != inW || H != inH;
     double FPS = 0;
     for (unsigned i = 0; i < max_files; i++) {
@@ -310,6 +322,14 @@ int main(int argc, const char **argv) {
             printf("ERROR: Need at least 3 support points!\n");
         else if (rc != SVB_OK)
             fprintf(stderr, "%s\n", svb_last_error());
+        if (o.extrapolate != 1 && rc == SVB_OK) {
+            const auto p0 = std::chrono::steady_clock::now();
+            if (svb_resize_bgra(left.data(), W, H, color_big.data(), PW, PH) != SVB_OK ||
+                svb_resize_gray(dmap.data(), W, H, dmap_big.data(), PW, PH) != SVB_OK ||
+                svb_reproject_u8(dmap_big.data(), PW, PH, Q, cal.XR, cal.XT, points) != SVB_OK)
+                fprintf(stderr, "%s\n", svb_last_error());
+            times[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - p0).count();
+        }
         const double t_t = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         printf("(FPS=%f) (%d, %d) (t_t=%f, dmap_t=%f, pc_t=%f)\n", 1 / t_t, H, W, t_t, times[0] * 1e-3, times[1] * 1e-3);
         FPS += 1 / t_t;
@@ -318,6 +338,15 @@ int main(int argc, const char **argv) {
             snprintf(name, sizeof(name), "/%010u_disp.pgm", i);
             std::string err;
             if (!svb::write_pgm(o.dump_dir + name, dmap.data(), W, H, &err)) fprintf(stderr, "%s\n", err.c_str());
+            if (o.extrapolate != 1) {  // the resized map and the cloud projected from it (raw float64 x, y, z)
+                snprintf(name, sizeof(name), "/%010u_disp_e.pgm", i);
+                if (!svb::write_pgm(o.dump_dir + name, dmap_big.data(), PW, PH, &err)) fprintf(stderr, "%s\n", err.c_str());
+                snprintf(name, sizeof(name), "/%010u_points_e.f64", i);
+                if (FILE *fp = fopen((o.dump_dir + name).c_str(), "wb")) {
+                    fwrite(points, 24, PN, fp);
+                    fclose(fp);
+                }
+            }
         }
     }
     printf("AVG_FPS=%f\n", max_files ? FPS / max_files : 0.0);

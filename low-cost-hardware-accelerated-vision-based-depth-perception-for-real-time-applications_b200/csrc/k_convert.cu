@@ -83,6 +83,22 @@ __global__ void __launch_bounds__(256) k_resize_linear_bgra(const uint8_t *__res
     reinterpret_cast<uint32_t *>(dst)[(size_t)dy * dw + dx] = out;
 }
 
+// The same arithmetic for a single-channel image (the u8 disparity map of publishPointCloud, stereo_vision.cu:249).
+__global__ void __launch_bounds__(256) k_resize_linear_gray(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const ResizeTab *__restrict__ xt,
+                                                            const ResizeTab *__restrict__ yt, int sw, int sh, int dw, int dh) {
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int dy = blockIdx.y;
+    if (dx >= dw) return;
+    const ResizeTab tx = xt[dx], ty = yt[dy];
+    const int x0 = tx.idx, x1 = min(tx.idx + 1, sw - 1);
+    const int y0 = min(max(ty.idx, 0), sh - 1), y1 = min(max(ty.idx + 1, 0), sh - 1);
+    const uint8_t *r0 = src + (size_t)y0 * sw, *r1 = src + (size_t)y1 * sw;
+    const int S0 = (int)r0[x0] * tx.w0 + (int)r0[x1] * tx.w1;
+    const int S1 = (int)r1[x0] * tx.w0 + (int)r1[x1] * tx.w1;
+    const int v = (((ty.w0 * (S0 >> 4)) >> 16) + ((ty.w1 * (S1 >> 4)) >> 16) + 2) >> 2;
+    dst[(size_t)dy * dw + dx] = (uint8_t)min(max(v, 0), 255);
+}
+
 void make_table(std::vector<ResizeTab> &t, int dn, int sn, bool clamp_weight) {
     const double scale = 1.0 / ((double)dn / sn);
     t.resize(dn);
@@ -109,7 +125,7 @@ void make_table(std::vector<ResizeTab> &t, int dn, int sn, bool clamp_weight) {
 }  // namespace
 }  // namespace svb
 
-extern "C" int svb_resize_bgra(const uint8_t *src, int src_width, int src_height, uint8_t *dst, int dst_width, int dst_height) {
+static int resize_u8(const char *who, int channels, const uint8_t *src, int src_width, int src_height, uint8_t *dst, int dst_width, int dst_height) {
     using namespace svb;
     if (!src || !dst || src_width < 1 || src_height < 1 || dst_width < 1 || dst_height < 1) return SVB_ERR_ARG;
     std::vector<ResizeTab> xt, yt;
@@ -117,7 +133,7 @@ extern "C" int svb_resize_bgra(const uint8_t *src, int src_width, int src_height
     make_table(yt, dst_height, src_height, false);
     uint8_t *d_src = nullptr, *d_dst = nullptr;
     ResizeTab *d_xt = nullptr, *d_yt = nullptr;
-    const size_t sb = (size_t)src_width * src_height * 4, db = (size_t)dst_width * dst_height * 4;
+    const size_t sb = (size_t)src_width * src_height * channels, db = (size_t)dst_width * dst_height * channels;
     int rc = SVB_OK;
     cudaError_t e = cudaMalloc(&d_src, sb);
     if (e == cudaSuccess) e = cudaMalloc(&d_dst, db);
@@ -128,13 +144,16 @@ extern "C" int svb_resize_bgra(const uint8_t *src, int src_width, int src_height
     if (e == cudaSuccess) e = cudaMemcpy(d_yt, yt.data(), yt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         dim3 grid((dst_width + 255) / 256, dst_height);
-        k_resize_linear_bgra<<<grid, 256>>>(d_src, d_dst, d_xt, d_yt, src_width, src_height, dst_width, dst_height);
+        if (channels == 4)
+            k_resize_linear_bgra<<<grid, 256>>>(d_src, d_dst, d_xt, d_yt, src_width, src_height, dst_width, dst_height);
+        else
+            k_resize_linear_gray<<<grid, 256>>>(d_src, d_dst, d_xt, d_yt, src_width, src_height, dst_width, dst_height);
         g_launch_counter++;
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(dst, d_dst, db, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) {
-        set_error("svb_resize_bgra: %s", cudaGetErrorString(e));
+        set_error("%s: %s", who, cudaGetErrorString(e));
         rc = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SVB_ERR_NO_DEVICE : SVB_ERR_CUDA;
     }
     cudaFree(d_src);
@@ -142,4 +161,12 @@ extern "C" int svb_resize_bgra(const uint8_t *src, int src_width, int src_height
     cudaFree(d_xt);
     cudaFree(d_yt);
     return rc;
+}
+
+extern "C" int svb_resize_bgra(const uint8_t *src, int src_width, int src_height, uint8_t *dst, int dst_width, int dst_height) {
+    return resize_u8("svb_resize_bgra", 4, src, src_width, src_height, dst, dst_width, dst_height);
+}
+
+extern "C" int svb_resize_gray(const uint8_t *src, int src_width, int src_height, uint8_t *dst, int dst_width, int dst_height) {
+    return resize_u8("svb_resize_gray", 1, src, src_width, src_height, dst, dst_width, dst_height);
 }

@@ -947,6 +947,34 @@ int svb_stage_reproject(svb_context *c, const float *D, const double *Q16, const
     return r;
 }
 
+// publishPointCloud on a u8 map of any size (no context: the map need not have the size a context was created for)
+int svb_reproject_u8(const uint8_t *dmap, int width, int height, const double *Q16, const double *XR9, const double *XT3, double *points_out) {
+    if (!dmap || !Q16 || !points_out || width < 1 || height < 1) return SVB_ERR_ARG;
+    Calib cal;
+    memcpy(cal.Q, Q16, sizeof(cal.Q));
+    memset(cal.XR, 0, sizeof(cal.XR));
+    memset(cal.XT, 0, sizeof(cal.XT));
+    for (int i = 0; i < 3; i++) cal.XR[4 * i] = 1.0;
+    if (XR9) memcpy(cal.XR, XR9, sizeof(cal.XR));
+    if (XT3) memcpy(cal.XT, XT3, sizeof(cal.XT));
+    const size_t N = (size_t)width * height;
+    uint8_t *d_map = nullptr;
+    double *d_pts = nullptr;
+    SVB_CUDA(cudaMalloc((void **)&d_map, N));
+    cudaError_t e = cudaMalloc((void **)&d_pts, N * 24);
+    if (e == cudaSuccess) e = cudaMemcpy(d_map, dmap, N, cudaMemcpyHostToDevice);
+    int r = SVB_OK;
+    if (e == cudaSuccess) r = launch_reproject_u8(cal, d_map, d_pts, width, height, nullptr);
+    if (e == cudaSuccess && r == SVB_OK) e = cudaMemcpy(points_out, d_pts, N * 24, cudaMemcpyDeviceToHost);
+    cudaFree(d_map);
+    cudaFree(d_pts);
+    if (e != cudaSuccess) {
+        set_error("svb_reproject_u8: %s", cudaGetErrorString(e));
+        return SVB_ERR_CUDA;
+    }
+    return r;
+}
+
 // ---- batch pipeline -----------------------------------------------------------------------------------------
 static int ensure_store(void **p, size_t *have_frames, size_t want_frames, size_t bytes_per_frame) {
     if (*p && *have_frames >= want_frames) return SVB_OK;

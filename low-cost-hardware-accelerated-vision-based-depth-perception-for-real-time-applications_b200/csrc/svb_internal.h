@@ -134,6 +134,7 @@ struct Calib {
     double XT[3];
 };
 int launch_reproject(const Dims &d, const Calib &c, const float *D, uint8_t *dmap, double *points, int nf, cudaStream_t s);
+int launch_reproject_u8(const Calib &c, const uint8_t *dmap, double *points, int W, int H, cudaStream_t s);
 // k_convert.cu
 int launch_bgra_to_gray(const uint8_t *bgra, uint8_t *gray, int n, cudaStream_t s);
 

@@ -89,9 +89,37 @@ def test_scale_factor(tmp_path, kitti_gray, ref):
     assert np.array_equal(got, want)
 
 
+def test_extrapolate_point_cloud(tmp_path, kitti_gray, golden_meta):
+    """-e 2 (publishPointCloud, stereo_vision.cu:245-265): the u8 map is resized like cv::resize does and the larger map is
+    projected with the same Q."""
+    import parity
+
+    with open(os.path.join(GOLDEN, "calib_golden.json")) as f:
+        case = [c for c in json.load(f)["cases"] if c["name"] == "data/calibration/kitti_2011_09_26.yml" and c["size"] == [1242, 375]
+                and c["alpha"] == 0.0][0]
+    seq = tmp_path / "seq"
+    make_sequence(str(seq), kitti_gray)
+    write_yaml(tmp_path / "k.yml", case)
+    dump = tmp_path / "dump"
+    os.makedirs(dump)
+    r = subprocess.run([EXE, "-k", str(seq), "-p=0", "-e", "2", "-c", str(tmp_path / "k.yml"), "-o", str(dump)], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    small = cv2.imread(str(dump / "0000000000_disp.pgm"), cv2.IMREAD_GRAYSCALE)
+    big = cv2.imread(str(dump / "0000000000_disp_e.pgm"), cv2.IMREAD_GRAYSCALE)
+    assert big.shape == (750, 2484) and np.array_equal(big, cv2.resize(small, (2484, 750)))
+    pts = np.fromfile(str(dump / "0000000000_points_e.f64"), np.float64).reshape(-1, 3)
+    with np.errstate(all="ignore"):
+        _, want = parity.reproject_oracle(big.astype(np.float32) / np.float32(4.0), np.array(case["Q"]).reshape(4, 4), case["XR"], case["XT"])
+    fin = np.isfinite(want).all(1)
+    assert np.array_equal(np.isfinite(pts).all(1), fin) and fin.any()
+    # the driver's own stereoRectify agrees with cv2's Q to 1e-13 (tests/test_calibration.py), hence not bit for bit here
+    assert np.allclose(pts[fin], want[fin], rtol=1e-9, atol=1e-9)
+
+
 def test_unsupported_options_fail_loudly(tmp_path):
-    r = subprocess.run([EXE, "-k", str(tmp_path), "-p", "0", "-e", "2"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
-    assert r.returncode != 0 and "not built" in r.stderr
+    r = subprocess.run([EXE, "-k", str(tmp_path), "-p", "0", "-e", "0"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "extrapolate_point_cloud" in r.stderr
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "Usage" in r.stderr
 

@@ -152,6 +152,7 @@ def test_resize_matches_cv2(svb):
         for scale in (0.5, 0.75, 1.0, 1.5, 2.0, 2.5, 3.0):
             dsize = (int(sw / scale), int(sh / scale))
             assert np.array_equal(svb.resize_bgra(img, dsize), cv2.resize(img, dsize)), (sw, sh, scale)
+            assert np.array_equal(svb.resize_gray(img[..., 1], dsize), cv2.resize(img[..., 1], dsize)), (sw, sh, scale)
 
 
 def test_bgra_to_gray_matches_cv2(svb):
@@ -220,3 +221,17 @@ def test_cpp_elas_gpu_class(tmp_path, golden, kitti_gray):
     D1 = np.frombuffer(outp.read_bytes(), np.float32).reshape(H, W)
     assert np.array_equal(D1, golden["pipeline_0_D1"])
     assert r.stdout.split()[:3] == ["3", "0", "0.85"]
+
+
+def test_reproject_u8_any_size(svb, golden_meta):
+    """svb_reproject_u8 (no context, any map size) against the numpy restatement of projectParallel, bit for bit."""
+    import parity
+
+    rng = np.random.default_rng(3)
+    for W, H in ((2484, 750), (333, 127), (17, 5)):
+        dm = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        dm[rng.random((H, W)) < 0.2] = 0
+        pts = svb.reproject_u8(dm, np.array(golden_meta["Q"]), golden_meta["XR"], golden_meta["XT"])
+        with np.errstate(all="ignore"):
+            _, want = parity.reproject_oracle(dm.astype(np.float32) / np.float32(4.0), golden_meta["Q"], golden_meta["XR"], golden_meta["XT"])
+        assert np.array_equal(pts, want, equal_nan=True), (W, H)
