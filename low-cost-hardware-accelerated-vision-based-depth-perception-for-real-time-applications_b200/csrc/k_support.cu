@@ -95,9 +95,11 @@ __device__ __forceinline__ int match_pass(const uint4 *__restrict__ own, const u
         e = sad16_acc(a1, tn, e);                                                          \
         e = sad16_acc(a2, BK, e);                                                          \
         e = sad16_acc(a3, bn, e);                                                          \
-        const unsigned key = (drel <= span) ? e * 65536u + drel : 0xFFFFFFFFu;             \
-        second = min(second, max(best, key));                                              \
-        best = min(best, key);                                                             \
+        const unsigned key = e * 65536u + drel;                                            \
+        if (drel <= span) { /* three predicated min/max instead of a select + three */    \
+            second = min(second, max(best, key));                                          \
+            best = min(best, key);                                                         \
+        }                                                                                  \
         drel += dstep;                                                                     \
         TK = tn;                                                                           \
         BK = bn;                                                                           \
@@ -181,6 +183,8 @@ __global__ void k_dcan_border(int16_t *__restrict__ dcan_raw, int cw, int ch) {
 // ------------------------------------------------------------------------------------------------
 constexpr int SF_THREADS = 1024;
 constexpr int SF_REMOVED = 0x4000;  // flag bit of a lattice cell (disparities are < 4096)
+constexpr int SF_MARK_A = 0x2000, SF_MARK_B = 0x1000;  // "re-examine in this / the next sweep" (alternating roles)
+constexpr int SF_VALUE = 0x0FFF;
 
 __device__ __forceinline__ bool precedes_colmajor(int u2, int v2, int u, int v) { return u2 < u || (u2 == u && v2 < v); }
 
@@ -240,12 +244,23 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(const int16_t *__
     __syncthreads();
 
     // ---- inconsistent points: parallel sweeps to the fixpoint; a removed cell keeps its value and gets SF_REMOVED ----
+    // Only the first sweep looks at every cell.  A cell's count can change only when a cell of its window is removed, so
+    // a removal marks its window for the NEXT sweep (two alternating mark bits in the cell itself; shared-memory lattice
+    // only, where the marks are 32-bit atomics on the word that holds the 16-bit cell).
+    unsigned *words = reinterpret_cast<unsigned *>(work);
+    int cur_bit = SF_MARK_A, next_bit = SF_MARK_B;
+    bool first = true;
     while (true) {
         if (tid == 0) s_changed = 0;
         __syncthreads();
         for (int i = tid; i < cells; i += SF_THREADS) {
             const int e = work[i];
             if (e < 0 || (e & SF_REMOVED)) continue;
+            if (SMEM && !first) {
+                if (!(e & cur_bit)) continue;
+                atomicAnd(words + (i >> 1), ~((unsigned)cur_bit << (16 * (i & 1))));
+            }
+            const int dc = e & SF_VALUE;
             const int v = i / cw, u = i - v * cw;
             const int u_lo = max(u - incon_window, 0), u_hi = min(u + incon_window, cw - 1);
             const int v_lo = max(v - incon_window, 0), v_hi = min(v + incon_window, ch - 1);
@@ -254,23 +269,36 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(const int16_t *__
                 for (int u2 = u_lo; u2 <= u_hi; u2++) {
                     const int e2 = work[v2 * cw + u2];
                     if (e2 < 0) continue;
-                    if (abs(e - (e2 & (SF_REMOVED - 1))) > incon_threshold) continue;
+                    if (abs(dc - (e2 & SF_VALUE)) > incon_threshold) continue;
                     if ((e2 & SF_REMOVED) && precedes_colmajor(u2, v2, u, v)) continue;
                     support_cnt++;
                 }
             if (support_cnt < incon_min_support) {
-                work[i] = (int16_t)(e | SF_REMOVED);
                 s_changed = 1;
+                if (SMEM) {
+                    atomicOr(words + (i >> 1), (unsigned)SF_REMOVED << (16 * (i & 1)));
+                    for (int v2 = v_lo; v2 <= v_hi; v2++)
+                        for (int u2 = u_lo; u2 <= u_hi; u2++) {
+                            const int j = v2 * cw + u2;
+                            if (work[j] >= 0) atomicOr(words + (j >> 1), (unsigned)next_bit << (16 * (j & 1)));
+                        }
+                } else {
+                    work[i] = (int16_t)(e | SF_REMOVED);
+                }
             }
         }
         __syncthreads();
         const int again = s_changed;
         __syncthreads();
         if (!again) break;
+        first = false;
+        const int t = cur_bit;
+        cur_bit = next_bit;
+        next_bit = t;
     }
     for (int i = tid; i < cells; i += SF_THREADS) {
         const int e = work[i];
-        if (e >= 0 && (e & SF_REMOVED)) work[i] = (int16_t)-1;
+        if (e >= 0) work[i] = (e & SF_REMOVED) ? (int16_t)-1 : (int16_t)(e & SF_VALUE);
     }
     __syncthreads();
 
@@ -404,11 +432,11 @@ int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc
 int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dcan_raw, int16_t *dcan, int32_t *support, int32_t *nsupport,
                           int32_t *h_support, int32_t *h_nsupport, int nf, cudaStream_t s) {
     if (nf <= 0) return SVB_OK;
-    if (p.disp_max >= SF_REMOVED) {
+    if (p.disp_max > SF_VALUE) {
         set_error("support filter: disp_max %d too large for the lattice cell encoding", p.disp_max);
         return SVB_ERR_UNSUPPORTED;
     }
-    const size_t smem = (size_t)d.cw * d.ch * sizeof(int16_t);
+    const size_t smem = ((size_t)d.cw * d.ch * sizeof(int16_t) + 3) & ~(size_t)3;  // whole 32-bit words: the sweep marks cells with word atomics
     if (smem <= 200 * 1024) {
         if (smem > 48 * 1024) {  // opt in to large dynamic shared memory (per device, so not cached in a static)
             cudaError_t e = cudaFuncSetAttribute(k_support_filter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
