@@ -160,6 +160,34 @@ def cpu_frames_per_s(n_frames_per_core, cores, first_frame=0, fast=True):
     return cores * n_frames_per_core / wall, wall
 
 
+def cpu_single_process(n_frames, omp):
+    """The reference's serial (one core) or OpenMP variant in THIS process: frames/s over n_frames synthetic frames."""
+    import ctypes as C
+
+    from oracle.ref import RefElas
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity
+
+    lib = C.CDLL([p for p in __import__("glob").glob(os.path.join(ROOT, "low-cost*", "lib", "libelas_b200.so"))][0])
+    try:
+        ref = RefElas(fast=True, omp=omp)
+    except (FileNotFoundError, OSError):
+        return None
+    p = ref.pipeline_params()
+    L = np.zeros((H, W), np.uint8)
+    R = np.zeros((H, W), np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    t_total = 0.0
+    for f in range(-1, n_frames):  # frame -1: warm-up, not timed
+        lib.svb_synth_pair(max(f, 0), W, H, max(f, 0) & 1, vp(L), vp(R))
+        t0 = time.perf_counter()
+        D1, _, _ = ref.process(p, L, R)
+        parity.reproject_oracle(D1, Q_KITTI, np.eye(3), np.zeros(3))
+        if f >= 0:
+            t_total += time.perf_counter() - t0
+    return n_frames / t_total
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -425,7 +453,11 @@ def main():
         fps, wall = cpu_frames_per_s(per_core, cores, first_frame=0, fast=True)
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference",
                "sample": "%d frames of the same synthetic workload (%d per core), reference serial ELAS (oracle/_ref, -O2 -ffast-math = "
-                         "reference Makefile flags) + numpy projectParallel, one process per core, %.1f s wall" % (per_core * cores, per_core, wall)}
+                         "reference Makefile flags) + numpy projectParallel, one process per core, %.1f s wall" % (per_core * cores, per_core, wall),
+               # the two single-process forms the reference's own binaries take (make serial=1 / make omp=1), 8 frames each
+               "serial_one_core_fps": cpu_single_process(8, omp=False),
+               "openmp_one_process_fps": cpu_single_process(8, omp=True),
+               "openmp_note": "src/omp_includes/elas with -fopenmp; its num_threads(2)/(3) clauses cap it at about 3 cores"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

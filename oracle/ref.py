@@ -57,8 +57,9 @@ def _p(a, t):
 
 
 class RefElas:
-    def __init__(self, fast=False):
-        name = "libelas_ref_fast.so" if fast else "libelas_ref.so"
+    def __init__(self, fast=False, omp=False):
+        # omp: the reference's OpenMP variant (timing only; it has no stage taps, only process())
+        name = "libelas_ref_omp.so" if omp else ("libelas_ref_fast.so" if fast else "libelas_ref.so")
         path = os.path.join(HERE, "_ref", name)
         if not os.path.exists(path):
             raise FileNotFoundError(path + " missing: run oracle/build_ref.sh where /root/reference exists")

@@ -8,9 +8,15 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load the resulting library.  The product (csrc/) never links or dlopens it.
 
+#ifdef ORACLE_REF_OMP
+// the reference's OpenMP variant (`make omp=1`): timing baseline only (racy, not a parity target); only process() is wrapped,
+// and `private` must stay a keyword for its `#pragma omp ... private(...)` clauses
+#include "omp_includes/elas/elas.cpp"
+#else
 #define private public
 #include "serial_includes/elas/elas.cpp"   // -I /root/reference/src
 #undef private
+#endif
 
 #include <chrono>
 
@@ -60,6 +66,7 @@ static Elas::parameters to_ref(const ref_params *p) {
     return q;
 }
 
+#ifndef ORACLE_REF_OMP  // ---- helpers of the stage taps (serial oracle only) ----
 static Elas make_elas(const ref_params *p, int W, int H) {
     Elas e(to_ref(p));
     e.width = W;
@@ -95,6 +102,8 @@ static std::vector<Elas::triangle> to_tris(const int32_t *tri, const float *plan
     }
     return v;
 }
+
+#endif  // ORACLE_REF_OMP
 
 extern "C" {
 
@@ -135,6 +144,7 @@ double ref_process(const ref_params *p, const uint8_t *I1, const uint8_t *I2, in
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+#ifndef ORACLE_REF_OMP  // ---- stage taps (serial oracle only) ----
 // Descriptor (src/common_includes/elas/descriptor.cpp:30) on the bpl-padded copy made like
 // process() does (elas.cpp:33-50).  out: 16*W*H bytes.
 void ref_descriptor(const uint8_t *I, int W, int H, int stride, int subsampling, uint8_t *out) {
@@ -301,6 +311,8 @@ void ref_median(const ref_params *p, int W, int H, float *D) {
     Elas e = make_elas(p, W, H);
     e.median(D);
 }
+
+#endif  // ORACLE_REF_OMP
 
 const char *ref_build_flags() {
 #ifdef ORACLE_REF_FLAGS
