@@ -78,26 +78,30 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     const int u = x << a.shift, v = y << a.shift;         // image pixel (elas.cpp:707-711: d_addr = (u/2, v/2) when subsampling)
     const int f = blockIdx.z >> 1;
     const int W = a.W, H = a.H;
-    const size_t N = (size_t)W * H;
     const bool in = x < a.Dw;
-    const size_t pix = (size_t)y * a.Dw + (in ? x : 0);
-    float *D = a.D[SIDE] + (size_t)f * a.DN;
+    // per-frame bases are warp-uniform 64-bit values; everything per pixel is a 32-bit offset from them (one IMAD.WIDE each)
+    // (unsigned x unsigned -> 64 bit is one IMAD.WIDE.U32; signed operands would drag sign extensions along)
+    const unsigned uf = (unsigned)f;
+    const size_t fN = (size_t)uf * (unsigned)(W * H), fDN = (size_t)uf * (unsigned)a.DN;
+    const int pix = y * a.Dw + (in ? x : 0);
+    float *D = a.D[SIDE] + fDN;
 
     const int row = max(min(v, H - 3), 2);  // elas.cpp:718
-    const uint4 *own = reinterpret_cast<const uint4 *>(a.desc[SIDE]) + (size_t)f * N + (size_t)row * W;
+    const int rowW = row * W;
+    const uint4 *own = reinterpret_cast<const uint4 *>(a.desc[SIDE]) + fN;
     // descriptor of the other image at this pixel's own column; hypothesis d reads po[-d] (left) / po[+d] (right).
     // Rows are contiguous and 2 <= row <= H-3, so po[+-d] stays inside the frame's descriptor image for every
     // d <= disp_max even where the warped column leaves the row: loads never need a guard, only the result does.
-    const uint4 *po = reinterpret_cast<const uint4 *>(a.desc[SIDE ^ 1]) + (size_t)f * N + (size_t)row * W + u;
+    const uint4 *po = desc_at(reinterpret_cast<const uint4 *>(a.desc[SIDE ^ 1]) + fN, rowW + u);
 
     // Three independent loads are issued up front (owner index, own descriptor, first 128 candidate bits of the grid
     // cell), so that the prologue waits for ONE memory round trip before the plane record instead of four chained ones.
     const int uc = in ? min(u, W - 1) : W - 1;
     const int gx = a.grid_size == 1 ? uc : (int)__umulhi((unsigned)uc, a.grid_magic);  // u / grid_size by reciprocal (exact for u < 2^16)
     const int gy = a.grid_size == 1 ? v : (int)__umulhi((unsigned)v, a.grid_magic);    // u, v >= 0: equals the float floor (elas.cpp:744-745)
-    const uint32_t *cell = a.grid[SIDE] + ((size_t)f * a.gw * a.gh + (size_t)gy * a.gw + gx) * a.gwords;
-    const int o = in ? __ldg(a.owner[SIDE] + (size_t)f * a.DN + pix) : -1;
-    const uint4 c = __ldg(own + uc);
+    const uint32_t *cell = a.grid[SIDE] + (size_t)uf * (unsigned)(a.gw * a.gh * a.gwords) + (unsigned)((gy * a.gw + gx) * a.gwords);
+    const int o = in ? __ldg(a.owner[SIDE] + fDN + (unsigned)pix) : -1;
+    const uint4 c = __ldg(desc_at(own, rowW + uc));
     uint4 m4_first = __ldg(reinterpret_cast<const uint4 *>(cell));
     const uint4 k128 = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
     // elas.cpp:714 (column range) and :731-736 (texture)
@@ -105,7 +109,7 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     int d_plane = 0, dmin = 1, dmax = 0;  // empty band for inactive lanes
     unsigned prior_on = 0u;
     if (active) {
-        const PlaneRec pr = a.rec[SIDE][(size_t)f * a.maxT + o];
+        const PlaneRec pr = (a.rec[SIDE] + (size_t)uf * (unsigned)a.maxT)[(unsigned)o];
         // elas.cpp:739: (a*u + b*v) + c in f32, separate roundings, truncation like cvttss2si
         const float fp = __fadd_rn(__fadd_rn(__fmul_rn(pr.a, (float)u), __fmul_rn(pr.b, (float)v)), pr.c);
         d_plane = f2i_trunc_x86(fp);
@@ -187,7 +191,7 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     if (in) {
         float out = -10.f;                                                    // elas.cpp:820-826: pixels nobody writes keep -10
         if (active) out = key != 0xFFFFFFFFu ? (float)(key & 0xFFFu) : -1.f;  // elas.cpp:797-800
-        D[pix] = out;
+        D[(unsigned)pix] = out;
     }
     if (COUNT) {
         const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, n_hyp);
