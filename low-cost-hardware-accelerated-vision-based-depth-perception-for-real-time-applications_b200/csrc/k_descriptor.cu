@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(NT) k_descriptor(const uint8_t *__restrict__ i
         const int r = i / SW, c = i - r * SW;
         const int y = y0 - 3 + r, x = x0 - 4 + c;
         vals[k] = 0;
-        if (i < IN_ROWS * SW && y >= 0 && y < H && x >= 0 && x < W) vals[k] = __ldg(I + (size_t)y * W + x);
+        if (i < IN_ROWS * SW && y >= 0 && y < H && x >= 0 && x < W) vals[k] = __ldg(I + (unsigned)(y * W) + x);
     }
 #pragma unroll
     for (int k = 0; k < P1_ITERS; k++) {
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(NT) k_descriptor(const uint8_t *__restrict__ i
                 // q.w = dv(v-1,u) | dv(v,u-1) | dv(v,u+1) | dv(v+1,u)
                 q.w = __byte_perm(__byte_perm(dw[k], dw[k + 1], 0x0641), dw[k + 2], 0x5210);
             }
-            out[(size_t)v * W + u] = q;
+            out[(unsigned)(v * W + u)] = q;
         }
     }
 }

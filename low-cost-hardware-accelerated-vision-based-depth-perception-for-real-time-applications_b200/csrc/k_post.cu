@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) k_lr_check(const float *__restrict__ D1in
     const int v_end = min(row0 + (int)(blockIdx.y + 1) * LR_ROWS, row1);
 #pragma unroll 4
     for (int v = row0 + blockIdx.y * LR_ROWS; v < v_end; v++) {
-        const size_t base = ((size_t)blockIdx.z * H + v) * W;
+        const size_t base = (size_t)blockIdx.z * (unsigned)(H * W) + (unsigned)(v * W);
         const float d1 = D1in[base + u];
         const float d2 = D2in[base + u];
         float o1 = -10.f, o2 = -10.f;
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(128) k_mean_h(const float *__restrict__ D_all,
     const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (c0 >= W) return;
     const int v = blockIdx.y;
-    const size_t base = ((size_t)blockIdx.z * H + v) * W;
+    const size_t base = (size_t)blockIdx.z * (unsigned)(H * W) + (unsigned)(v * W);
     const float *row = D_all + base;
     float x[11];
 #pragma unroll
@@ -267,18 +267,18 @@ __global__ void __launch_bounds__(128) k_mean_v(const float *__restrict__ tmp_al
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u < 3 || u >= W - 3) return;
     const int r0 = blockIdx.y * 4;
-    const size_t img = (size_t)blockIdx.z * H * W;
+    const size_t img = (size_t)blockIdx.z * (unsigned)(H * W);
     float x[11];
 #pragma unroll
     for (int k = 0; k < 11; k++) {
         const int rr = r0 - 4 + k;
-        x[k] = (rr >= 0 && rr < H) ? tmp_all[img + (size_t)rr * W + u] : -10.f;
+        x[k] = (rr >= 0 && rr < H) ? tmp_all[img + (unsigned)(rr * W + u)] : -10.f;
     }
     float r;
-    if (r0 + 0 >= 4 && r0 + 0 <= H - 4 && mean8<MODE, 0>(x, &r)) D_all[img + (size_t)(r0 + 0) * W + u] = r;
-    if (r0 + 1 >= 4 && r0 + 1 <= H - 4 && mean8<MODE, 1>(x, &r)) D_all[img + (size_t)(r0 + 1) * W + u] = r;
-    if (r0 + 2 >= 4 && r0 + 2 <= H - 4 && mean8<MODE, 2>(x, &r)) D_all[img + (size_t)(r0 + 2) * W + u] = r;
-    if (r0 + 3 >= 4 && r0 + 3 <= H - 4 && mean8<MODE, 3>(x, &r)) D_all[img + (size_t)(r0 + 3) * W + u] = r;
+    if (r0 + 0 >= 4 && r0 + 0 <= H - 4 && mean8<MODE, 0>(x, &r)) D_all[img + (unsigned)((r0 + 0) * W + u)] = r;
+    if (r0 + 1 >= 4 && r0 + 1 <= H - 4 && mean8<MODE, 1>(x, &r)) D_all[img + (unsigned)((r0 + 1) * W + u)] = r;
+    if (r0 + 2 >= 4 && r0 + 2 <= H - 4 && mean8<MODE, 2>(x, &r)) D_all[img + (unsigned)((r0 + 2) * W + u)] = r;
+    if (r0 + 3 >= 4 && r0 + 3 <= H - 4 && mean8<MODE, 3>(x, &r)) D_all[img + (unsigned)((r0 + 3) * W + u)] = r;
 }
 
 // Half-resolution variant (subsampling, elas.cpp:1334-1400): 4 taps c-2 .. c+1, ring slots = coordinate mod 4, the four
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(128) k_mean4_h(const float *__restrict__ D_all
     const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (c0 >= W) return;
     const int v = blockIdx.y;
-    const size_t base = ((size_t)blockIdx.z * H + v) * W;
+    const size_t base = (size_t)blockIdx.z * (unsigned)(H * W) + (unsigned)(v * W);
     const float *row = D_all + base;
     float x[7];
 #pragma unroll
@@ -341,18 +341,18 @@ __global__ void __launch_bounds__(128) k_mean4_v(const float *__restrict__ tmp_a
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u < 3 || u >= W - 3) return;
     const int r0 = blockIdx.y * 4;
-    const size_t img = (size_t)blockIdx.z * H * W;
+    const size_t img = (size_t)blockIdx.z * (unsigned)(H * W);
     float x[7];
 #pragma unroll
     for (int k = 0; k < 7; k++) {
         const int rr = r0 - 2 + k;
-        x[k] = (rr >= 0 && rr < H) ? tmp_all[img + (size_t)rr * W + u] : -10.f;
+        x[k] = (rr >= 0 && rr < H) ? tmp_all[img + (unsigned)(rr * W + u)] : -10.f;
     }
     float r;
-    if (r0 + 0 >= 2 && r0 + 0 <= H - 2 && mean4<MODE, 0>(x, &r)) D_all[img + (size_t)(r0 + 0) * W + u] = r;
-    if (r0 + 1 >= 2 && r0 + 1 <= H - 2 && mean4<MODE, 1>(x, &r)) D_all[img + (size_t)(r0 + 1) * W + u] = r;
-    if (r0 + 2 >= 2 && r0 + 2 <= H - 2 && mean4<MODE, 2>(x, &r)) D_all[img + (size_t)(r0 + 2) * W + u] = r;
-    if (r0 + 3 >= 2 && r0 + 3 <= H - 2 && mean4<MODE, 3>(x, &r)) D_all[img + (size_t)(r0 + 3) * W + u] = r;
+    if (r0 + 0 >= 2 && r0 + 0 <= H - 2 && mean4<MODE, 0>(x, &r)) D_all[img + (unsigned)((r0 + 0) * W + u)] = r;
+    if (r0 + 1 >= 2 && r0 + 1 <= H - 2 && mean4<MODE, 1>(x, &r)) D_all[img + (unsigned)((r0 + 1) * W + u)] = r;
+    if (r0 + 2 >= 2 && r0 + 2 <= H - 2 && mean4<MODE, 2>(x, &r)) D_all[img + (unsigned)((r0 + 2) * W + u)] = r;
+    if (r0 + 3 >= 2 && r0 + 3 <= H - 2 && mean4<MODE, 3>(x, &r)) D_all[img + (unsigned)((r0 + 3) * W + u)] = r;
 }
 
 // ---- median -------------------------------------------------------------------------------------------
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(128) k_median_h(const float *__restrict__ D_al
     const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (c0 >= W) return;
     const int v = blockIdx.y;
-    const size_t base = ((size_t)blockIdx.z * H + v) * W;
+    const size_t base = (size_t)blockIdx.z * (unsigned)(H * W) + (unsigned)(v * W);
     float out[4] = {0.f, 0.f, 0.f, 0.f};
     if (v >= 3 && v < H - 3) {
         float x[10];
@@ -403,18 +403,18 @@ __global__ void __launch_bounds__(128) k_median_v(const float *__restrict__ tmp_
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u < 3 || u >= W - 3) return;
     const int r0 = blockIdx.y * 4;
-    const size_t img = (size_t)blockIdx.z * H * W;
+    const size_t img = (size_t)blockIdx.z * (unsigned)(H * W);
     float x[10];
 #pragma unroll
     for (int k = 0; k < 10; k++) {
         const int rr = r0 - 3 + k;
-        x[k] = (rr >= 0 && rr < H) ? tmp_all[img + (size_t)rr * W + u] : 0.f;
+        x[k] = (rr >= 0 && rr < H) ? tmp_all[img + (unsigned)(rr * W + u)] : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int v = r0 + j;
         if (v >= 3 && v < H - 3) {
-            const size_t idx = img + (size_t)v * W + u;
+            const size_t idx = img + (unsigned)(v * W + u);
             if (D_all[idx] >= 0.f) D_all[idx] = median7(x[j], x[j + 1], x[j + 2], x[j + 3], x[j + 4], x[j + 5], x[j + 6]);
         }
     }
