@@ -6,11 +6,14 @@
 // the relation is symmetric, so the partition (and therefore the result) does not depend on the order.
 // (Invalid pixels are -10 after the L/R check, |(-10) - d| >= 10 > threshold, so they never join a segment.)
 //
-// Algorithm: lock-free union-find over pixel indices (roots are the minimum index of a component).
-//   1. init   : every pixel links to the leftmost pixel of its horizontal run (warp ballot, no atomics);
-//   2. merge  : vertical edges and run boundaries are united with atomicMin hooks;
-//   3. count  : each pixel finds its root and adds 1 to the root's counter;
-//   4. prune  : pixels whose root counts < speckle_size become -10.
+// Algorithm: two-level lock-free union-find (roots are the minimum index of a component).
+//   1. tile    : a CTA labels a 128 x 16 pixel tile entirely in shared memory (run starts by warp ballot, vertical
+//                edges with atomicMin hooks), counts the sizes of the tile-local components and writes, per pixel, the
+//                global index of its LOCAL root; local roots start as their own parents in the global forest;
+//   2. borders : only the edges that cross tile borders (1/16 of the vertical, 1/128 of the horizontal ones) are united
+//                in global memory, and only between local roots -- a few thousand nodes instead of W*H;
+//   3. totals  : every local root adds its size to its global root;
+//   4. prune   : pixels whose global root counts < speckle_size become -10.
 #include "svb_internal.h"
 
 namespace svb {
@@ -46,138 +49,153 @@ __device__ void unite(int32_t *labels, int a, int b) {
 }
 
 // Every per-pixel kernel below lets a thread walk RPB consecutive rows of its column: 8x fewer, 8x longer CTAs than
-// one pixel per thread (the one-pixel form was bound by CTA launch rate and exposed load latency: ~1.2 TB/s effective).
+// one pixel per thread (the one-pixel form was bound by CTA launch rate and exposed load latency).
 constexpr int RPB = 8;
+constexpr int TW = 128, TH = 2 * RPB;  // tile: 128 columns x 16 rows, 256 threads (thread = one column, 8 rows)
 
-// grid: (ceil(W/128), ceil(H/RPB), nimg)   labels are indices local to the image; invalid pixels get label -1
-__global__ void __launch_bounds__(128) k_ccl_init(const float *__restrict__ D_all, int32_t *__restrict__ labels_all, int32_t *__restrict__ sizes_all,
-                                                 int W, int H, float thr) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t img = (size_t)blockIdx.z * W * H;
-    const int lane = threadIdx.x & 31;
-    const bool in = u < W;
-    const int v_end = min((int)(blockIdx.y + 1) * RPB, H);
-#pragma unroll 4
-  for (int v = blockIdx.y * RPB; v < v_end; v++) {
-    const int idx = v * W + u;
-    const float d = in ? D_all[img + idx] : -10.f;
-    const float dl = __shfl_up_sync(0xFFFFFFFFu, d, 1);
-    const float dleft = (lane == 0) ? ((in && u > 0) ? D_all[img + idx - 1] : -10.f) : dl;
-    // linked to the left neighbour?
-    const bool link = in && u > 0 && similar(d, dleft, thr);
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, link);
-    if (!in) continue;
-    // run start inside this warp: the nearest lane at or below `lane` whose link bit is clear
-    const unsigned clear_below = ~bal & ((2u << lane) - 1u);  // lanes <= lane with no left link (lane 31: all bits)
-    const unsigned mask = (lane == 31) ? ~bal : clear_below;
-    const int start_lane = mask ? (31 - __clz(mask)) : -1;
-    int label;
-    if (d < 0.f) {
-        label = -1;  // never joins anything (|-10 - x| > thr); pruned unconditionally (a segment of one pixel)
-    } else if (start_lane >= 0) {
-        label = idx - (lane - start_lane);
-    } else {
-        // the run continues into the previous warp: link to the pixel just left of this warp's first lane
-        label = idx - lane - 1;
-    }
-    labels_all[img + idx] = label;
-    if (label == idx) sizes_all[img + idx] = 0;  // only run starts can end up as roots (a root is its segment's minimum index)
-  }
-}
-
-// Vertical edges.  An edge (u,v)-(u,v-1) is skipped when the edge one column to the left already unites the same two
-// runs: both pixels are linked to their left neighbours and those neighbours are vertically similar.
-__global__ void __launch_bounds__(128) k_ccl_merge(const float *__restrict__ D_all, int32_t *__restrict__ labels_all, int W, int H, float thr) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= W) return;
-    const size_t img = (size_t)blockIdx.z * W * H;
-    const int v0 = max((int)blockIdx.y * RPB, 1), v_end = min((int)(blockIdx.y + 1) * RPB, H);
-    if (v0 >= v_end) return;
-    // the row above is carried in registers from one step to the next
-    float du = D_all[img + (size_t)(v0 - 1) * W + u];
-    float dul = u > 0 ? D_all[img + (size_t)(v0 - 1) * W + u - 1] : -10.f;
-    for (int v = v0; v < v_end; v++) {
-        const int idx = v * W + u;
-        const float d = D_all[img + idx];
-        const float dl = u > 0 ? D_all[img + idx - 1] : -10.f;
-        if (similar(d, du, thr) && !(u > 0 && similar(d, dl, thr) && similar(du, dul, thr) && similar(dl, dul, thr)))
-            unite(labels_all + img, idx, idx - W);
-        du = d;
-        dul = dl;
-    }
-}
-
-// Flatten labels to roots and count segment sizes.  A CTA covers a 128 x 8 pixel tile; equal roots are first combined
-// inside each warp (match.any), then across the CTA in a small shared-memory hash table, so a large segment costs one
-// global atomic per tile instead of one per pixel.
-constexpr int CNT_ROWS = 8;
-constexpr int CNT_SLOTS = 64;
-
-__global__ void __launch_bounds__(32 * CNT_ROWS) k_ccl_count(int32_t *__restrict__ labels_all, int32_t *__restrict__ sizes_all, int W, int H) {
-    __shared__ int s_key[CNT_SLOTS];
-    __shared__ int s_val[CNT_SLOTS];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x < CNT_SLOTS) {
-        s_key[threadIdx.x] = -1;
-        s_val[threadIdx.x] = 0;
+// grid: (ceil(W/TW), ceil(H/TH), nimg).  labels: -1 for invalid pixels, else the global index (v*W + u) of the pixel's
+// tile-local root; sizes = size of the tile-local component at its local root, 0 everywhere else.
+__global__ void __launch_bounds__(2 * TW) k_ccl_tile(const float *__restrict__ D_all, int32_t *__restrict__ labels_all,
+                                                    int32_t *__restrict__ sizes_all, int W, int H, float thr) {
+    __shared__ float sD[TH * TW];
+    __shared__ int sL[TH * TW];
+    __shared__ int sS[TH * TW];
+    const size_t img = (size_t)blockIdx.z * (unsigned)(W * H);
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int c = threadIdx.x & (TW - 1), r0 = (threadIdx.x >> 7) * RPB, lane = threadIdx.x & 31;
+    const int u = x0 + c;
+#pragma unroll
+    for (int k = 0; k < RPB; k++) {
+        const int r = r0 + k, v = y0 + r;
+        sD[r * TW + c] = (u < W && v < H) ? D_all[img + (unsigned)(v * W + u)] : -10.f;
+        sS[r * TW + c] = 0;
     }
     __syncthreads();
-    const size_t img = (size_t)blockIdx.z * W * H;
-    int32_t *labels = labels_all + img;
-    int32_t *sizes = sizes_all + img;
-    const int v = blockIdx.y * CNT_ROWS + wid;
-    if (v < H) {
+    // every pixel links to the leftmost pixel of its horizontal run inside the warp's 32 columns (ballot, no atomics);
+    // a run that continues into the previous warp links to the pixel just left of this warp
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int u = blockIdx.x * 128 + k * 32 + lane;
-            int r = -1;
-            if (u < W) {
-                const int idx = v * W + u;
-                const int l = labels[idx];
-                if (l >= 0) {
-                    r = find_root(labels, l);
-                    if (r != l) labels[idx] = r;  // roots are fixed once merging has finished
-                }
-            }
-            const unsigned act = __ballot_sync(0xFFFFFFFFu, r >= 0);
-            if (r >= 0) {
-                const unsigned same = __match_any_sync(act, r);
-                if (lane == __ffs(same) - 1) {
-                    const int cnt = __popc(same);
-                    unsigned h = ((unsigned)r * 2654435761u) >> 26;
-                    bool done = false;
-#pragma unroll 1
-                    for (int t = 0; t < 4 && !done; t++) {
-                        const int old = atomicCAS(&s_key[h], -1, r);
-                        if (old == -1 || old == r) {
-                            atomicAdd(&s_val[h], cnt);
-                            done = true;
-                        }
-                        h = (h + 1) & (CNT_SLOTS - 1);
-                    }
-                    if (!done) atomicAdd(sizes + r, cnt);
-                }
-            }
+    for (int k = 0; k < RPB; k++) {
+        const int idx = (r0 + k) * TW + c;
+        const float d = sD[idx];
+        const bool link = c > 0 && similar(d, sD[idx - 1], thr);
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, link);
+        const unsigned clear_below = ~bal & ((2u << lane) - 1u);  // lanes <= lane with no left link (lane 31: all bits)
+        const unsigned mask = (lane == 31) ? ~bal : clear_below;
+        const int start_lane = mask ? (31 - __clz(mask)) : -1;
+        int label = -1;  // invalid pixels never join anything (|-10 - x| > thr) and are pruned unconditionally
+        if (d >= 0.f) label = start_lane >= 0 ? idx - (lane - start_lane) : idx - lane - 1;
+        sL[idx] = label;
+    }
+    __syncthreads();
+    // vertical edges inside the tile; an edge is skipped when the edge one column to the left unites the same two runs
+#pragma unroll
+    for (int k = 0; k < RPB; k++) {
+        const int r = r0 + k, idx = r * TW + c;
+        if (r == 0) continue;
+        const float d = sD[idx], du = sD[idx - TW];
+        if (!similar(d, du, thr)) continue;
+        if (c > 0) {
+            const float dl = sD[idx - 1], dul = sD[idx - TW - 1];
+            if (similar(d, dl, thr) && similar(du, dul, thr) && similar(dl, dul, thr)) continue;
+        }
+        unite(sL, idx, idx - TW);
+    }
+    __syncthreads();
+    // flatten, count the tile-local sizes (equal roots combined inside each warp first)
+    int root[RPB];
+#pragma unroll
+    for (int k = 0; k < RPB; k++) {
+        const int idx = (r0 + k) * TW + c;
+        const int l = sL[idx];
+        root[k] = l >= 0 ? find_root(sL, l) : -1;
+        const unsigned act = __ballot_sync(0xFFFFFFFFu, root[k] >= 0);
+        if (root[k] >= 0) {
+            const unsigned same = __match_any_sync(act, root[k]);
+            if (lane == __ffs(same) - 1) atomicAdd(&sS[root[k]], __popc(same));
         }
     }
     __syncthreads();
-    if (threadIdx.x < CNT_SLOTS && s_key[threadIdx.x] >= 0) atomicAdd(sizes + s_key[threadIdx.x], s_val[threadIdx.x]);
+    int32_t *labels = labels_all + img;
+    int32_t *sizes = sizes_all + img;
+#pragma unroll
+    for (int k = 0; k < RPB; k++) {
+        const int r = r0 + k, v = y0 + r, idx = r * TW + c;
+        if (u >= W || v >= H) continue;
+        const unsigned g = (unsigned)(v * W + u);
+        int label = -1;
+        if (root[k] >= 0) {
+            const int rr = root[k] >> 7, rc = root[k] & (TW - 1);
+            label = (y0 + rr) * W + x0 + rc;
+        }
+        labels[g] = label;
+        sizes[g] = root[k] == idx ? sS[idx] : 0;  // > 0 marks a tile-local root
+    }
+}
+
+// Edges across tile borders: rows v = TH, 2 TH, ... (against v - 1) and columns u = TW, 2 TW, ... (against u - 1).
+// grid: (ceil((nrow*W + ncol*H) / 256), nimg).  A horizontal-border edge is skipped when the edge one column to the left
+// (same border, same tile column) unites the same two components.
+__global__ void __launch_bounds__(256) k_ccl_borders(const float *__restrict__ D_all, int32_t *__restrict__ labels_all, int W, int H, float thr) {
+    const size_t img = (size_t)blockIdx.y * (unsigned)(W * H);
+    const float *D = D_all + img;
+    int32_t *labels = labels_all + img;
+    const int nrow = (H - 1) / TH, ncol = (W - 1) / TW;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int p, q;
+    if (i < nrow * W) {
+        const int k = i / W, u = i - k * W;
+        p = (k + 1) * TH * W + u;
+        q = p - W;
+        const float d = D[p], du = D[q];
+        if (!similar(d, du, thr)) return;
+        if ((u & (TW - 1)) != 0) {
+            const float dl = D[p - 1], dul = D[q - 1];
+            if (similar(d, dl, thr) && similar(du, dul, thr) && similar(dl, dul, thr)) return;
+        }
+    } else if (i < nrow * W + ncol * H) {
+        const int j = i - nrow * W;
+        const int k = j / H, v = j - k * H;
+        p = v * W + (k + 1) * TW;
+        q = p - 1;
+        if (!similar(D[p], D[q], thr)) return;
+    } else {
+        return;
+    }
+    unite(labels, labels[p], labels[q]);  // both pixels are valid: their labels are local roots
+}
+
+// Every tile-local root adds its size to the root of its component.
+__global__ void __launch_bounds__(128) k_ccl_totals(const int32_t *__restrict__ labels_all, int32_t *__restrict__ sizes_all, int W, int H) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= W) return;
+    const size_t img = (size_t)blockIdx.z * (unsigned)(W * H);
+    const int32_t *labels = labels_all + img;
+    int32_t *sizes = sizes_all + img;
+    const int v_end = min((int)(blockIdx.y + 1) * RPB, H);
+#pragma unroll 4
+    for (int v = blockIdx.y * RPB; v < v_end; v++) {
+        const int idx = v * W + u;
+        const int n = sizes[idx];
+        if (n <= 0 || labels[idx] == idx) continue;  // not a local root, or a local root that is also its component's root
+        atomicAdd(sizes + find_root(labels, idx), n);  // nobody else touches sizes[idx]: idx is not a global root
+    }
 }
 
 __global__ void __launch_bounds__(128) k_ccl_prune(float *__restrict__ D_all, const int32_t *__restrict__ labels_all,
                                                   const int32_t *__restrict__ sizes_all, int W, int H, int min_size) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= W) return;
-    const size_t img = (size_t)blockIdx.z * W * H;
+    const size_t img = (size_t)blockIdx.z * (unsigned)(W * H);
+    const int32_t *labels = labels_all + img;
     const int v_end = min((int)(blockIdx.y + 1) * RPB, H);
 #pragma unroll 4
     for (int v = blockIdx.y * RPB; v < v_end; v++) {
         const int idx = v * W + u;
-        const int r = labels_all[img + idx];
+        const int r = labels[idx];
         if (r < 0) {
-            if (1 < min_size) D_all[img + idx] = -10.f;
-        } else if (sizes_all[img + r] < min_size) {
-            D_all[img + idx] = -10.f;
+            if (1 < min_size) D_all[img + (unsigned)idx] = -10.f;
+        } else if (sizes_all[img + (unsigned)find_root(labels, r)] < min_size) {
+            D_all[img + (unsigned)idx] = -10.f;
         }
     }
 }
@@ -189,15 +207,16 @@ int launch_remove_small_segments(const Dims &d, const svb_params &p, float *D, i
     const int W = d.Dw, H = d.Dh;
     // elas.cpp:1017-1022: at half resolution a speckle is sqrt(speckle_size) * 2 pixels
     const int min_size = d.sub ? (int)(sqrtf((float)p.speckle_size) * 2) : p.speckle_size;
-    dim3 grid((W + 127) / 128, (H + RPB - 1) / RPB, nimg);
-    k_ccl_init<<<grid, 128, 0, s>>>(D, labels, sizes, W, H, p.speckle_sim_threshold);
+    dim3 tiles((W + TW - 1) / TW, (H + TH - 1) / TH, nimg);
+    k_ccl_tile<<<tiles, 2 * TW, 0, s>>>(D, labels, sizes, W, H, p.speckle_sim_threshold);
     SVB_LAUNCH_CHECK();
-    if (H > 1) {
-        k_ccl_merge<<<grid, 128, 0, s>>>(D, labels, W, H, p.speckle_sim_threshold);
+    const int border_edges = ((H - 1) / TH) * W + ((W - 1) / TW) * H;
+    if (border_edges > 0) {
+        k_ccl_borders<<<dim3((border_edges + 255) / 256, nimg), 256, 0, s>>>(D, labels, W, H, p.speckle_sim_threshold);
         SVB_LAUNCH_CHECK();
     }
-    dim3 gc((W + 127) / 128, (H + CNT_ROWS - 1) / CNT_ROWS, nimg);
-    k_ccl_count<<<gc, 32 * CNT_ROWS, 0, s>>>(labels, sizes, W, H);
+    dim3 grid((W + 127) / 128, (H + RPB - 1) / RPB, nimg);
+    k_ccl_totals<<<grid, 128, 0, s>>>(labels, sizes, W, H);
     SVB_LAUNCH_CHECK();
     k_ccl_prune<<<grid, 128, 0, s>>>(D, labels, sizes, W, H, min_size);
     SVB_LAUNCH_CHECK();
