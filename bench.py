@@ -465,7 +465,7 @@ def main():
             "dtype": "u8/int32 SAD + f32 filters + f64 reprojection", "data": "synthetic",
             "config": {"workload": "synthetic KITTI-shape 1242x375 stereo pairs, batch of %d frames per GPU (BASELINE configs[1]), pipeline "
                                    "preset (MIDDLEBURY + postprocess_only_left + filter_adaptive_mean), disparity + point cloud" % args.batch,
-                       "frames_per_gpu": args.batch, "frames_per_launch": args.chunk, "lanes": 3, "single_stream": bool(args.single_stream),
+                       "frames_per_gpu": args.batch, "frames_per_launch": args.chunk, "lanes": int(os.environ.get("SVB_LANES", "4")), "single_stream": bool(args.single_stream),
                        "l2": "inputs larger than L2 (%.0f MB of images, %.0f MB of descriptors per step)" % (2 * N * args.batch / 1e6,
                                                                                                             32 * N * args.batch / 1e6),
                        "parallelism": "frame-batch data parallel x%d, no collective" % world},

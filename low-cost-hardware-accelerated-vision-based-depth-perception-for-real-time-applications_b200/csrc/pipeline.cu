@@ -529,7 +529,7 @@ svb_context *svb_create(const svb_params *params, int width, int height, int chu
         const char *g = getenv("SVB_GPU_ORDER");
         if (g && atoi(g) == 0) c->gpu_order = false;
         const char *e = getenv("SVB_LANES");
-        const int n = e ? atoi(e) : 3;
+        const int n = e ? atoi(e) : 4;
         c->n_lanes = n < 1 ? 1 : (n > MAX_LANES ? MAX_LANES : n);
         if (c->chunk == 1) c->n_lanes = 1;  // single-frame contexts never pipeline
     }
