@@ -218,6 +218,43 @@ __device__ __forceinline__ void redundant_line(int16_t *work, int base, int stri
     }
 }
 
+// OR / AND-NOT of flag bits into one 16-bit lattice cell through a 32-bit atomic on the word that holds it (shared or
+// global memory; the other half of the word belongs to a neighbouring cell and is left alone).
+__device__ __forceinline__ void cell_set(int16_t *cell, int bits) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(cell);
+    atomicOr(reinterpret_cast<unsigned *>(a & ~(uintptr_t)3), (unsigned)bits << ((a & 2) * 8));
+}
+__device__ __forceinline__ void cell_clear(int16_t *cell, int bits) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(cell);
+    atomicAnd(reinterpret_cast<unsigned *>(a & ~(uintptr_t)3), ~((unsigned)bits << ((a & 2) * 8)));
+}
+
+// First sweep of removeInconsistentSupportPoints for every cell of every frame at once (the fixpoint iteration of
+// k_support_filter starts from R = {}: this IS its first sweep, and by far the most expensive one -- every valid cell
+// scans its window until it has found its supporters).  dcan = raw, plus SF_REMOVED where the count falls short.
+// grid: (ceil(cells / 256), nf)
+__global__ void __launch_bounds__(256) k_incon_first_sweep(const int16_t *__restrict__ dcan_raw_all, int16_t *__restrict__ dcan_all, int cw, int ch,
+                                                          int incon_window, int incon_threshold, int incon_min_support) {
+    const int cells = cw * ch;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    const int16_t *raw = dcan_raw_all + (size_t)blockIdx.y * (unsigned)cells;
+    int e = raw[i];
+    if (e >= 0) {
+        const int v = i / cw, u = i - v * cw;
+        const int u_lo = max(u - incon_window, 0), u_hi = min(u + incon_window, cw - 1);
+        const int v_lo = max(v - incon_window, 0), v_hi = min(v + incon_window, ch - 1);
+        int support_cnt = 0;
+        for (int v2 = v_lo; v2 <= v_hi && support_cnt < incon_min_support; v2++)
+            for (int u2 = u_lo; u2 <= u_hi; u2++) {
+                const int e2 = raw[v2 * cw + u2];
+                support_cnt += (e2 >= 0 && abs(e - e2) <= incon_threshold) ? 1 : 0;
+            }
+        if (support_cnt < incon_min_support) e |= SF_REMOVED;
+    }
+    dcan_all[(size_t)blockIdx.y * (unsigned)cells + i] = (int16_t)e;
+}
+
 // SMEM = true: the lattice lives in shared memory (2 bytes per cell; every frame size up to about 1080p at step 5);
 // SMEM = false: it is worked on in place in the global dcan array (4K frames).
 template <bool SMEM>
@@ -240,26 +277,36 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(const int16_t *__
     __shared__ int s_base;
     __shared__ unsigned long long s_best[4];
 
-    for (int i = tid; i < cells; i += SF_THREADS) work[i] = raw[i];
-    __syncthreads();
+    // dcan already holds the result of the first sweep (k_incon_first_sweep): raw values, SF_REMOVED where it struck
+    (void)raw;
+    if (SMEM) {
+        for (int i = tid; i < cells; i += SF_THREADS) work[i] = dcan[i];
+        __syncthreads();
+    }
 
     // ---- inconsistent points: parallel sweeps to the fixpoint; a removed cell keeps its value and gets SF_REMOVED ----
-    // Only the first sweep looks at every cell.  A cell's count can change only when a cell of its window is removed, so
-    // a removal marks its window for the NEXT sweep (two alternating mark bits in the cell itself; shared-memory lattice
-    // only, where the marks are 32-bit atomics on the word that holds the 16-bit cell).
-    unsigned *words = reinterpret_cast<unsigned *>(work);
+    // A cell's count can change only when a cell of its window is removed, so a removal marks its window for the NEXT
+    // sweep (two alternating mark bits in the cell itself, set with 32-bit atomics on the word that holds the cell).
+    // The removals of the first sweep mark their windows here.
+    // in global memory the flag atomics act in L2: the cells are read around L1 for as long as flags are in play
+    auto cell = [&](int idx) -> int { return SMEM ? (int)work[idx] : (int)__ldcg(work + idx); };
     int cur_bit = SF_MARK_A, next_bit = SF_MARK_B;
-    bool first = true;
+    for (int i = tid; i < cells; i += SF_THREADS) {
+        const int e = cell(i);
+        if (e < 0 || !(e & SF_REMOVED)) continue;
+        const int v = i / cw, u = i - v * cw;
+        for (int v2 = max(v - incon_window, 0); v2 <= min(v + incon_window, ch - 1); v2++)
+            for (int u2 = max(u - incon_window, 0); u2 <= min(u + incon_window, cw - 1); u2++)
+                if (cell(v2 * cw + u2) >= 0) cell_set(work + v2 * cw + u2, cur_bit);
+    }
+    __syncthreads();
     while (true) {
         if (tid == 0) s_changed = 0;
         __syncthreads();
         for (int i = tid; i < cells; i += SF_THREADS) {
-            const int e = work[i];
-            if (e < 0 || (e & SF_REMOVED)) continue;
-            if (SMEM && !first) {
-                if (!(e & cur_bit)) continue;
-                atomicAnd(words + (i >> 1), ~((unsigned)cur_bit << (16 * (i & 1))));
-            }
+            const int e = cell(i);
+            if (e < 0 || (e & SF_REMOVED) || !(e & cur_bit)) continue;
+            cell_clear(work + i, cur_bit);
             const int dc = e & SF_VALUE;
             const int v = i / cw, u = i - v * cw;
             const int u_lo = max(u - incon_window, 0), u_hi = min(u + incon_window, cw - 1);
@@ -267,7 +314,7 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(const int16_t *__
             int support_cnt = 0;
             for (int v2 = v_lo; v2 <= v_hi && support_cnt < incon_min_support; v2++)
                 for (int u2 = u_lo; u2 <= u_hi; u2++) {
-                    const int e2 = work[v2 * cw + u2];
+                    const int e2 = cell(v2 * cw + u2);
                     if (e2 < 0) continue;
                     if (abs(dc - (e2 & SF_VALUE)) > incon_threshold) continue;
                     if ((e2 & SF_REMOVED) && precedes_colmajor(u2, v2, u, v)) continue;
@@ -275,29 +322,22 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(const int16_t *__
                 }
             if (support_cnt < incon_min_support) {
                 s_changed = 1;
-                if (SMEM) {
-                    atomicOr(words + (i >> 1), (unsigned)SF_REMOVED << (16 * (i & 1)));
-                    for (int v2 = v_lo; v2 <= v_hi; v2++)
-                        for (int u2 = u_lo; u2 <= u_hi; u2++) {
-                            const int j = v2 * cw + u2;
-                            if (work[j] >= 0) atomicOr(words + (j >> 1), (unsigned)next_bit << (16 * (j & 1)));
-                        }
-                } else {
-                    work[i] = (int16_t)(e | SF_REMOVED);
-                }
+                cell_set(work + i, SF_REMOVED);
+                for (int v2 = v_lo; v2 <= v_hi; v2++)
+                    for (int u2 = u_lo; u2 <= u_hi; u2++)
+                        if (cell(v2 * cw + u2) >= 0) cell_set(work + v2 * cw + u2, next_bit);
             }
         }
         __syncthreads();
         const int again = s_changed;
         __syncthreads();
         if (!again) break;
-        first = false;
         const int t = cur_bit;
         cur_bit = next_bit;
         next_bit = t;
     }
     for (int i = tid; i < cells; i += SF_THREADS) {
-        const int e = work[i];
+        const int e = cell(i);
         if (e >= 0) work[i] = (e & SF_REMOVED) ? (int16_t)-1 : (int16_t)(e & SF_VALUE);
     }
     __syncthreads();
@@ -436,6 +476,11 @@ int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dca
         set_error("support filter: disp_max %d too large for the lattice cell encoding", p.disp_max);
         return SVB_ERR_UNSUPPORTED;
     }
+    // first sweep of the inconsistent-point filter for all cells of all frames at once (dcan = raw + SF_REMOVED flags); the
+    // one-CTA-per-frame kernel below continues from there
+    k_incon_first_sweep<<<dim3((d.cw * d.ch + 255) / 256, nf), 256, 0, s>>>(dcan_raw, dcan, d.cw, d.ch, p.incon_window_size, p.incon_threshold,
+                                                                             p.incon_min_support);
+    SVB_LAUNCH_CHECK();
     const size_t smem = ((size_t)d.cw * d.ch * sizeof(int16_t) + 3) & ~(size_t)3;  // whole 32-bit words: the sweep marks cells with word atomics
     if (smem <= 200 * 1024) {
         if (smem > 48 * 1024) {  // opt in to large dynamic shared memory (per device, so not cached in a static)

@@ -137,7 +137,7 @@ int lane_create(svb_context *c, Lane &L) {
         SVB_TRY(host_alloc(&L.h_tri[s], C * d.maxT * 3));
     }
     SVB_TRY(dev_alloc(&L.dcan_raw, C * d.cw * d.ch));
-    SVB_TRY(dev_alloc(&L.dcan, C * d.cw * d.ch));
+    SVB_TRY(dev_alloc(&L.dcan, C * d.cw * d.ch + 2));  // + 2: the filters set flag bits with 32-bit atomics on the word holding a cell
     SVB_TRY(dev_alloc(&L.support, C * d.maxS * 3));
     SVB_TRY(dev_alloc(&L.nsupport, C));
     SVB_TRY(dev_alloc(&L.ntri, C * 3));

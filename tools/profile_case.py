@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """One chunk of the bench workload (32 synthetic KITTI-shape pairs, pipeline preset, disparity + point cloud), run
 `reps` times on one stream -- the program ncu is pointed at:
-   ncu --set full --import-source on --clock-control none --launch-skip 22 -c 22 -o gpurun_out/prof python tools/profile_case.py
-(22 launches per chunk; the first repetition is the warm-up that is skipped)."""
+   ncu --set full --import-source on --clock-control none --launch-skip 24 -c 24 -o gpurun_out/prof python tools/profile_case.py
+(24 launches per chunk; the first repetition is the warm-up that is skipped)."""
 import os
 import sys
 
