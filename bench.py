@@ -431,16 +431,19 @@ def main():
         ach = per_stage[top]["GBps"]
         # dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernels per launch of `ncu_frames_per_launch` frames, from the
         # committed `ncu --set full` capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py), scaled to this chunk size
-        traffic = None
+        traffic, ncu_pipes = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if top in tj.get("stages", {}):
                 traffic = tj["stages"][top]["dram_bytes_per_launch"] * args.chunk / tj["frames_per_launch"]
+                ncu_pipes = {k: tj["stages"][top][k] for k in ("alu_pipe_pct", "issue_active_pct") if k in tj["stages"][top]}
         roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_launch": sb[top] * args.chunk,
                 "avg_launch_ms": kernel_stages[top] / nlaunch_per_stage,
                 "share_of_step": kernel_stages[top] / sum(stage_ms.values()),
+                # what actually bounds this kernel (same committed ncu capture): the two SAD kernels are integer-ALU bound, DESIGN.md 5
+                "ncu_pipes": ncu_pipes,
                 "note": "durations from the single-stream timed steps (CUDA events on the launching stream bracket each stage; "
                         "no other kernel of ours runs concurrently), see DESIGN.md"}
 

@@ -21,6 +21,8 @@ rows = list(csv.reader(open(sys.argv[1])))
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 head, units = rows[0], rows[1]
 ki, ri, wi, ti = head.index("Kernel Name"), head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum"), head.index("gpu__time_duration.sum")
+ai = head.index("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")
+ii = head.index("smsp__issue_active.avg.pct_of_peak_sustained_active")
 out = {}
 for r in rows[2:]:
     stage = next((s for k, s in STAGE_OF if k in r[ki]), None)
@@ -29,5 +31,12 @@ for r in rows[2:]:
     e = out.setdefault(stage, {"dram_bytes_per_launch": 0.0, "kernels": 0, "ncu_time_us": 0.0})
     e["dram_bytes_per_launch"] += to_bytes(r[ri], units[ri]) + to_bytes(r[wi], units[wi])
     e["kernels"] += 1
-    e["ncu_time_us"] += float(r[ti].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[ti], 1e-3)
+    t_us = float(r[ti].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[ti], 1e-3)
+    e["ncu_time_us"] += t_us
+    if t_us > e.get("_longest", 0.0):  # pipe utilisation of the stage's longest kernel
+        e["_longest"] = t_us
+        e["alu_pipe_pct"] = float(r[ai].replace(",", ""))
+        e["issue_active_pct"] = float(r[ii].replace(",", ""))
+for e in out.values():
+    e.pop("_longest", None)
 print(json.dumps({"source": sys.argv[1], "frames_per_launch": frames, "stages": out}, indent=1))
