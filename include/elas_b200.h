@@ -124,6 +124,10 @@ int svb_stage_support(svb_context *ctx, const uint8_t *desc1, const uint8_t *des
 /* Elas::computeDelaunayTriangulation (elas.cpp:442-501) -- the host stage on its own */
 int svb_stage_delaunay(const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out);
 /* Elas::computeDisparityPlanes (elas.cpp:503-575): planes = m x {t1a,t1b,t1c,t2a,t2b,t2c} */
+/* The host half of the pipeline's stage: `order` = the n support indices in the order the divide-and-conquer meets them
+ * (lexicographic (x, y) sort, then the alternating-axis median partition with subsets of <= 3 x-sorted; duplicate-free
+ * input only), as csrc/k_order.cu computes it on the device. */
+int svb_stage_delaunay_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int32_t *tri, int cap, int *n_tri_out);
 /* The same stage as the pipeline runs it: vertex order (sort + alternating cuts) on the device, recursion on the host;
  * *used_device_order = 0 when the device flagged the list (duplicate coordinates, > 4096 points) and the host did it all. */
 int svb_stage_delaunay_pipeline(svb_context *ctx, const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out,

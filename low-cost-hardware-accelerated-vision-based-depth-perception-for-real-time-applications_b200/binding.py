@@ -121,6 +121,7 @@ def load():
         "svb_stage_support": [vp, vp, vp, vp, vp, vp, C.c_int, vp],
         "svb_stage_delaunay": [vp, C.c_int, C.c_int, vp, C.c_int, vp],
         "svb_stage_delaunay_pipeline": [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp],
+        "svb_stage_delaunay_ordered": [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp],
         "svb_stage_planes": [vp, vp, C.c_int, vp, C.c_int, vp],
         "svb_stage_grid": [vp, vp, C.c_int, C.c_int, vp],
         "svb_stage_disparity": [vp, vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp],
@@ -190,6 +191,21 @@ def delaunay(support, right):
     tri = np.zeros((cap, 3), np.int32)
     m = C.c_int(0)
     rc = lib.svb_stage_delaunay(_ptr(support), n, int(right), _ptr(tri), cap, C.byref(m))
+    if rc != 0:
+        raise SvbError(rc, lib.svb_last_error().decode())
+    return tri[: m.value].copy()
+
+
+def delaunay_ordered(support, right, order):
+    """Host half of the pipeline's Delaunay stage (no GPU needed): the recursion on a given vertex order."""
+    lib = load()
+    support = np.ascontiguousarray(support, np.int32)
+    order = np.ascontiguousarray(order, np.int32)
+    n = len(support)
+    cap = 2 * n + 16
+    tri = np.zeros((cap, 3), np.int32)
+    m = C.c_int(0)
+    rc = lib.svb_stage_delaunay_ordered(_ptr(support), n, int(right), _ptr(order), _ptr(tri), cap, C.byref(m))
     if rc != 0:
         raise SvbError(rc, lib.svb_last_error().decode())
     return tri[: m.value].copy()

@@ -797,6 +797,19 @@ int svb_stage_delaunay(const int32_t *support, int n, int right_image, int32_t *
     return SVB_OK;
 }
 
+// The host half of the pipeline's Delaunay stage on its own (no GPU needed): `order` is what k_order.cu would deliver.
+int svb_stage_delaunay_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int32_t *tri, int cap, int *n_tri_out) {
+    if (!support || !order || !tri || n < 0 || cap < 0) return SVB_ERR_ARG;
+    DelaunayScratch scratch;
+    const int m = delaunay_support_ordered(support, n, right_image ? 1 : 0, order, tri, cap, scratch);
+    if (m < 0) {
+        set_error("svb_stage_delaunay_ordered: `order` is not a permutation of 0..n-1");
+        return SVB_ERR_ARG;
+    }
+    if (n_tri_out) *n_tri_out = m;
+    return SVB_OK;
+}
+
 // Host Delaunay stage exactly as the pipeline runs it: the device orders the vertices (k_order.cu), the host recurses;
 // *used_device_order tells whether the device's order was usable (0: duplicates, > 4096 points, ... -> complete host path).
 int svb_stage_delaunay_pipeline(svb_context *c, const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out,

@@ -113,6 +113,33 @@ def test_host_delaunay_matches_reference_on_random_lattices(svb, ref, seed, n):
         assert np.array_equal(got, want), "seed %d n %d side %d" % (seed, n, side)
 
 
+def kd_order(x, y):
+    """numpy statement of the vertex order k_order.cu computes: lexicographic (x, y) sort, then alternating-axis median
+    cuts (x first), subsets of <= 3 left x-sorted (triangle.cpp:5243-5325, 5882-5913)."""
+    idx = np.lexsort((y, x))
+
+    def cut(ids, axis):
+        if len(ids) <= 3:
+            return list(ids[np.lexsort((y[ids], x[ids]))])
+        k = np.lexsort((y[ids], x[ids])) if axis == 0 else np.lexsort((x[ids], y[ids]))
+        ids = ids[k]
+        d = len(ids) >> 1
+        return cut(ids[:d], 1 - axis) + cut(ids[d:], 1 - axis)
+
+    return np.array(cut(idx, 0), np.int32)
+
+
+@pytest.mark.parametrize("seed,n", [(1, 3), (2, 4), (3, 7), (4, 50), (5, 400), (6, 2500)])
+def test_host_recursion_on_a_given_vertex_order(svb, ref, seed, n):
+    """delaunay_support_ordered (the host half of the pipeline's stage) fed with the order the device kernel is specified
+    to deliver; left image only (lattice points are distinct there, the right image may hold duplicates)."""
+    s = lattice_support(np.random.default_rng(seed), n)
+    order = kd_order(s[:, 0].astype(np.int64), s[:, 1].astype(np.int64))
+    assert np.array_equal(svb.delaunay_ordered(s, 0, order), ref.delaunay(s, 0))
+    with pytest.raises(Exception):
+        svb.delaunay_ordered(s, 0, np.zeros(len(s), np.int32) + len(s))  # not a permutation
+
+
 def test_host_delaunay_degenerate_inputs(svb, ref):
     # all collinear (one lattice column): Triangle emits no triangle
     col = np.array([(50, 5 * i, 3) for i in range(1, 30)], np.int32)
