@@ -115,3 +115,34 @@ def test_batch_with_a_textureless_frame(svb):
     finally:
         ctx.close()
         one.close()
+
+
+def test_batch_is_identical_across_stream_modes_lanes_and_vertex_order(svb, golden_meta, monkeypatch):
+    """The same frames through the multi-lane pipeline, the single-stream pipeline, six lanes, and with the device
+    vertex order switched off (complete host Delaunay path): bit-identical maps and point clouds."""
+    W, H, n = 640, 240, 44
+    pairs = [svb.synth_pair(300 + i, W, H, i & 1) for i in range(n)]
+    Ls = np.stack([p[0] for p in pairs])
+    Rs = np.stack([p[1] for p in pairs])
+    Q = np.array(golden_meta["Q"])
+
+    def run(single_stream, env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = svb.Context(svb.default_params(svb.PIPELINE), W, H, chunk=8)
+        for k in env:
+            monkeypatch.delenv(k)
+        try:
+            ctx.set_calibration(Q)
+            ctx.set_single_stream(single_stream)
+            ctx.batch_upload(Ls, Rs)
+            ctx.batch_run(n, svb.OUT_DISPARITY | svb.OUT_POINTS)
+            return [ctx.batch_disparity(i) for i in range(n)], [ctx.batch_points(i) for i in (0, 7, n - 1)]
+        finally:
+            ctx.close()
+
+    want = run(False, {})
+    for single, env in ((False, {}), (True, {}), (False, {"SVB_LANES": "6"}), (False, {"SVB_GPU_ORDER": "0"})):
+        got = run(single, env)
+        assert all(np.array_equal(a, b) for a, b in zip(got[0], want[0])), (single, env)
+        assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got[1], want[1])), (single, env)
