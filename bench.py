@@ -254,6 +254,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--single-stream", type=int, default=0)
     ap.add_argument("--delaunay-threads", type=int, default=0)
+    ap.add_argument("--pin", type=int, default=0, help="N > 1: give every rank its own slice of the host cores (sched_setaffinity); "
+                    "measured SLOWER on the 8-GPU box (105.8k vs 128.5k frames/s): the launcher and host-stage threads then fight the workers")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
 
@@ -280,6 +282,17 @@ def main():
         raise RuntimeError("bench.py: no CUDA device; the product has no CPU path")
     cores = host_cores()
     threads_per_rank = max(2, cores // max(world, 1))
+    pinned_to = None
+    if world > 1 and args.pin and hasattr(os, "sched_setaffinity"):
+        # one process per GPU: the Delaunay workers of a rank (created below, inheriting the mask) stay on their own cores
+        allowed = sorted(os.sched_getaffinity(0))
+        per = len(allowed) // world
+        if per >= 1:
+            pinned_to = allowed[local_rank * per:(local_rank + 1) * per]
+            try:
+                os.sched_setaffinity(0, pinned_to)
+            except OSError:
+                pinned_to = None
 
     p = svb.default_params(svb.PIPELINE)
     ctx = svb.Context(p, W, H, chunk=args.chunk, device=local_rank)
@@ -490,6 +503,7 @@ def main():
             "host_delaunay": {"ms_per_frame_cpu": delaunay_ms / (args.batch * args.steps), "wall_ms_per_step": delaunay_wall / args.steps,
                               "threads": min(threads_per_rank, 64) if args.delaunay_threads <= 0 else args.delaunay_threads},
             "wall_ms_per_step": wall_ms / args.steps,
+            "rank0_pinned_to_cores": pinned_to,
             "support_points_per_frame": st_last["support_points"] / max(1, st_last["frames"]),
             "valid_fraction_frame0": valid_frac,
             "input_generation_s": t_gen,
