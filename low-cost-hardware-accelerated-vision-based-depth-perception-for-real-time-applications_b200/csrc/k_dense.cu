@@ -200,7 +200,7 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
 }
 
 template <int RADIUS, bool COUNT>
-__global__ void __launch_bounds__(128) k_dense(const DenseArgs a) {
+__global__ void __launch_bounds__(128, 12) k_dense(const DenseArgs a) {
     if (blockIdx.z & 1)
         dense_body<1, RADIUS, COUNT>(a);
     else
