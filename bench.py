@@ -248,7 +248,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="frames per GPU per step (BASELINE configs[1]: 1024)")
     ap.add_argument("--chunk", type=int, default=32, help="frames per kernel launch")
-    ap.add_argument("--e2e-batch", type=int, default=256, help="frames per GPU per end-to-end step")
+    ap.add_argument("--e2e-batch", type=int, default=1024, help="frames per GPU per end-to-end step (the same batch as `value`)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the cpu_baseline leg")
     ap.add_argument("--ref-frames-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
