@@ -158,21 +158,24 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     const unsigned span = hi2 >= lo2 ? (unsigned)(hi2 - lo2) : 0u;
     const int lo3 = hi2 >= lo2 ? lo2 : 0x40000000;  // empty interval: nothing passes the unsigned range test
     if (RADIUS > 0) {
+        // the band's descriptors sit at consecutive addresses around pb = po -+ d_plane: loads with immediate offsets,
+        // predicated on the hypothesis being admissible (an inadmissible d may point anywhere; it is never dereferenced)
+        const uint4 *pb = desc_at(po, SIDE ? d_plane : -d_plane);
         uint4 ob[2 * RADIUS + 1];
         bool okb[2 * RADIUS + 1];
-        int dsb[2 * RADIUS + 1];
 #pragma unroll
         for (int k = -RADIUS; k <= RADIUS; k++) {
             const int d = (int)((unsigned)d_plane + (unsigned)k);
             okb[k + RADIUS] = (unsigned)(d - lo3) <= span;
-            dsb[k + RADIUS] = okb[k + RADIUS] ? d : 0;
-            ob[k + RADIUS] = __ldg(desc_at(po, SIDE ? dsb[k + RADIUS] : -dsb[k + RADIUS]));
+            ob[k + RADIUS] = make_uint4(0u, 0u, 0u, 0u);
+            if (okb[k + RADIUS]) ob[k + RADIUS] = __ldg(pb + (SIDE ? k : -k));
             if (COUNT) n_hyp += okb[k + RADIUS] ? 1u : 0u;
         }
 #pragma unroll
         for (int k = -RADIUS; k <= RADIUS; k++) {
             const unsigned seed = 16u + ((unsigned)a.P[k < 0 ? -k : k] & prior_on);
-            const unsigned cand = (sad16_acc(c, ob[k + RADIUS], seed) << 13) + (0x1000u + (unsigned)dsb[k + RADIUS]);
+            const unsigned dk = (unsigned)d_plane + (unsigned)(0x1000 + k);  // phase bit + d
+            const unsigned cand = (sad16_acc(c, ob[k + RADIUS], seed) << 13) + dk;
             key = min(key, okb[k + RADIUS] ? cand : 0xFFFFFFFFu);
         }
     } else {
