@@ -59,7 +59,7 @@ struct Dims {
 int make_dims(const svb_params &p, int W, int H, Dims *out);
 
 // plane of one triangle for one side, as consumed by the dense matcher
-struct PlaneRec {
+struct __align__(16) PlaneRec {
     float a, b, c;  // plane in the image being matched (t1* for left, t2* for right)
     int valid;      // fabs(a) < 0.7 && fabs(other side's a) < 0.7 (elas.cpp:910)
 };
