@@ -348,3 +348,24 @@ def test_device_vertex_order_feeds_the_same_triangulation(svb, ref):
         assert used and len(got) == 0
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("name", ["cones", "urban1"])
+def test_reference_profile_pairs(svb, ref, name):
+    """Two of the reference's own runProfiling inputs (datasets/profile, 900x750 and 1344x391) with runProfiling's
+    parameters (default preset, postprocess_only_left = false, stereo_vision.cu:727-730): both maps bit for bit."""
+    import os
+
+    from conftest import GOLDEN
+
+    z = np.load(os.path.join(GOLDEN, "profile_gray.npz"))
+    L, R = z[name + "_L"], z[name + "_R"]
+    p = svb.default_params(svb.ROBOTICS, postprocess_only_left=0)
+    ctx = svb.Context(p, L.shape[1], L.shape[0])
+    try:
+        D1, D2 = ctx.process(L, R)
+    finally:
+        ctx.close()
+    W1, W2, _ = ref.process(ref.params(0, postprocess_only_left=0), L, R)
+    assert np.array_equal(D1, W1) and np.array_equal(D2, W2)
+    assert (D1 >= 0).mean() > 0.5
