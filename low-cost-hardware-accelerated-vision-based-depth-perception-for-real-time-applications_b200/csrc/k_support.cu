@@ -166,8 +166,9 @@ __global__ void k_dcan_border(int16_t *__restrict__ dcan_raw, int cw, int ch) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// One CTA per frame runs the three in-place lattice filters with the reference's sequential
-// (column-major) semantics, then compacts.
+// The three in-place lattice filters with the reference's sequential (column-major) semantics, then the compaction.
+// k_incon_first_sweep (all cells of all frames at once) does the first and most expensive sweep of the first filter;
+// one CTA per frame (k_support_filter) continues from its flags.
 //
 // removeInconsistentSupportPoints (elas.cpp:152-176) is a sweep in which a cell sees the FINAL state of
 // the cells that precede it in column-major order and the ORIGINAL state of those that follow.  Let R* be
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(256) k_incon_first_sweep(const int16_t *__rest
 // SMEM = true: the lattice lives in shared memory (2 bytes per cell; every frame size up to about 1080p at step 5);
 // SMEM = false: it is worked on in place in the global dcan array (4K frames).
 template <bool SMEM>
-__global__ void __launch_bounds__(SF_THREADS) k_support_filter(const int16_t *__restrict__ dcan_raw_all, int16_t *__restrict__ dcan_all,
+__global__ void __launch_bounds__(SF_THREADS) k_support_filter(int16_t *__restrict__ dcan_all,
                                                                int32_t *__restrict__ support_all, int32_t *__restrict__ nsupport_all,
                                                                int32_t *__restrict__ h_support_all, int32_t *__restrict__ h_nsupport_all, int W,
                                                                int H, int cw, int ch, int step, int incon_window, int incon_threshold,
@@ -267,7 +268,6 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(const int16_t *__
     const int f = blockIdx.x;
     const int tid = threadIdx.x;
     const int cells = cw * ch;
-    const int16_t *raw = dcan_raw_all + (size_t)f * cells;
     int16_t *dcan = dcan_all + (size_t)f * cells;
     int16_t *work = SMEM ? s_lattice : dcan;
     int32_t *support = support_all + (size_t)f * maxS * 3;
@@ -278,7 +278,6 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(const int16_t *__
     __shared__ unsigned long long s_best[4];
 
     // dcan already holds the result of the first sweep (k_incon_first_sweep): raw values, SF_REMOVED where it struck
-    (void)raw;
     if (SMEM) {
         for (int i = tid; i < cells; i += SF_THREADS) work[i] = dcan[i];
         __syncthreads();
@@ -490,10 +489,10 @@ int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dca
                 return SVB_ERR_CUDA;
             }
         }
-        k_support_filter<true><<<nf, SF_THREADS, smem, s>>>(dcan_raw, dcan, support, nsupport, h_support, h_nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
+        k_support_filter<true><<<nf, SF_THREADS, smem, s>>>(dcan, support, nsupport, h_support, h_nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
                                                             p.incon_threshold, p.incon_min_support, p.add_corners, d.maxS);
     } else {
-        k_support_filter<false><<<nf, SF_THREADS, 0, s>>>(dcan_raw, dcan, support, nsupport, h_support, h_nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
+        k_support_filter<false><<<nf, SF_THREADS, 0, s>>>(dcan, support, nsupport, h_support, h_nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
                                                           p.incon_threshold, p.incon_min_support, p.add_corners, d.maxS);
     }
     SVB_LAUNCH_CHECK();
