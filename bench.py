@@ -248,7 +248,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="frames per GPU per step (BASELINE configs[1]: 1024)")
     ap.add_argument("--chunk", type=int, default=32, help="frames per kernel launch")
-    ap.add_argument("--e2e-batch", type=int, default=1024, help="frames per GPU per end-to-end step (the same batch as `value`)")
+    ap.add_argument("--e2e-batch", type=int, default=0, help="frames per GPU per end-to-end step; 0 = the whole batch at N = 1, 512 at N > 1 "
+                    "(page-locking 14 GB of result buffers per rank takes a while when 8 ranks do it at once)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the cpu_baseline leg")
     ap.add_argument("--ref-frames-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -372,7 +373,7 @@ def main():
     dense_hyp = sum_over_ranks(float(n_dense_hyp)) / (args.batch * world)
 
     # ---- end to end from pinned host buffers ----------------------------------------------------------------
-    nb = min(args.e2e_batch, args.batch)
+    nb = min(args.e2e_batch if args.e2e_batch > 0 else (args.batch if world == 1 else 512), args.batch)
     hl = svb.PinnedArray((nb, H, W), np.uint8)
     hr = svb.PinnedArray((nb, H, W), np.uint8)
     hD = svb.PinnedArray((nb, H, W), np.float32)
