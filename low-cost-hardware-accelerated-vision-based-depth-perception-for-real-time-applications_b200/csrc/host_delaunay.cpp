@@ -83,6 +83,23 @@ struct Mesh {
                (int64_t)clift * (adx * bdy - bdx * ady);
     }
     int64_t incircle(int a, int b, int c, int d) const { return incircle(P[a], P[b], P[c], P[d]); }
+    // The same determinant for one circle (a, b, c) and many query points: translated to a, expanded along the query's
+    // row; the three cofactors are computed once.  test(d) == incircle(a, b, c, d) exactly (|cofactors| < 2^44, terms < 2^59).
+    struct Circle {
+        Pt a;
+        int64_t bx, by, cx, cy, k0, k1, k2;
+        // orientation part only: k2 = 2 x signed area of (a, b, c) = ccw(c, a, b)
+        Circle(Pt a_, Pt b, Pt c) : a(a_), bx(b.x - a_.x), by(b.y - a_.y), cx(c.x - a_.x), cy(c.y - a_.y), k0(0), k1(0) { k2 = bx * cy - by * cx; }
+        void finish() {  // the two cofactors that need the lifts
+            const int64_t bl = bx * bx + by * by, cl = cx * cx + cy * cy;
+            k0 = by * cl - bl * cy;
+            k1 = bx * cl - bl * cx;
+        }
+        int64_t test(Pt d) const {
+            const int64_t dx = d.x - a.x, dy = d.y - a.y;
+            return dy * k1 - dx * k0 - (dx * dx + dy * dy) * k2;  // = -det[b'; c'; d'] = det[a-d; b-d; c-d]
+        }
+    };
 
     void merge(int &farleft, int &innerleft, int &innerright, int &farright, int axis);
     void recurse(const int32_t *sorted, int count, int axis, int &farleft, int &farright);
@@ -159,8 +176,11 @@ void Mesh::merge(int &farleft, int &innerleft, int &innerright, int &farright, i
     int upperleft = apex(leftcand), upperright = apex(rightcand);
     Pt pll = P[lowerleft], plr = P[lowerright], pul = P[upperleft], pur = P[upperright];  // coordinates ride along
     while (true) {
-        const bool leftfinished = ccw(pul, pll, plr) <= 0;
-        const bool rightfinished = ccw(pur, pll, plr) <= 0;
+        // circles through the base edge and either candidate; their orientation term is the "finished" test
+        // (ccw(upper, lowerleft, lowerright) = 2 x area of (lowerleft, lowerright, upper), elas' triangle.cpp:5480-5483)
+        Circle cleft(pll, plr, pul), cright(pll, plr, pur);
+        const bool leftfinished = cleft.k2 <= 0;
+        const bool rightfinished = cright.k2 <= 0;
         if (leftfinished && rightfinished) {
             // top bounding record
             int top = make();
@@ -192,10 +212,11 @@ void Mesh::merge(int &farleft, int &innerleft, int &innerright, int &farright, i
             return;
         }
         if (!leftfinished) {
+            cleft.finish();  // used by the left deletion test and by the final choice
             // would deleting the left candidate edge expose a vertex that violates the Delaunay property?
             int next = sym(lprev(leftcand));
             int nextapex = apex(next);
-            while (nextapex >= 0 && incircle(pll, plr, pul, P[nextapex]) > 0) {
+            while (nextapex >= 0 && cleft.test(P[nextapex]) > 0) {
                 // edge flip: the left triangulation gains one bounding record
                 next = lnext(next);
                 const int topcasing = sym(next);
@@ -215,6 +236,8 @@ void Mesh::merge(int &farleft, int &innerleft, int &innerright, int &farright, i
                 setapex(next, nextapex);
                 upperleft = nextapex;
                 pul = P[nextapex];
+                cleft = Circle(pll, plr, pul);
+                cleft.finish();
                 next = sidecasing;
                 nextapex = apex(next);
             }
@@ -222,7 +245,8 @@ void Mesh::merge(int &farleft, int &innerleft, int &innerright, int &farright, i
         if (!rightfinished) {
             int next = sym(lnext(rightcand));
             int nextapex = apex(next);
-            while (nextapex >= 0 && incircle(pll, plr, pur, P[nextapex]) > 0) {
+            cright.finish();
+            while (nextapex >= 0 && cright.test(P[nextapex]) > 0) {
                 next = lprev(next);
                 const int topcasing = sym(next);
                 next = lprev(next);
@@ -241,11 +265,14 @@ void Mesh::merge(int &farleft, int &innerleft, int &innerright, int &farright, i
                 setapex(next, nextapex);
                 upperright = nextapex;
                 pur = P[nextapex];
+                cright = Circle(pll, plr, pur);
+                cright.finish();
                 next = sidecasing;
                 nextapex = apex(next);
             }
         }
-        if (leftfinished || (!rightfinished && incircle(pul, pll, plr, pur) > 0)) {
+        // incircle(pul, pll, plr, pur): the same circle as `cleft` (a cyclic shift of the rows leaves the determinant alone)
+        if (leftfinished || (!rightfinished && cleft.test(pur) > 0)) {
             // new edge lowerleft -- upperright
             bond(base, rightcand);
             base = lprev(rightcand);
