@@ -39,6 +39,10 @@ W, H = 1242, 375
 N = W * H
 METRIC = "frames/s at 1242x375 (disparity + point cloud)"
 UNIT = "frames/s"
+# config.workload is the same string in both arms (--impl b200 / --impl reference): it names the workload, everything that differs
+# between the arms (batch per step, sample size) sits in the other config keys
+WORKLOAD = ("synthetic KITTI-shape 1242x375 stereo pairs (BASELINE configs[1]), pipeline preset (MIDDLEBURY + postprocess_only_left + "
+            "filter_adaptive_mean), disparity + point cloud")
 
 # Q / XR / XT of data/calibration/kitti_2011_09_26.yml at 1242x375 (tests/golden/golden_meta.json, cv2.stereoRectify)
 Q_KITTI = [[1.0, 0.0, 0.0, -738.7995529174805], [0.0, 1.0, 0.0, -254.75721931457520], [0.0, 0.0, 0.0, 1027.8551581758902],
@@ -49,6 +53,15 @@ def load_pkg():
     from __graft_entry__ import load_package
 
     return load_package().binding
+
+
+def synth_lib():
+    """The synthetic-input generator as its own tiny host library (csrc/synth.cpp alone): the CPU legs generate their inputs
+    with it, so a process that times the reference never maps the product's libelas_b200.so."""
+    import ctypes as C
+    import glob
+
+    return C.CDLL(glob.glob(os.path.join(ROOT, "low-cost*", "lib", "libsvb_synth.so"))[0])
 
 
 # ---- algorithmic HBM bytes per frame of each stage (DESIGN.md "Kernels and rooflines"; SURVEY.md 8d) ---------------
@@ -130,7 +143,7 @@ def _cpu_worker(args):
     from oracle.ref import RefElas
     import parity
 
-    lib = C.CDLL([p for p in __import__("glob").glob(os.path.join(ROOT, "low-cost*", "lib", "libelas_b200.so"))][0])
+    lib = synth_lib()
     ref = RefElas(fast=fast)
     p = ref.pipeline_params()
     L = np.zeros((H, W), np.uint8)
@@ -168,7 +181,7 @@ def cpu_single_process(n_frames, omp):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import parity
 
-    lib = C.CDLL([p for p in __import__("glob").glob(os.path.join(ROOT, "low-cost*", "lib", "libelas_b200.so"))][0])
+    lib = synth_lib()
     try:
         ref = RefElas(fast=True, omp=omp)
     except (FileNotFoundError, OSError):
@@ -214,8 +227,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 SAD + f32 filters + f64 reprojection",
         "data": "synthetic",
-        "config": {"workload": "synthetic KITTI-shape 1242x375 stereo pairs, pipeline preset (MIDDLEBURY + postprocess_only_left + "
-                               "filter_adaptive_mean), disparity + point cloud; bounded sample: " + sample},
+        "config": {"workload": WORKLOAD, "frames_per_step": cores * per_core, "bounded_sample": sample},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference",
                          "sample": sample + "; oracle/_ref/libelas_ref_fast.so = reference serial ELAS with the reference Makefile's "
                                             "flags (-O2 -ffast-math), one process per core, + numpy projectParallel"},
@@ -248,10 +260,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="frames per GPU per step (BASELINE configs[1]: 1024)")
     ap.add_argument("--chunk", type=int, default=32, help="frames per kernel launch")
-    ap.add_argument("--e2e-batch", type=int, default=0, help="frames per GPU per end-to-end step; 0 = the whole batch at N = 1, 512 at N > 1 "
-                    "(page-locking 14 GB of result buffers per rank takes a while when 8 ranks do it at once)")
+    ap.add_argument("--e2e-batch", type=int, default=512, help="frames per GPU per end-to-end step, the same at every N (page-locking "
+                    "14 GB of result buffers per rank for 1024 frames takes a while when 8 ranks do it at once)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the cpu_baseline leg")
-    ap.add_argument("--ref-frames-per-core", type=int, default=2)
+    ap.add_argument("--ref-frames-per-core", type=int, default=8, help="--impl reference: frames per host core and step (about 0.35 s each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--single-stream", type=int, default=0)
     ap.add_argument("--delaunay-threads", type=int, default=0)
@@ -373,7 +385,7 @@ def main():
     dense_hyp = sum_over_ranks(float(n_dense_hyp)) / (args.batch * world)
 
     # ---- end to end from pinned host buffers ----------------------------------------------------------------
-    nb = min(args.e2e_batch if args.e2e_batch > 0 else (args.batch if world == 1 else 512), args.batch)
+    nb = min(args.e2e_batch if args.e2e_batch > 0 else args.batch, args.batch)
     hl = svb.PinnedArray((nb, H, W), np.uint8)
     hr = svb.PinnedArray((nb, H, W), np.uint8)
     hD = svb.PinnedArray((nb, H, W), np.float32)
@@ -480,8 +492,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int32 SAD + f32 filters + f64 reprojection", "data": "synthetic",
-            "config": {"workload": "synthetic KITTI-shape 1242x375 stereo pairs, batch of %d frames per GPU (BASELINE configs[1]), pipeline "
-                                   "preset (MIDDLEBURY + postprocess_only_left + filter_adaptive_mean), disparity + point cloud" % args.batch,
+            "config": {"workload": WORKLOAD,
                        "frames_per_gpu": args.batch, "frames_per_launch": args.chunk, "lanes": int(os.environ.get("SVB_LANES", "4")), "single_stream": bool(args.single_stream),
                        "l2": "inputs larger than L2 (%.0f MB of images, %.0f MB of descriptors per step)" % (2 * N * args.batch / 1e6,
                                                                                                             32 * N * args.batch / 1e6),

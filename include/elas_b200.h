@@ -161,6 +161,11 @@ int svb_batch_upload(svb_context *ctx, const uint8_t *left, const uint8_t *right
 /* run the whole path on the resident inputs; results stay resident.  flags: SVB_OUT_* */
 enum svb_out_flags { SVB_OUT_DISPARITY = 1, SVB_OUT_POINTS = 2 };
 int svb_batch_run(svb_context *ctx, int n_frames, int flags);
+/* Per-frame status of the last batch call: nsupport_out[f] = support points of frame f.  A frame with fewer than 3 has no
+ * triangulation ("ERROR: Need at least 3 support points!", elas.cpp:64-69): its batch outputs are what generatePointCloud
+ * delivers in that case -- disparity 0 everywhere (the driver's maps are zero-initialised, stereo_vision.cu:311-312) and
+ * the point cloud of that map -- and it is counted in svb_stats::frames_failed. */
+int svb_batch_frame_support(svb_context *ctx, int32_t *nsupport_out, int n_frames);
 int svb_batch_download_disparity(svb_context *ctx, int frame, float *D1_out);
 int svb_batch_download_points(svb_context *ctx, int frame, double *points_out);
 /* end to end from pinned or pageable HOST buffers: H2D inputs, run, D2H outputs, all inside */

@@ -134,6 +134,7 @@ def load():
         "svb_set_calibration": [vp, vp, vp, vp],
         "svb_batch_upload": [vp, vp, vp, C.c_int],
         "svb_batch_run": [vp, C.c_int, C.c_int],
+        "svb_batch_frame_support": [vp, vp, C.c_int],
         "svb_batch_download_disparity": [vp, C.c_int, vp],
         "svb_batch_download_points": [vp, C.c_int, vp],
         "svb_batch_run_host": [vp, vp, vp, C.c_int, C.c_int, vp, vp],
@@ -583,6 +584,12 @@ class Context:
     def batch_run_host(self, left, right, flags=OUT_POINTS, D1_out=None, points_out=None):
         n = left.shape[0]
         self._chk(self.lib.svb_batch_run_host(self.h, _ptr(left), _ptr(right), n, flags, _ptr(D1_out), _ptr(points_out)))
+
+    def batch_frame_support(self, n):
+        """Support points of every frame of the last batch call (< 3: the frame failed and its disparity is 0 everywhere)."""
+        out = np.zeros(n, np.int32)
+        self._chk(self.lib.svb_batch_frame_support(self.h, _ptr(out), n))
+        return out
 
     def batch_disparity(self, frame):
         out = np.zeros((self.Dh, self.Dw), np.float32)

@@ -295,6 +295,10 @@ int main(int argc, const char **argv) {
     const int PW = W * o.extrapolate, PH = H * o.extrapolate;
     const size_t PN = (size_t)PW * PH;
     double *points = (double *)svb_host_alloc(PN * 24);
+    if (!points) {
+        fprintf(stderr, "%s\n", svb_last_error());
+        return 1;
+    }
     std::vector<uint8_t> left, right, left_in, right_in, dmap(N), dmap_big, color_big;
     if (o.extrapolate != 1) {
         dmap_big.resize(PN);

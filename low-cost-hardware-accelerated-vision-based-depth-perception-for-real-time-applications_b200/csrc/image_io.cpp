@@ -1,5 +1,7 @@
 #include "image_io.h"
 
+#include <exception>
+
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -62,6 +64,10 @@ bool read_png(const std::string &path, ImageU8 *out, std::string *err) {
         }
         const uint8_t *body = &file[pos + 8];
         if (!memcmp(type, "IHDR", 4) && len >= 13) {
+            if (W != 0) {
+                *err = path + ": duplicate IHDR chunk";
+                return false;
+            }
             W = be32(body);
             H = be32(body + 4);
             depth = body[8];
@@ -76,8 +82,8 @@ bool read_png(const std::string &path, ImageU8 *out, std::string *err) {
         }
         pos += 12 + (size_t)len;
     }
-    if (W == 0 || H == 0 || W > 65535 || H > 65535) {
-        *err = path + ": bad IHDR";
+    if (W == 0 || H == 0 || W > 16384 || H > 16384) {
+        *err = path + ": bad IHDR (sides of 1 .. 16384 pixels are accepted)";
         return false;
     }
     if (interlace != 0 || !(depth == 8 || depth == 16) || !(ctype == 0 || ctype == 2 || ctype == 3 || ctype == 4 || ctype == 6) ||
@@ -89,6 +95,12 @@ bool read_png(const std::string &path, ImageU8 *out, std::string *err) {
     const int bps = depth / 8;
     const size_t bpp = (size_t)samples * bps;   // bytes per pixel in the stream
     const size_t stride = (size_t)W * bpp;       // bytes per scanline without the filter byte
+    // deflate expands by at most ~1032x: a header that promises more than the IDAT payload can hold is rejected BEFORE anything
+    // of that size is allocated (a crafted 100-byte file must not ask for gigabytes)
+    if ((stride + 1) * (size_t)H > idat.size() * 1032 + 1024) {
+        *err = path + ": IDAT payload too small for the image size in IHDR";
+        return false;
+    }
     std::vector<uint8_t> raw((stride + 1) * H);
     uLongf raw_len = (uLongf)raw.size();
     const int zr = uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size());
@@ -217,7 +229,14 @@ extern "C" int svb_image_read(const char *path, uint8_t *out, int64_t capacity, 
     std::string err;
     const size_t n = strlen(path);
     const bool pgm = n > 4 && (!strcmp(path + n - 4, ".pgm") || !strcmp(path + n - 4, ".PGM"));
-    if (!(pgm ? svb::read_pgm(path, &im, &err) : svb::read_png(path, &im, &err))) {
+    bool ok = false;
+    try {  // no exception may cross the C boundary (std::bad_alloc on a huge image, ...)
+        ok = pgm ? svb::read_pgm(path, &im, &err) : svb::read_png(path, &im, &err);
+    } catch (const std::exception &e) {
+        err = std::string(path) + ": " + e.what();
+        ok = false;
+    }
+    if (!ok) {
         svb::set_error("%s", err.c_str());
         return SVB_ERR_ARG;
     }

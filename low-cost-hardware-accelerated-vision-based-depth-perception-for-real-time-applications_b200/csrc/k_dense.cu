@@ -30,6 +30,7 @@ struct DenseArgs {
     int Dw, DN, shift;  // disparity map width / size and log2 of the pixel step (1 with subsampling: map pixel (x,y) = image (2x,2y))
     unsigned grid_magic;  // ceil(2^32 / grid_size)
     int P[8];
+    unsigned bias;  // Dims::cost_bias: keeps SAD + P >= 0 in the unsigned key
     unsigned long long *evals;  // COUNT variant only: number of evaluated hypotheses (elas.cpp:759-793)
 };
 
@@ -146,8 +147,8 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
                 const int d1 = bit1 ? (w << 5) + (31 - __clz(bit1)) : d0;
                 const uint4 o0 = __ldg(desc_at(po, SIDE ? d0 : -d0));
                 const uint4 o1 = __ldg(desc_at(po, SIDE ? d1 : -d1));
-                const unsigned cand0 = (sad16_acc(c, o0, 16u) << 13) + (unsigned)d0;
-                const unsigned cand1 = (sad16_acc(c, o1, 16u) << 13) + (unsigned)d1;
+                const unsigned cand0 = (sad16_acc(c, o0, a.bias) << 13) + (unsigned)d0;
+                const unsigned cand1 = (sad16_acc(c, o1, a.bias) << 13) + (unsigned)d1;
                 key = min(key, (mine & bit0) ? cand0 : 0xFFFFFFFFu);
                 key = min(key, (mine & bit1) ? cand1 : 0xFFFFFFFFu);
             }
@@ -173,7 +174,7 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
         }
 #pragma unroll
         for (int k = -RADIUS; k <= RADIUS; k++) {
-            const unsigned seed = 16u + ((unsigned)a.P[k < 0 ? -k : k] & prior_on);
+            const unsigned seed = a.bias + ((unsigned)a.P[k < 0 ? -k : k] & prior_on);
             const unsigned dk = (unsigned)d_plane + (unsigned)(0x1000 + k);  // phase bit + d
             const unsigned cand = (sad16_acc(c, ob[k + RADIUS], seed) << 13) + dk;
             key = min(key, okb[k + RADIUS] ? cand : 0xFFFFFFFFu);
@@ -185,7 +186,7 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
             const bool ok = (unsigned)(d - lo3) <= span;
             if (COUNT) n_hyp += ok ? 1u : 0u;
             const int ds = ok ? d : 0;
-            const unsigned seed = 16u + ((unsigned)a.P[k < 0 ? -k : k] & prior_on);
+            const unsigned seed = a.bias + ((unsigned)a.P[k < 0 ? -k : k] & prior_on);
             const unsigned cost = sad16_acc(c, __ldg(desc_at(po, SIDE ? ds : -ds)), seed);
             const unsigned cand = (cost << 13) + (0x1000u + (unsigned)ds);
             key = min(key, ok ? cand : 0xFFFFFFFFu);
@@ -245,6 +246,7 @@ int launch_dense_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, 
     a.match_texture = p.match_texture;
     a.plane_radius = d.plane_radius;
     for (int i = 0; i < 8; i++) a.P[i] = d.P[i];
+    a.bias = (unsigned)d.cost_bias;
     a.row0 = row0;
     a.Dw = d.Dw;
     a.DN = d.DN;

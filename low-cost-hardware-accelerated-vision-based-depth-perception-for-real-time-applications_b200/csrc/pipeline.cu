@@ -40,8 +40,10 @@ void set_error(const char *fmt, ...) {
 int make_dims(const svb_params &p, int W, int H, Dims *out) {
     Dims d;
     memset(&d, 0, sizeof(d));
-    if (W < 16 || H < 16 || W > 16384 || H > 16384) {
-        set_error("unsupported image size %dx%d", W, H);
+    // 8192: coordinate range of the device vertex order (k_order.cu) and of the host stage's radix sort (host_delaunay.cpp), and
+    // every shared-memory line buffer of the post filters fits (4 rows x 8192 px x 4 B)
+    if (W < 16 || H < 16 || W > 8192 || H > 8192) {
+        set_error("unsupported image size %dx%d (16 .. 8192 per side)", W, H);
         return SVB_ERR_ARG;
     }
     if (p.disp_max < 0 || p.disp_max > 4095 || p.grid_size < 1 || p.candidate_stepsize < 1) {
@@ -77,6 +79,19 @@ int make_dims(const svb_params &p, int W, int H, Dims *out) {
     }
     for (int delta = 0; delta < 8; delta++)
         d.P[delta] = (int32_t)((-log(p.gamma + exp(-delta * delta / two_sigma_squared)) + log(p.gamma)) / p.beta);
+    // The dense matcher packs (cost + bias) << 13 | phase | d into one unsigned key (k_dense.cu); cost = SAD + P[.] is signed in the
+    // reference (elas.cpp:672-684) and P <= 0 grows with 1 / beta, so the bias follows the table instead of assuming the presets.
+    int minP = 0, maxP = 0;
+    for (int delta = 0; delta <= d.plane_radius; delta++) {
+        minP = d.P[delta] < minP ? d.P[delta] : minP;
+        maxP = d.P[delta] > maxP ? d.P[delta] : maxP;
+    }
+    d.cost_bias = minP < -16 ? -minP : 16;
+    if ((long long)4080 + maxP + d.cost_bias >= (1 << 19) || minP < -(1 << 18)) {
+        set_error("prior table out of range for the packed matching key (P in [%d, %d]; gamma=%g beta=%g sigma=%g)", minP, maxP, p.gamma, p.beta,
+                  p.sigma);
+        return SVB_ERR_UNSUPPORTED;
+    }
     *out = d;
     return SVB_OK;
 }
@@ -130,11 +145,11 @@ int lane_create(svb_context *c, Lane &L) {
             SVB_CUDA(cudaMemset(L.desc_base[s], 0, C * N * 16 + 2 * pad));
             L.desc[s] = L.desc_base[s] + pad;
         }
-        SVB_TRY(dev_alloc(&L.tri[s], C * d.maxT * 3));
+        SVB_TRY(dev_alloc(&L.tri[s], C * (d.maxT + 8) * 3));  // + 8: stage_host() reserves 2 n + 8 triangles per frame
         SVB_TRY(dev_alloc(&L.rec[s], C * d.maxT));
         SVB_TRY(dev_alloc(&L.grid[s], C * d.gw * d.gh * d.gwords));
         SVB_TRY(dev_alloc(&L.owner[s], C * N));
-        SVB_TRY(host_alloc(&L.h_tri[s], C * d.maxT * 3));
+        SVB_TRY(host_alloc(&L.h_tri[s], C * (d.maxT + 8) * 3));
     }
     SVB_TRY(dev_alloc(&L.dcan_raw, C * d.cw * d.ch));
     SVB_TRY(dev_alloc(&L.dcan, C * d.cw * d.ch + 2));  // + 2: the filters set flag bits with 32-bit atomics on the word holding a cell
@@ -300,8 +315,8 @@ int svb::stage_host(svb_context *c, Lane &L, int nf) {
             off += cap;
         }
         h_trioff[nf] = off;  // total (h_ntri holds 3*chunk ints + slack, h_trioff[chunk] is the slack slot)
-        if ((size_t)off > (size_t)c->chunk * d.maxT) {
-            set_error("triangle lists do not fit the arena (%d > %zu)", off, (size_t)c->chunk * d.maxT);
+        if ((size_t)off > (size_t)c->chunk * (d.maxT + 8)) {
+            set_error("triangle lists do not fit the arena (%d > %zu)", off, (size_t)c->chunk * (d.maxT + 8));
             return SVB_ERR_ARG;
         }
     }
@@ -334,6 +349,7 @@ int svb::stage_host(svb_context *c, Lane &L, int nf) {
         c->stats.support_points += L.h_nsupport[f];
         c->stats.triangles += L.h_ntri[2 * f] + L.h_ntri[2 * f + 1];
         if (L.h_nsupport[f] < 3) c->stats.frames_failed++;
+        if (L.first_frame >= 0 && (size_t)(L.first_frame + f) < c->frame_nsupport.size()) c->frame_nsupport[L.first_frame + f] = L.h_nsupport[f];
     }
     return SVB_OK;
 }
@@ -409,6 +425,11 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, 
         }
     }
     SVB_TRY(T.mark(ST_REPROJECT));
+    // Batch outputs of a frame with fewer than 3 support points: Elas::process returns without touching D (elas.cpp:64-69) and the
+    // driver's maps start as zeros (stereo_vision.cu:311-312), so the frame's disparity is 0 everywhere, like svb_point_cloud_bgra
+    if (out_D1 || out_points)
+        for (int f = 0; f < nf; f++)
+            if (L.h_nsupport[f] < 3) SVB_CUDA(cudaMemsetAsync(D1 + (size_t)f * DN, 0, DN * 4, L.stream));
     if (out_D1) SVB_CUDA(cudaMemcpyAsync(out_D1, D1, DN * 4 * nf, cudaMemcpyDeviceToDevice, L.stream));
     if (out_points) SVB_TRY(launch_reproject(d, c->calib, D1, L.dmap, out_points, nf, L.stream));
     SVB_TRY(T.mark(ST_COUNT));
@@ -506,9 +527,16 @@ svb_context *svb_create(const svb_params *params, int width, int height, int chu
         set_error("no CUDA device available (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
         return nullptr;
     }
-    if (device < 0) {
-        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
-    }
+    int caller_device = -1;
+    if (cudaGetDevice(&caller_device) != cudaSuccess) caller_device = -1;
+    if (device < 0) device = caller_device >= 0 ? caller_device : 0;
+    // the caller's current device is restored on every way out (RAII)
+    struct RestoreDevice {
+        int dev;
+        ~RestoreDevice() {
+            if (dev >= 0) cudaSetDevice(dev);
+        }
+    } restore{caller_device};
     if (device >= ndev) {
         set_error("device %d out of range (%d devices)", device, ndev);
         return nullptr;
@@ -576,6 +604,7 @@ void svb_destroy(svb_context *c) {
 
 int svb_set_mean_mode(svb_context *c, int mode) {
     if (!c || (mode != 0 && mode != 1)) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
     c->mean_mode = mode;
     return SVB_OK;
 }
@@ -637,6 +666,7 @@ int svb_get_eval_counts(svb_context *c, uint64_t *support_hypotheses, uint64_t *
 
 int svb_set_tap_mode(svb_context *c, int on) {
     if (!c) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
     SVB_CUDA(cudaSetDevice(c->device));
     c->tap_mode = on != 0;
     if (c->tap_mode && !c->planes_ref[0])
@@ -646,6 +676,7 @@ int svb_set_tap_mode(svb_context *c, int on) {
 
 int svb_inject_triangles(svb_context *c, int side, const int32_t *tri, int n) {
     if (!c || side < 0 || side > 1) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
     if (n < 0 || !tri) {
         c->inject[side] = false;
         c->inject_tri[side].clear();
@@ -658,6 +689,7 @@ int svb_inject_triangles(svb_context *c, int side, const int32_t *tri, int n) {
 
 int svb_set_calibration(svb_context *c, const double *Q16, const double *XR9, const double *XT3) {
     if (!c || !Q16) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
     memcpy(c->calib.Q, Q16, sizeof(double) * 16);
     if (XR9)
         memcpy(c->calib.XR, XR9, sizeof(double) * 9);
@@ -736,6 +768,7 @@ int svb_process(svb_context *c, const uint8_t *I1, const uint8_t *I2, int stride
 
 int64_t svb_tap(svb_context *c, const char *name, void *dst, int64_t cap) {
     if (!c || !name || !dst) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
     for (auto &t : c->taps)
         if (t.name == name) {
             if ((int64_t)t.bytes > cap) {
@@ -1039,6 +1072,7 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
         return SVB_ERR_ARG;
     }
     stats_reset(c);
+    c->frame_nsupport.assign((size_t)n_frames, 0);
     if (want_D) SVB_TRY(ensure_store((void **)&c->out_D1, &c->out_D1_frames, n_frames, DN * 4));
     if (want_P) SVB_TRY(ensure_store((void **)&c->out_points, &c->out_points_frames, n_frames, N * 24));
     const int nchunks = (n_frames + C - 1) / C;
@@ -1056,6 +1090,7 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
         Lane &L = c->lanes[k % LANES];
         const int nf = frames_of(k);
         const size_t off = (size_t)k * C * N;
+        L.first_frame = k * C;
         if (from_host) {
             SVB_CUDA(cudaMemcpyAsync(L.img[0], h_left + off, nf * N, cudaMemcpyHostToDevice, L.stream));
             SVB_CUDA(cudaMemcpyAsync(L.img[1], h_right + off, nf * N, cudaMemcpyHostToDevice, L.stream));
@@ -1135,6 +1170,7 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
         hs.cv.notify_all();
     }
     host_thread.join();
+    for (int l = 0; l < LANES; l++) c->lanes[l].first_frame = -1;
     if (drive_rc != SVB_OK) {
         cudaDeviceSynchronize();
         cudaEventDestroy(ev0);
@@ -1177,15 +1213,30 @@ int svb_batch_run_host(svb_context *c, const uint8_t *left, const uint8_t *right
     return batch_drive(c, n_frames, flags, left, right, D1_out, points_out);
 }
 
+int svb_batch_frame_support(svb_context *c, int32_t *nsupport_out, int n_frames) {
+    if (!c || !nsupport_out || n_frames < 0) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if ((size_t)n_frames > c->frame_nsupport.size()) {
+        set_error("svb_batch_frame_support: the last batch call had %zu frames", c->frame_nsupport.size());
+        return SVB_ERR_ARG;
+    }
+    memcpy(nsupport_out, c->frame_nsupport.data(), sizeof(int32_t) * (size_t)n_frames);
+    return SVB_OK;
+}
+
 int svb_batch_download_disparity(svb_context *c, int frame, float *out) {
-    if (!c || !out || frame < 0 || (size_t)frame >= c->out_D1_frames || !c->out_D1) return SVB_ERR_ARG;
+    if (!c || !out || frame < 0) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if ((size_t)frame >= c->out_D1_frames || !c->out_D1) return SVB_ERR_ARG;
     SVB_CUDA(cudaSetDevice(c->device));
     SVB_CUDA(cudaMemcpy(out, c->out_D1 + (size_t)frame * c->d.DN, (size_t)c->d.DN * 4, cudaMemcpyDeviceToHost));
     return SVB_OK;
 }
 
 int svb_batch_download_points(svb_context *c, int frame, double *out) {
-    if (!c || !out || frame < 0 || (size_t)frame >= c->out_points_frames || !c->out_points) return SVB_ERR_ARG;
+    if (!c || !out || frame < 0) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if ((size_t)frame >= c->out_points_frames || !c->out_points) return SVB_ERR_ARG;
     SVB_CUDA(cudaSetDevice(c->device));
     SVB_CUDA(cudaMemcpy(out, c->out_points + (size_t)frame * c->d.N * 3, (size_t)c->d.N * 24, cudaMemcpyDeviceToHost));
     return SVB_OK;
@@ -1265,6 +1316,7 @@ int svb_stage_bgra_to_gray(svb_context *c, const uint8_t *bgra, uint8_t *gray_ou
 
 int svb_get_stats(svb_context *c, svb_stats *out) {
     if (!c || !out) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
     *out = c->stats;
     return SVB_OK;
 }

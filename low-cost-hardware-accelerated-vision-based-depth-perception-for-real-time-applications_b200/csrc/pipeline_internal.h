@@ -39,6 +39,7 @@ struct Lane {
     int32_t *h_support = nullptr, *h_nsupport = nullptr, *h_tri[2] = {nullptr, nullptr}, *h_ntri = nullptr;
     int32_t *h_order = nullptr;     // [chunk][2][maxS] recursion order of the Delaunay stage (k_order.cu), written by the device
     int32_t *h_order_ok = nullptr;  // [chunk][2] 1 = h_order is valid for that list
+    int first_frame = -1;           // batch paths: index of the chunk's first frame in the batch (per-frame status), else -1
 };
 
 // CUDA events bracketing every stage of one chunk (stage timing): [i] is recorded in front of stage i, [ST_COUNT] after
@@ -85,6 +86,7 @@ struct svb_context {
     size_t out_D1_frames = 0;
     double *out_points = nullptr;
     size_t out_points_frames = 0;
+    std::vector<int32_t> frame_nsupport;  // support points of every frame of the last batch call (< 3: the frame failed)
     // stats
     svb_stats stats;
     bool stage_timing = false;

@@ -51,6 +51,7 @@ struct Dims {
     int maxT;             // capacity of one triangle list (2*maxS is an upper bound for a planar triangulation)
     int plane_radius;     // elas.cpp:832
     int P[8];             // prior table P[|d - d_plane|] for deltas 0..plane_radius (elas.cpp:831)
+    int cost_bias;        // added to every matching cost so that SAD + P stays >= 0 in the unsigned packed key: max(16, -min P)
     // optional device counters (svb_set_eval_counting): [0] support-matching hypotheses (64-byte SADs), [1] dense-matching
     // hypotheses (16-byte SADs), counted the way the reference evaluates them; nullptr = the kernels without counting
     unsigned long long *evals;

@@ -29,4 +29,18 @@ g++ $FAST -fPIC -shared -DORACLE_REF_FLAGS="\"g++ $FAST\"" -include "$HERE/ref_p
 OMP="-O2 -std=c++17 -w -ffast-math -fopenmp"
 g++ $OMP -fPIC -shared -DORACLE_REF_OMP -DORACLE_REF_FLAGS="\"g++ $OMP\"" -include "$HERE/ref_prelude.h" -I"$REF/src" \
     "$HERE/ref_taps.cpp" $COMMON -o "$OUT/libelas_ref_omp.so" || echo "build_ref.sh: the OpenMP variant did not build (baseline skipped)" >&2
+# Row 19 (projectParallel): the reference's own CUDA kernel, cut out of its driver where it lies (the driver as a whole needs OpenCV /
+# popt / GL and does not compile here) and compiled with the reference Makefile's nvcc flags for sm_100a.  Runs on the GPU box only.
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+SV="$REF/src/parallel_includes/main/stereo_vision.cu"
+if [ -x "$NVCC" ] && [ -f "$SV" ]; then
+    awk '/^__global__ void projectParallel\(/{on=1} on{print} on&&/^}/{exit}' "$SV" > "$OUT/project_parallel_extract.cuh"
+    if [ "$(grep -c 'make_double3' "$OUT/project_parallel_extract.cuh")" = "1" ]; then
+        PFLAGS="-O2 -std=c++17 -w -gencode arch=compute_100a,code=sm_100a"
+        "$NVCC" $PFLAGS -DORACLE_REF_PROJECT_FLAGS="\"nvcc $PFLAGS\"" -shared -Xcompiler -fPIC -I"$OUT" "$HERE/ref_project.cu" \
+            -o "$OUT/libproject_ref.so" || echo "build_ref.sh: projectParallel did not build (row-19 reference oracle skipped)" >&2
+    else
+        echo "build_ref.sh: could not locate projectParallel in $SV" >&2
+    fi
+fi
 echo "built $OUT/libelas_ref.so $OUT/libelas_ref_fast.so $OUT/libelas_ref_omp.so"

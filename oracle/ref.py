@@ -232,3 +232,30 @@ class RefElas:
                     t["D%s%s" % (s, nm)] = cur
             t["D" + s] = cur
         return t
+
+
+class RefProject:
+    """TEST INFRASTRUCTURE ONLY: the reference's own `projectParallel` CUDA kernel (stereo_vision.cu:188-212), cut out of the
+    reference's driver and compiled by oracle/build_ref.sh into oracle/_ref/libproject_ref.so.  Needs a CUDA device (GPU box)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libproject_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " missing: run oracle/build_ref.sh where /root/reference and nvcc exist")
+        self.lib = C.CDLL(path)
+        self.lib.ref_project_flags.restype = C.c_char_p
+        self.flags = self.lib.ref_project_flags().decode()
+
+    def project(self, dmap, Q, XR, XT):
+        """dmap: u8 (H, W) -> (H*W, 3) float64, exactly what publishPointCloud copies back into `points`."""
+        dmap = np.ascontiguousarray(dmap, np.uint8)
+        H, W = dmap.shape
+        Q = np.ascontiguousarray(Q, np.float64).reshape(16)
+        XR = np.ascontiguousarray(XR, np.float64).reshape(9)
+        XT = np.ascontiguousarray(XT, np.float64).reshape(3)
+        pts = np.zeros((H * W, 3), np.float64)
+        rc = self.lib.ref_project_parallel(_p(dmap, C.c_uint8), _p(pts, C.c_double), H, W, _p(XT, C.c_double), _p(XR, C.c_double),
+                                           _p(Q, C.c_double))
+        if rc != 0:
+            raise RuntimeError("ref_project_parallel: cudaError %d" % rc)
+        return pts

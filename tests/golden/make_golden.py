@@ -2,7 +2,7 @@
 
 Inputs : datasets/kitti_mini frames (RGB PNG) -> gray exactly like the reference driver does it
          (sv.py:185-188 BGR->BGRA, stereo_vision.cu:346-347 BGRA->GRAY), via python cv2.
-Outputs: tests/golden/kitti_gray.npz     gray stereo pairs (uint8), frames 0 and 7
+Outputs: (tests/golden/kitti_gray.npz, the gray stereo pairs, is written by make_dataset_fixtures.py: all 21 pairs)
          tests/golden/kitti_golden.npz   outputs of oracle/_ref/libelas_ref.so (= the reference's serial ELAS,
                                          strict-IEEE build) for those pairs: support points, both triangle lists,
                                          the final left disparity (float16-exactness checked, else float32) and a
@@ -73,7 +73,6 @@ def main():
             gold[key + "_D1raw"] = t["D1raw"].astype(np.int16)  # integers, -1 or -10
             gold[key + "_D2raw"] = t["D2raw"].astype(np.int16)
             print(key, "support", len(t["support"]), "tri", len(t["tri1"]), len(t["tri2"]), "valid", int((t["D1"] >= 0).sum()))
-    np.savez_compressed(os.path.join(HERE, "kitti_gray.npz"), **gray)
     np.savez_compressed(os.path.join(HERE, "kitti_golden.npz"), **gold)
 
     # calibration -> Q exactly as findRectificationMap does it (stereo_vision.cu:447), scale_factor 1

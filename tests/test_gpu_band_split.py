@@ -23,6 +23,9 @@ def test_band_split_matches_reference_kitti(svb, kitti_gray, golden, n_bands):
         assert np.array_equal(D1, golden["pipeline_0_D1"])
         st = g.stats()
         assert st["bands"] == n_bands and st["support_points"] == len(golden["pipeline_0_support"]) and st["gpu_ms"] > 0
+        if n_bands > 1 and svb.device_count() > 1:
+            # distinct devices: the bands really live in different GPUs' memories and the copies cross NVLink
+            assert len(set(device_list(svb, n_bands))) == min(n_bands, svb.device_count()) and st["peer_links"] > 0
         if n_bands > 1:
             # halos: 2 images x 2 rows x 16 W bytes per band edge and side; lattice rows; both maps' band rows
             assert st["p2p_copies"] >= 4 * (n_bands - 1) + (n_bands - 1) + 2 * (n_bands - 1)

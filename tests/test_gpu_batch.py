@@ -146,3 +146,32 @@ def test_batch_is_identical_across_stream_modes_lanes_and_vertex_order(svb, gold
         got = run(single, env)
         assert all(np.array_equal(a, b) for a, b in zip(got[0], want[0])), (single, env)
         assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got[1], want[1])), (single, env)
+
+
+def test_batch_frame_without_support_points(svb):
+    """A frame that yields fewer than 3 support points (a blank pair under the ROBOTICS preset: no texture, no corners) inside a
+    batch: Elas::process would return without touching D (elas.cpp:64-69) and the driver's maps start as zeros, so the batch
+    delivers disparity 0 everywhere for THAT frame, reports it per frame, and the neighbours are untouched."""
+    W, H = 640, 240
+    n = 5
+    L, R = make_batch(svb, n, W, H)
+    L[2] = 90
+    R[2] = 90
+    p = svb.default_params(svb.ROBOTICS)
+    one = svb.Context(p, W, H, chunk=1)
+    ctx = svb.Context(p, W, H, chunk=2)
+    try:
+        ctx.batch_upload(L, R)
+        ctx.batch_run(n, svb.OUT_DISPARITY | svb.OUT_POINTS)
+        nsup = ctx.batch_frame_support(n)
+        assert nsup[2] < 3 and (np.delete(nsup, 2) >= 3).all()
+        assert ctx.stats()["frames_failed"] == 1
+        assert (ctx.batch_disparity(2) == 0).all()
+        pts = ctx.batch_points(2)
+        assert (pts[:, 2] == 0).all()  # default calibration Q = I: (x, y, d8 = 0)
+        for i in (0, 1, 3, 4):
+            D1, _ = one.process(L[i], R[i])
+            assert np.array_equal(ctx.batch_disparity(i), D1), i
+    finally:
+        ctx.close()
+        one.close()

@@ -299,6 +299,44 @@ def test_reproject_parity(svb, golden, golden_meta):
         ctx.close()
 
 
+def test_reproject_against_the_reference_kernel(svb, golden, golden_meta, kitti_gray):
+    """Row 19 pinned to the reference ITSELF: `projectParallel` (stereo_vision.cu:188-212), cut out of the reference's driver and
+    compiled by oracle/build_ref.sh (oracle/_ref/libproject_ref.so, reference Makefile flags = FMA contraction on), run on this
+    GPU.  Checked: (1) the product's fused u8 + reprojection kernel against it -- identical inf / NaN pattern, <= 1e-4 relative
+    (north_star; the two differ only by the reference's contracted multiply-adds, ~1e-13 near the principal point);
+    (2) the numpy restatement tests/parity.py::reproject_oracle, which the other tests use, against it as well."""
+    from oracle.ref import RefProject
+
+    rp = RefProject()
+    assert "nvcc" in rp.flags and "-O2" in rp.flags
+    Q = np.array(golden_meta["Q"])
+    Qg = Q.copy()
+    Qg[3, 0], Qg[3, 1], Qg[3, 3] = 1e-4, -3e-4, 0.37  # a general Q: w depends on x and y too
+    cases = [(golden["pipeline_0_D1"], Q, np.eye(3), np.zeros(3)),
+             (golden["pipeline_7_D1"], Q, np.array(golden_meta["XR"]), np.array(golden_meta["XT"])),
+             (golden["robotics_0_D1"], Q, np.array(golden_meta["XR"]), np.array(golden_meta["XT"])),  # invalid pixels: d8 = 0 -> w = 0
+             (golden["robotics_7_D1"], Qg, np.array(golden_meta["XR"]), np.array(golden_meta["XT"]))]
+    H, W = cases[0][0].shape
+    ctx = svb.Context(svb.default_params(svb.PIPELINE), W, H)
+    try:
+        worst = 0.0
+        for D, q, XR, XT in cases:
+            dm, pts = ctx.reproject(D, q, XR, XT)
+            dm_np, pts_np = parity.reproject_oracle(D, q, XR, XT)
+            assert np.array_equal(dm, dm_np)
+            want = rp.project(dm, q, XR, XT)  # the reference kernel on the product's u8 map (= cv convertTo of the float map)
+            for got, name in ((pts, "product"), (pts_np, "numpy restatement")):
+                assert np.array_equal(np.isnan(got), np.isnan(want)), name
+                assert np.array_equal(np.isinf(got), np.isinf(want)) and np.array_equal(np.signbit(got[np.isinf(got)]), np.signbit(want[np.isinf(want)])), name
+                fin = np.isfinite(want)
+                rel = np.abs(got[fin] - want[fin]) / np.maximum(np.abs(want[fin]), 1e-300)
+                assert rel.max() <= POINT_RTOL, (name, rel.max())
+                worst = max(worst, float(rel.max()))
+        print("worst relative difference to the reference kernel: %.3g" % worst)  # contraction differences only (~1e-13)
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("setting,support_m,dense_m", [("ROBOTICS", 4.84, 7.09), ("MIDDLEBURY", 5.89, 11.43)])
 def test_hypothesis_counters_match_instrumented_reference(svb, kitti_gray, setting, support_m, dense_m):
     """svb_set_eval_counting: the counters behind bench.py's pixel-disparity evals/s.  Known answers = the counts of an
@@ -350,10 +388,26 @@ def test_device_vertex_order_feeds_the_same_triangulation(svb, ref):
         ctx.close()
 
 
-@pytest.mark.parametrize("name", ["cones", "urban1"])
+def _sha(a):
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _digests():
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    return json.load(open(os.path.join(GOLDEN, "dataset_digests.json")))
+
+
+@pytest.mark.parametrize("name", ["cones", "aloe", "raindeer", "urban1", "urban2", "urban3", "urban4"])
 def test_reference_profile_pairs(svb, ref, name):
-    """Two of the reference's own runProfiling inputs (datasets/profile, 900x750 and 1344x391) with runProfiling's
-    parameters (default preset, postprocess_only_left = false, stereo_vision.cu:727-730): both maps bit for bit."""
+    """ALL SEVEN of the reference's own runProfiling inputs (datasets/profile: 900x750, 1282x1110, 1342x1110 -- the largest
+    inputs the reference ships -- and 4 x 1344x391) with runProfiling's parameters (default preset, postprocess_only_left =
+    false, stereo_vision.cu:727-730): both maps bit for bit against the live oracle AND against the committed digests."""
     import os
 
     from conftest import GOLDEN
@@ -364,8 +418,60 @@ def test_reference_profile_pairs(svb, ref, name):
     ctx = svb.Context(p, L.shape[1], L.shape[0])
     try:
         D1, D2 = ctx.process(L, R)
+        nsup = ctx.stats()["support_points"]
     finally:
         ctx.close()
     W1, W2, _ = ref.process(ref.params(0, postprocess_only_left=0), L, R)
     assert np.array_equal(D1, W1) and np.array_equal(D2, W2)
+    want = _digests()["profile_runprofiling"][name]
+    assert (nsup, _sha(D1), _sha(D2)) == (want["support"], want["D1"], want["D2"])
     assert (D1 >= 0).mean() > 0.5
+
+
+def test_kitti_mini_all_21_pairs(svb, ref, kitti_gray):
+    """Every stereo pair of datasets/kitti_mini (BASELINE configs[0]) through the frame-batch pipeline with the driver's preset:
+    disparity bit for bit against the live oracle and against the committed digests, support point counts included; the point
+    cloud of every frame against the numpy restatement of projectParallel."""
+    n = 21
+    L = np.stack([kitti_gray["L%d" % i] for i in range(n)])
+    R = np.stack([kitti_gray["R%d" % i] for i in range(n)])
+    H, W = L.shape[1:]
+    dig = _digests()["kitti_pipeline"]
+    ctx = svb.Context(svb.default_params(svb.PIPELINE), W, H, chunk=8)
+    try:
+        Q = np.array([[1.0, 0, 0, -738.7995529174805], [0, 1.0, 0, -254.7572193145752], [0, 0, 0, 1027.8551581758902], [0, 0, 1.8616160699568378, 0]])
+        ctx.set_calibration(Q)
+        ctx.batch_upload(L, R)
+        ctx.batch_run(n, svb.OUT_DISPARITY | svb.OUT_POINTS)
+        nsup = ctx.batch_frame_support(n)
+        for i in range(n):
+            D1 = ctx.batch_disparity(i)
+            W1, _, _ = ref.process(ref.pipeline_params(), L[i], R[i])
+            assert np.array_equal(D1, W1), "kitti pair %d" % i
+            assert (int(nsup[i]), _sha(D1), int((D1 >= 0).sum())) == (dig[str(i)]["support"], dig[str(i)]["D1"], dig[str(i)]["valid1"]), i
+            if i % 5 == 0:
+                _, pts_o = parity.reproject_oracle(D1, Q, np.eye(3), np.zeros(3))
+                pts = ctx.batch_points(i)
+                fin = np.isfinite(pts_o).all(1)
+                assert np.array_equal(np.isfinite(pts).all(1), fin)
+                assert (np.abs(pts[fin] - pts_o[fin]) / np.maximum(np.abs(pts_o[fin]), 1e-300)).max() <= POINT_RTOL
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("gamma,beta,sigma,sradius", [(1.0, 0.01, 1.0, 2.0), (0.5, 0.004, 1.5, 3.0), (15.0, 0.05, 0.8, 2.0)])
+def test_non_preset_prior_parameters(svb, ref, kitti_gray, gamma, beta, sigma, sradius):
+    """Elas::parameters is a public drop-in field: gamma / beta / sigma outside the two presets give prior tables far below the
+    presets' -14 (P[0] = log(gamma / (gamma + 1)) / beta: -69, -274, ...), which the packed matching key has to carry
+    (Dims::cost_bias).  Raw integer disparities and the final maps against the oracle."""
+    L, R = kitti_gray["L3"], kitti_gray["R3"]
+    over = dict(gamma=gamma, beta=beta, sigma=sigma, sradius=sradius)
+    p = svb.default_params(svb.ROBOTICS, **over)
+    p_ref = ref.params(0, **over)
+    ctx = svb.Context(p, L.shape[1], L.shape[0])
+    try:
+        res, t, _ = parity.staged_parity(ctx, ref, p_ref, L, R, inject=False)
+        assert_all_equal(res)
+        assert_float_bar(res)
+    finally:
+        ctx.close()

@@ -62,6 +62,31 @@ def test_survey_known_answers(golden):
     assert int((golden["pipeline_0_D1"] >= 0).sum()) == 465750
 
 
+def test_oracle_reproduces_dataset_digests(ref, kitti_gray):
+    """The oracle on ALL of the reference's own inputs -- the 21 pairs of datasets/kitti_mini (driver preset) and the 7 pairs of
+    datasets/profile (runProfiling's parameters, stereo_vision.cu:727-730) -- against the digests that
+    tests/golden/make_dataset_fixtures.py recorded from it (support points, triangles, valid pixels, sha256 of both maps)."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    dig = json.load(open(os.path.join(GOLDEN, "dataset_digests.json")))
+    assert ref.flags == dig["oracle_flags"]
+    for i in (0, 5, 13, 20):  # a spread of the kitti pairs here; the -m gpu tests run all 21 against the live oracle
+        D1, D2, _ = ref.process(ref.pipeline_params(), kitti_gray["L%d" % i], kitti_gray["R%d" % i])
+        want = dig["kitti_pipeline"][str(i)]
+        assert (sha(D1), sha(D2), int((D1 >= 0).sum())) == (want["D1"], want["D2"], want["valid1"]), "kitti pair %d" % i
+    z = np.load(os.path.join(GOLDEN, "profile_gray.npz"))
+    assert sorted(dig["profile_runprofiling"]) == sorted({k[:-2] for k in z.files})
+    for name in ("cones", "urban3"):
+        L, R = z[name + "_L"], z[name + "_R"]
+        assert list(L.shape) == dig["profile_runprofiling"][name]["shape"]
+        D1, D2, _ = ref.process(ref.params(0, postprocess_only_left=0), L, R)
+        want = dig["profile_runprofiling"][name]
+        assert (sha(D1), sha(D2), int((D1 >= 0).sum()), int((D2 >= 0).sum())) == (want["D1"], want["D2"], want["valid1"], want["valid2"]), name
+
+
 def test_oracle_prior_table(ref):
     """P[] of elas.cpp:831 as listed in SURVEY.md 8a row 11, restated in numpy."""
     for setting, want in ((0, [-14, -9, -2, 0]), (1, [-9, -5, -1, 0])):
