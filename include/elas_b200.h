@@ -128,8 +128,14 @@ int svb_stage_delaunay(const int32_t *support, int n, int right_image, int32_t *
  * (lexicographic (x, y) sort, then the alternating-axis median partition with subsets of <= 3 x-sorted; duplicate-free
  * input only), as csrc/k_order.cu computes it on the device. */
 int svb_stage_delaunay_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int32_t *tri, int cap, int *n_tri_out);
-/* The same stage as the pipeline runs it: vertex order (sort + alternating cuts) on the device, recursion on the host;
- * *used_device_order = 0 when the device flagged the list (duplicate coordinates, > 4096 points) and the host did it all. */
+/* The device's share of the stage restated on the host (tests; no GPU needed): the recursion levels from the leaves up to depth
+ * `host_levels` built level by level, every node independently, in 16-bit records -- what csrc/k_delaunay.cu does with one thread per
+ * node -- and the levels above by the host recursion (0: the device's work is the whole triangulation).  n <= 4096. */
+int svb_stage_delaunay_levels(const int32_t *support, int n, int right_image, const int32_t *order, int host_levels, int32_t *tri, int cap,
+                              int *n_tri_out);
+/* The same stage as the pipeline runs it: vertex order (sort + alternating cuts) and the divide-and-conquer on the device
+ * (*used_device_order = 2), or -- SVB_DELAUNAY_DEVICE=0 -- the recursion on the host (1); 0 when the device flagged the list
+ * (duplicate coordinates, > 4096 points) and the host did it all. */
 int svb_stage_delaunay_pipeline(svb_context *ctx, const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out,
                                 int *used_device_order);
 int svb_stage_planes(svb_context *ctx, const int32_t *support, int n, const int32_t *tri, int m, float *planes);
@@ -159,7 +165,10 @@ int svb_set_calibration(svb_context *ctx, const double *Q16, const double *XR9, 
 /* copy n frames (tight W*H u8 each) into the device-resident input store */
 int svb_batch_upload(svb_context *ctx, const uint8_t *left, const uint8_t *right, int n_frames);
 /* run the whole path on the resident inputs; results stay resident.  flags: SVB_OUT_* */
-enum svb_out_flags { SVB_OUT_DISPARITY = 1, SVB_OUT_POINTS = 2 };
+/* SVB_OUT_POINTS: the drop-in point cloud (u8 disparity x4 as in generateDisparityMap, stereo_vision.cu:324, clips at 63.75 px);
+ * SVB_OUT_POINTS_FLOATDISP (opt-in, instead of SVB_OUT_POINTS): the filtered FLOAT disparity enters Q, no quantisation and no clip --
+ * what a 4K / disparity-range-512 caller needs; invalid pixels project like disparity 0. */
+enum svb_out_flags { SVB_OUT_DISPARITY = 1, SVB_OUT_POINTS = 2, SVB_OUT_POINTS_FLOATDISP = 4 };
 int svb_batch_run(svb_context *ctx, int n_frames, int flags);
 /* Per-frame status of the last batch call: nsupport_out[f] = support points of frame f.  A frame with fewer than 3 has no
  * triangulation ("ERROR: Need at least 3 support points!", elas.cpp:64-69): its batch outputs are what generatePointCloud
@@ -222,6 +231,8 @@ typedef struct svb_stats {
     int64_t frames;
     int64_t frames_failed;     /* frames with < 3 support points */
     double stage_ms[24];       /* per-stage CUDA-event time, index = svb_stage_id */
+    int64_t delaunay_lists_device; /* triangulations the device made (csrc/k_delaunay.cu), both sides counted */
+    int64_t delaunay_lists_host;   /* triangulations the host stage made (duplicate coordinates, > 4096 points, injected lists, SVB_DELAUNAY_DEVICE=0) */
 } svb_stats;
 int svb_get_stats(svb_context *ctx, svb_stats *out);
 const char *svb_stage_name(int stage_id);

@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libelas_b200.so")
 
 ROBOTICS, MIDDLEBURY, PIPELINE = 0, 1, 2
-OUT_DISPARITY, OUT_POINTS = 1, 2
+OUT_DISPARITY, OUT_POINTS, OUT_POINTS_FLOATDISP = 1, 2, 4
 ERR_FEW_SUPPORT = -5
 
 STAGE_NAMES = None
@@ -60,6 +60,8 @@ class Stats(C.Structure):
         ("frames", C.c_int64),
         ("frames_failed", C.c_int64),
         ("stage_ms", C.c_double * 24),
+        ("delaunay_lists_device", C.c_int64),
+        ("delaunay_lists_host", C.c_int64),
     ]
 
 
@@ -122,6 +124,7 @@ def load():
         "svb_stage_delaunay": [vp, C.c_int, C.c_int, vp, C.c_int, vp],
         "svb_stage_delaunay_pipeline": [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp],
         "svb_stage_delaunay_ordered": [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp],
+        "svb_stage_delaunay_levels": [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp],
         "svb_stage_planes": [vp, vp, C.c_int, vp, C.c_int, vp],
         "svb_stage_grid": [vp, vp, C.c_int, C.c_int, vp],
         "svb_stage_disparity": [vp, vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp],
@@ -207,6 +210,21 @@ def delaunay_ordered(support, right, order):
     tri = np.zeros((cap, 3), np.int32)
     m = C.c_int(0)
     rc = lib.svb_stage_delaunay_ordered(_ptr(support), n, int(right), _ptr(order), _ptr(tri), cap, C.byref(m))
+    if rc != 0:
+        raise SvbError(rc, lib.svb_last_error().decode())
+    return tri[: m.value].copy()
+
+
+def delaunay_levels(support, right, order, host_levels):
+    """The device's share of the Delaunay stage restated on the host (level-synchronous, 16-bit records) + host finish."""
+    lib = load()
+    support = np.ascontiguousarray(support, np.int32)
+    order = np.ascontiguousarray(order, np.int32)
+    n = len(support)
+    cap = 2 * n + 16
+    tri = np.zeros((cap, 3), np.int32)
+    m = C.c_int(0)
+    rc = lib.svb_stage_delaunay_levels(_ptr(support), n, int(right), _ptr(order), int(host_levels), _ptr(tri), cap, C.byref(m))
     if rc != 0:
         raise SvbError(rc, lib.svb_last_error().decode())
     return tri[: m.value].copy()
@@ -402,15 +420,15 @@ class Context:
         self._chk(self.lib.svb_set_single_stream(self.h, int(on)))
 
     def delaunay_pipeline(self, support, right):
-        """The Delaunay stage as the pipeline runs it (vertex order on the device, recursion on the host).
-        Returns (triangles, used_device_order)."""
+        """The Delaunay stage as the pipeline runs it.  Returns (triangles, used): 2 = the device made the whole list
+        (k_delaunay.cu), 1 = device vertex order + host recursion, 0 = complete host path."""
         support = np.ascontiguousarray(support, np.int32)
         n = len(support)
         cap = 2 * n + 16
         tri = np.zeros((cap, 3), np.int32)
         m, used = C.c_int(0), C.c_int(0)
         self._chk(self.lib.svb_stage_delaunay_pipeline(self.h, _ptr(support), n, int(right), _ptr(tri), cap, C.byref(m), C.byref(used)))
-        return tri[: m.value].copy(), bool(used.value)
+        return tri[: m.value].copy(), int(used.value)
 
     def set_eval_counting(self, on=True):
         self._chk(self.lib.svb_set_eval_counting(self.h, int(on)))

@@ -25,6 +25,8 @@
 // per level); only an input that does contain duplicates goes through the restated randomised quicksort.
 #include "host_delaunay.h"
 
+#include "delaunay_mesh.h"
+
 #include <algorithm>
 #include <cstring>
 
@@ -32,364 +34,7 @@ namespace svb {
 
 namespace {
 
-// Record r occupies R[8r .. 8r+7] = {nbr0, nbr1, nbr2, -, vtx0, vtx1, vtx2, -}; a handle is (8r + orientation), i.e.
-// the index of its own neighbour slot, and its apex sits four ints further.
-struct Pt {
-    int32_t x, y;
-};
-
-struct Mesh {
-    const Pt *__restrict P;  // coordinates by vertex id (= position in the lexicographic order); index -1 is the "NULL" sentinel
-    int32_t *__restrict R;
-    int ntri;
-
-    static int lnext(int e) { return (e & 3) == 2 ? e - 2 : e + 1; }
-    static int lprev(int e) { return (e & 3) == 0 ? e + 2 : e - 1; }
-    int &nbr(int e) { return R[e]; }
-    int &vtx(int e) { return R[e + 4]; }
-    int apex(int e) { return vtx(e); }
-    int org(int e) { return vtx(lnext(e)); }
-    int dest(int e) { return vtx(lprev(e)); }
-    void setapex(int e, int v) { vtx(e) = v; }
-    void setorg(int e, int v) { vtx(lnext(e)) = v; }
-    void setdest(int e, int v) { vtx(lprev(e)) = v; }
-    int sym(int e) { return nbr(e); }
-    void bond(int a, int b) {
-        nbr(a) = b;
-        nbr(b) = a;
-    }
-    // record 0 is the "outer space" record: its neighbours are itself and its vertices are NULL
-    int make() {
-        const int t = ntri++;
-        int32_t *r = R + 8 * t;
-        r[0] = r[1] = r[2] = r[3] = 0;
-        r[4] = r[5] = r[6] = r[7] = -1;
-        return t << 3;
-    }
-
-    // exact orientation: > 0 iff a, b, c are counter-clockwise.  |coordinate differences| < 2^14: 32-bit exact.
-    static int32_t ccw(Pt a, Pt b, Pt c) { return (a.x - c.x) * (b.y - c.y) - (a.y - c.y) * (b.x - c.x); }
-    int32_t ccw(int a, int b, int c) const { return ccw(P[a], P[b], P[c]); }
-    // exact in-circle: > 0 iff d lies inside the circle through a, b, c (a, b, c counter-clockwise).
-    // lifts and 2x2 minors stay below 2^29 (32-bit), their products below 2^58 (64-bit).
-    static int64_t incircle(Pt a, Pt b, Pt c, Pt d) {
-        const int32_t adx = a.x - d.x, ady = a.y - d.y;
-        const int32_t bdx = b.x - d.x, bdy = b.y - d.y;
-        const int32_t cdx = c.x - d.x, cdy = c.y - d.y;
-        const int32_t alift = adx * adx + ady * ady;
-        const int32_t blift = bdx * bdx + bdy * bdy;
-        const int32_t clift = cdx * cdx + cdy * cdy;
-        return (int64_t)alift * (bdx * cdy - cdx * bdy) + (int64_t)blift * (cdx * ady - adx * cdy) +
-               (int64_t)clift * (adx * bdy - bdx * ady);
-    }
-    int64_t incircle(int a, int b, int c, int d) const { return incircle(P[a], P[b], P[c], P[d]); }
-    // The same determinant for one circle (a, b, c) and many query points: translated to a, expanded along the query's
-    // row; the three cofactors are computed once.  test(d) == incircle(a, b, c, d) exactly (|cofactors| < 2^44, terms < 2^59).
-    struct Circle {
-        Pt a;
-        int64_t bx, by, cx, cy, k0, k1, k2;
-        // orientation part only: k2 = 2 x signed area of (a, b, c) = ccw(c, a, b)
-        Circle(Pt a_, Pt b, Pt c) : a(a_), bx(b.x - a_.x), by(b.y - a_.y), cx(c.x - a_.x), cy(c.y - a_.y), k0(0), k1(0) { k2 = bx * cy - by * cx; }
-        void finish() {  // the two cofactors that need the lifts
-            const int64_t bl = bx * bx + by * by, cl = cx * cx + cy * cy;
-            k0 = by * cl - bl * cy;
-            k1 = bx * cl - bl * cx;
-        }
-        int64_t test(Pt d) const {
-            const int64_t dx = d.x - a.x, dy = d.y - a.y;
-            return dy * k1 - dx * k0 - (dx * dx + dy * dy) * k2;  // = -det[b'; c'; d'] = det[a-d; b-d; c-d]
-        }
-    };
-
-    void merge(int &farleft, int &innerleft, int &innerright, int &farright, int axis);
-    void recurse(const int32_t *sorted, int count, int axis, int &farleft, int &farright);
-};
-
-// Knit two adjacent triangulations together (triangle.cpp:5362-5651).
-void Mesh::merge(int &farleft, int &innerleft, int &innerright, int &farright, int axis) {
-    int innerleftdest = dest(innerleft), innerleftapex = apex(innerleft);
-    int innerrightorg = org(innerright), innerrightapex = apex(innerright);
-    if (axis == 1) {
-        // horizontal cut: move the extreme handles from leftmost/rightmost to bottommost/topmost vertices
-        int farleftpt = org(farleft), farleftapex = apex(farleft);
-        int farrightpt = dest(farright);
-        while (P[farleftapex].y < P[farleftpt].y) {
-            farleft = sym(lnext(farleft));
-            farleftpt = farleftapex;
-            farleftapex = apex(farleft);
-        }
-        int check = sym(innerleft);
-        int checkv = apex(check);
-        while (P[checkv].y > P[innerleftdest].y) {
-            innerleft = lnext(check);
-            innerleftapex = innerleftdest;
-            innerleftdest = checkv;
-            check = sym(innerleft);
-            checkv = apex(check);
-        }
-        while (P[innerrightapex].y < P[innerrightorg].y) {
-            innerright = sym(lnext(innerright));
-            innerrightorg = innerrightapex;
-            innerrightapex = apex(innerright);
-        }
-        check = sym(farright);
-        checkv = apex(check);
-        while (P[checkv].y > P[farrightpt].y) {
-            farright = lnext(check);
-            farrightpt = checkv;
-            check = sym(farright);
-            checkv = apex(check);
-        }
-    }
-    // lower common tangent
-    bool changed;
-    do {
-        changed = false;
-        if (ccw(innerleftdest, innerleftapex, innerrightorg) > 0) {
-            innerleft = sym(lprev(innerleft));
-            innerleftdest = innerleftapex;
-            innerleftapex = apex(innerleft);
-            changed = true;
-        }
-        if (ccw(innerrightapex, innerrightorg, innerleftdest) > 0) {
-            innerright = sym(lnext(innerright));
-            innerrightorg = innerrightapex;
-            innerrightapex = apex(innerright);
-            changed = true;
-        }
-    } while (changed);
-
-    int leftcand = sym(innerleft);
-    int rightcand = sym(innerright);
-    // bottom bounding record
-    int base = make();
-    bond(base, innerleft);
-    base = lnext(base);
-    bond(base, innerright);
-    base = lnext(base);
-    setorg(base, innerrightorg);
-    setdest(base, innerleftdest);
-    if (innerleftdest == org(farleft)) farleft = lnext(base);
-    if (innerrightorg == dest(farright)) farright = lprev(base);
-
-    int lowerleft = innerleftdest, lowerright = innerrightorg;
-    int upperleft = apex(leftcand), upperright = apex(rightcand);
-    Pt pll = P[lowerleft], plr = P[lowerright], pul = P[upperleft], pur = P[upperright];  // coordinates ride along
-    while (true) {
-        // circles through the base edge and either candidate; their orientation term is the "finished" test
-        // (ccw(upper, lowerleft, lowerright) = 2 x area of (lowerleft, lowerright, upper), elas' triangle.cpp:5480-5483)
-        Circle cleft(pll, plr, pul), cright(pll, plr, pur);
-        const bool leftfinished = cleft.k2 <= 0;
-        const bool rightfinished = cright.k2 <= 0;
-        if (leftfinished && rightfinished) {
-            // top bounding record
-            int top = make();
-            setorg(top, lowerleft);
-            setdest(top, lowerright);
-            bond(top, base);
-            top = lnext(top);
-            bond(top, rightcand);
-            top = lnext(top);
-            bond(top, leftcand);
-            if (axis == 1) {
-                // restore the extreme handles to the leftmost / rightmost vertices
-                int farleftpt = org(farleft);
-                int farrightpt = dest(farright), farrightapex = apex(farright);
-                int check = sym(farleft);
-                int checkv = apex(check);
-                while (P[checkv].x < P[farleftpt].x) {
-                    farleft = lprev(check);
-                    farleftpt = checkv;
-                    check = sym(farleft);
-                    checkv = apex(check);
-                }
-                while (P[farrightapex].x > P[farrightpt].x) {
-                    farright = sym(lprev(farright));
-                    farrightpt = farrightapex;
-                    farrightapex = apex(farright);
-                }
-            }
-            return;
-        }
-        if (!leftfinished) {
-            cleft.finish();  // used by the left deletion test and by the final choice
-            // would deleting the left candidate edge expose a vertex that violates the Delaunay property?
-            int next = sym(lprev(leftcand));
-            int nextapex = apex(next);
-            while (nextapex >= 0 && cleft.test(P[nextapex]) > 0) {
-                // edge flip: the left triangulation gains one bounding record
-                next = lnext(next);
-                const int topcasing = sym(next);
-                next = lnext(next);
-                const int sidecasing = sym(next);
-                bond(next, topcasing);
-                bond(leftcand, sidecasing);
-                leftcand = lnext(leftcand);
-                const int outercasing = sym(leftcand);
-                next = lprev(next);
-                bond(next, outercasing);
-                setorg(leftcand, lowerleft);
-                setdest(leftcand, -1);
-                setapex(leftcand, nextapex);
-                setorg(next, -1);
-                setdest(next, upperleft);
-                setapex(next, nextapex);
-                upperleft = nextapex;
-                pul = P[nextapex];
-                cleft = Circle(pll, plr, pul);
-                cleft.finish();
-                next = sidecasing;
-                nextapex = apex(next);
-            }
-        }
-        if (!rightfinished) {
-            int next = sym(lnext(rightcand));
-            int nextapex = apex(next);
-            cright.finish();
-            while (nextapex >= 0 && cright.test(P[nextapex]) > 0) {
-                next = lprev(next);
-                const int topcasing = sym(next);
-                next = lprev(next);
-                const int sidecasing = sym(next);
-                bond(next, topcasing);
-                bond(rightcand, sidecasing);
-                rightcand = lprev(rightcand);
-                const int outercasing = sym(rightcand);
-                next = lnext(next);
-                bond(next, outercasing);
-                setorg(rightcand, -1);
-                setdest(rightcand, lowerright);
-                setapex(rightcand, nextapex);
-                setorg(next, upperright);
-                setdest(next, -1);
-                setapex(next, nextapex);
-                upperright = nextapex;
-                pur = P[nextapex];
-                cright = Circle(pll, plr, pur);
-                cright.finish();
-                next = sidecasing;
-                nextapex = apex(next);
-            }
-        }
-        // incircle(pul, pll, plr, pur): the same circle as `cleft` (a cyclic shift of the rows leaves the determinant alone)
-        if (leftfinished || (!rightfinished && cleft.test(pur) > 0)) {
-            // new edge lowerleft -- upperright
-            bond(base, rightcand);
-            base = lprev(rightcand);
-            setdest(base, lowerleft);
-            lowerright = upperright;
-            plr = pur;
-            rightcand = sym(base);
-            upperright = apex(rightcand);
-            pur = P[upperright];
-        } else {
-            // new edge upperleft -- lowerright (also taken on a co-circular tie)
-            bond(base, leftcand);
-            base = lnext(leftcand);
-            setorg(base, lowerright);
-            lowerleft = upperleft;
-            pll = pul;
-            leftcand = sym(base);
-            upperleft = apex(leftcand);
-            pul = P[upperleft];
-        }
-    }
-}
-
-// triangle.cpp:5670-5815
-void Mesh::recurse(const int32_t *s, int count, int axis, int &farleft, int &farright) {
-    if (count == 2) {
-        // an edge: two bounding records glued along all three sides
-        farleft = make();
-        setorg(farleft, s[0]);
-        setdest(farleft, s[1]);
-        farright = make();
-        setorg(farright, s[1]);
-        setdest(farright, s[0]);
-        bond(farleft, farright);
-        farleft = lprev(farleft);
-        farright = lnext(farright);
-        bond(farleft, farright);
-        farleft = lprev(farleft);
-        farright = lnext(farright);
-        bond(farleft, farright);
-        farleft = lprev(farright);  // origin of farleft = s[0]
-        return;
-    }
-    if (count == 3) {
-        int mid = make(), t1 = make(), t2 = make(), t3 = make();
-        const int64_t area = ccw(s[0], s[1], s[2]);
-        if (area == 0) {
-            // collinear: two edges, four bounding records
-            setorg(mid, s[0]);
-            setdest(mid, s[1]);
-            setorg(t1, s[1]);
-            setdest(t1, s[0]);
-            setorg(t2, s[2]);
-            setdest(t2, s[1]);
-            setorg(t3, s[1]);
-            setdest(t3, s[2]);
-            bond(mid, t1);
-            bond(t2, t3);
-            mid = lnext(mid);
-            t1 = lprev(t1);
-            t2 = lnext(t2);
-            t3 = lprev(t3);
-            bond(mid, t3);
-            bond(t1, t2);
-            mid = lnext(mid);
-            t1 = lprev(t1);
-            t2 = lnext(t2);
-            t3 = lprev(t3);
-            bond(mid, t1);
-            bond(t2, t3);
-            farleft = t1;
-            farright = t2;
-        } else {
-            // one real triangle (mid) surrounded by three bounding records
-            setorg(mid, s[0]);
-            setdest(t1, s[0]);
-            setorg(t3, s[0]);
-            if (area > 0) {
-                setdest(mid, s[1]);
-                setorg(t1, s[1]);
-                setdest(t2, s[1]);
-                setapex(mid, s[2]);
-                setorg(t2, s[2]);
-                setdest(t3, s[2]);
-            } else {
-                setdest(mid, s[2]);
-                setorg(t1, s[2]);
-                setdest(t2, s[2]);
-                setapex(mid, s[1]);
-                setorg(t2, s[1]);
-                setdest(t3, s[1]);
-            }
-            bond(mid, t1);
-            mid = lnext(mid);
-            bond(mid, t2);
-            mid = lnext(mid);
-            bond(mid, t3);
-            t1 = lprev(t1);
-            t2 = lnext(t2);
-            bond(t1, t2);
-            t1 = lprev(t1);
-            t3 = lprev(t3);
-            bond(t1, t3);
-            t2 = lnext(t2);
-            t3 = lprev(t3);
-            bond(t2, t3);
-            farleft = t1;
-            farright = area > 0 ? t2 : lnext(farleft);
-        }
-        return;
-    }
-    const int divider = count >> 1;
-    int innerleft, innerright;
-    recurse(s, divider, 1 - axis, farleft, innerleft);
-    recurse(s + divider, count - divider, 1 - axis, innerright, farright);
-    merge(farleft, innerleft, innerright, farright, axis);
-}
+using Mesh = MeshT<int32_t>;
 
 struct Lcg {  // triangle.cpp:3833-3836, seeded with 1 by triangleinit (:3818)
     unsigned long seed = 1;
@@ -580,24 +225,31 @@ int delaunay_xy(const int32_t *x, const int32_t *y, int n, int32_t *tri_out, int
     else
         kd_order<uint64_t, 32>(by_y, m, A, sorted);
 
-    // 4. divide and conquer
+    // 4. divide and conquer on the vertices renumbered in recursion order (a node's vertices are then consecutive ids)
+    Pt *P2 = (Pt *)A + 1;  // the sort / rank arrays are free now: 5 n uint64 >= (n + 1) points + n ids
+    int32_t *vid2 = (int32_t *)(P2 + m);
+    for (int i = 0; i < m; i++) {
+        P2[i] = P[sorted[i]];
+        vid2[i] = vid[sorted[i]];
+    }
+    P2[-1] = Pt{0, 0};
     Mesh mesh;
-    mesh.P = P;
+    mesh.P = P2;
     mesh.R = R;
     mesh.ntri = 0;
     mesh.make();  // record 0: outer space
     int hullleft, hullright;
-    mesh.recurse(sorted, m, 0, hullleft, hullright);
+    mesh.recurse(0, m, 0, 0, 1, -1, hullleft, hullright);
 
     int count = 0;
-    for (int t = 1; t < mesh.ntri; t++) {
+    for (int t = 1; t < 2 * m - 1; t++) {
         const int32_t *r = R + 8 * t + 4;
         const int a = r[1], b = r[2], c = r[0];  // org, dest, apex at orientation 0
         if ((a | b | c) < 0) continue;           // bounding record (removeghosts, :5817-5859)
         if (count < cap) {
-            tri_out[3 * count] = vid[a];
-            tri_out[3 * count + 1] = vid[b];
-            tri_out[3 * count + 2] = vid[c];
+            tri_out[3 * count] = vid2[a];
+            tri_out[3 * count + 1] = vid2[b];
+            tri_out[3 * count + 2] = vid2[c];
         }
         count++;
     }
@@ -607,21 +259,20 @@ int delaunay_xy(const int32_t *x, const int32_t *y, int n, int32_t *tri_out, int
 int delaunay_support_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int32_t *tri_out, int cap,
                              DelaunayScratch &scratch) {
     if (n < 3) return 0;
-    // arena (int32 units): [{x,y} sentinel + n][identity sequence n][records 8 R]
+    // arena (int32 units): [{x,y} sentinel + n][records 8 R]
     const size_t max_records = 1 + (size_t)4 * n + 16;
     const size_t need = 2 * (size_t)(n + 1) + (size_t)n + 8 * max_records + 2;
     if (scratch.storage.size() < need) scratch.storage.resize(need);
     int32_t *base = scratch.storage.data();
     base += ((uintptr_t)base & 7) ? 1 : 0;
     Pt *P = (Pt *)base + 1;
-    int32_t *seq = (int32_t *)(P + n), *R = seq + n;
+    int32_t *R = (int32_t *)(P + n);
     P[-1] = Pt{0, 0};
     for (int i = 0; i < n; i++) {
         const int id = order[i];
         if ((unsigned)id >= (unsigned)n) return -1;
         const int32_t *sp = support + 3 * id;
         P[i] = Pt{right_image ? sp[0] - sp[2] : sp[0], sp[1]};  // elas.cpp:451-461
-        seq[i] = i;
     }
     Mesh mesh;
     mesh.P = P;
@@ -629,10 +280,69 @@ int delaunay_support_ordered(const int32_t *support, int n, int right_image, con
     mesh.ntri = 0;
     mesh.make();  // record 0: outer space
     int hullleft, hullright;
-    mesh.recurse(seq, n, 0, hullleft, hullright);
+    mesh.recurse(0, n, 0, 0, 1, -1, hullleft, hullright);
     int count = 0;
-    for (int t = 1; t < mesh.ntri; t++) {
+    for (int t = 1; t < 2 * n - 1; t++) {
         const int32_t *r = R + 8 * t + 4;
+        const int a = r[1], b = r[2], c = r[0];
+        if ((a | b | c) < 0) continue;
+        if (count < cap) {
+            tri_out[3 * count] = order[a];
+            tri_out[3 * count + 1] = order[b];
+            tri_out[3 * count + 2] = order[c];
+        }
+        count++;
+    }
+    return count;
+}
+
+int delaunay_support_levels(const int32_t *support, int n, int right_image, const int32_t *order, int host_levels, int32_t *tri_out, int cap,
+                            DelaunayScratch &scratch) {
+    if (n < 3) return 0;
+    if (n > 4096) return -1;
+    const size_t records = 2 * (size_t)n;
+    // arena (int32 units): [{x,y} sentinel + n][int32 records 8 R][uint16 records 8 R]
+    const size_t need = 2 * (size_t)(n + 1) + 8 * records + 4 * records + 4;
+    if (scratch.storage.size() < need) scratch.storage.resize(need);
+    int32_t *base = scratch.storage.data();
+    base += ((uintptr_t)base & 7) ? 1 : 0;
+    Pt *P = (Pt *)base + 1;
+    int32_t *R32 = (int32_t *)(P + n);
+    uint16_t *R16 = (uint16_t *)(R32 + 8 * records);
+    P[-1] = Pt{0, 0};
+    for (int i = 0; i < n; i++) {
+        const int id = order[i];
+        if ((unsigned)id >= (unsigned)n) return -1;
+        const int32_t *sp = support + 3 * id;
+        P[i] = Pt{right_image ? sp[0] - sp[2] : sp[0], sp[1]};
+    }
+    // "device": levels max_depth .. host_levels, every node of a level independently of the others
+    MeshT<uint16_t> dm;
+    dm.P = P;
+    dm.R = R16;
+    dm.ntri = 0;
+    dm.make();
+    const int max_depth = delaunay_max_depth(n);
+    if (host_levels < 0) host_levels = 0;
+    for (int depth = max_depth; depth >= host_levels; depth--)
+        for (int k = (1 << depth) - 1; k >= 0; k--) {  // any order within a level must do: run it backwards
+            const DelaunayNode nd = delaunay_node_at(n, depth, k);
+            if (nd.exists) dm.build_node(nd);
+        }
+    // records widen to the host's 32-bit layout (neighbour handles zero-extended, vertex ids sign-extended)
+    for (size_t t = 0; t < 2 * (size_t)n - 1; t++)
+        for (int q = 0; q < 8; q++) R32[8 * t + q] = (q & 3) == 3 ? (int32_t)R16[8 * t + q] : (q < 4 ? (int32_t)R16[8 * t + q] : (int32_t)(int16_t)R16[8 * t + q]);
+    Mesh mesh;
+    mesh.P = P;
+    mesh.R = R32;
+    mesh.ntri = 0;
+    if (host_levels > 0) {
+        int hullleft, hullright;
+        mesh.recurse(0, n, 0, 0, 1, host_levels, hullleft, hullright);
+    }
+    int count = 0;
+    for (int t = 1; t < 2 * n - 1; t++) {
+        const int32_t *r = R32 + 8 * t + 4;
         const int a = r[1], b = r[2], c = r[0];
         if ((a | b | c) < 0) continue;
         if (count < cap) {

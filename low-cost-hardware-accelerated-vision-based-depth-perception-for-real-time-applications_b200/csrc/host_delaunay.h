@@ -24,6 +24,12 @@ int delaunay_support(const int32_t *support, int n, int right_image, int32_t *tr
 int delaunay_support_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int32_t *tri_out, int cap,
                              DelaunayScratch &scratch);
 
+// The device's share of the stage, restated on the host (tests, no GPU needed): the levels of the recursion tree from the leaves up
+// to depth `host_levels` are built level by level in 16-bit records -- exactly what k_delaunay.cu does with one thread per node --
+// and the host recursion finishes the levels above (host_levels = 0: nothing is left for it but the list).  n <= 4096.
+int delaunay_support_levels(const int32_t *support, int n, int right_image, const int32_t *order, int host_levels, int32_t *tri_out, int cap,
+                            DelaunayScratch &scratch);
+
 // Same on explicit integer coordinates.
 int delaunay_xy(const int32_t *x, const int32_t *y, int n, int32_t *tri_out, int cap, DelaunayScratch &scratch);
 

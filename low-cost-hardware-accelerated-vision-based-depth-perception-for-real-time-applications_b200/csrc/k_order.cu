@@ -64,14 +64,19 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long *K, int np2) {
 
 // grid: (nf, 2); blockIdx.y = image side (0: (u, v), 1: (u - d, v), elas.cpp:451-461)
 __global__ void __launch_bounds__(OR_THREADS) k_delaunay_order(const int32_t *__restrict__ support_all, const int32_t *__restrict__ nsupport_all,
-                                                              int32_t *__restrict__ h_order_all, int32_t *__restrict__ h_ok_all, int maxS) {
+                                                              int32_t *__restrict__ h_order_all, int32_t *__restrict__ h_ok_all,
+                                                              int32_t *__restrict__ d_order_all, int32_t *__restrict__ d_ok_all, int maxS) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OrderSmem &S = *reinterpret_cast<OrderSmem *>(smem_raw);
     const int f = blockIdx.x, side = blockIdx.y, tid = threadIdx.x;
     const int n = nsupport_all[f];
     int32_t *ok_out = h_ok_all + 2 * f + side;
+    int32_t *ok_dev = d_ok_all ? d_ok_all + 2 * f + side : nullptr;  // device copies for the divide-and-conquer kernel (k_delaunay.cu)
     if (n < 3 || n > OR_MAXN || n > maxS) {  // uniform
-        if (tid == 0) *ok_out = 0;
+        if (tid == 0) {
+            *ok_out = 0;
+            if (ok_dev) *ok_dev = 0;
+        }
         return;
     }
     const int32_t *support = support_all + (size_t)f * maxS * 3;
@@ -97,7 +102,10 @@ __global__ void __launch_bounds__(OR_THREADS) k_delaunay_order(const int32_t *__
         if (i > 0 && (S.K[i] >> 32) == (S.K[i - 1] >> 32)) S.bad = 1;  // duplicate coordinates: the host decides which survives
     __syncthreads();
     if (S.bad) {
-        if (tid == 0) *ok_out = 0;
+        if (tid == 0) {
+            *ok_out = 0;
+            if (ok_dev) *ok_dev = 0;
+        }
         return;
     }
     // 2. y rank: sort (y, x) keys that carry the x rank
@@ -216,16 +224,25 @@ __global__ void __launch_bounds__(OR_THREADS) k_delaunay_order(const int32_t *__
             isp = t;
         }
     }
-    for (int i = tid; i < n; i += OR_THREADS) order[i] = (int32_t)S.orig[S.L[ix][i] >> 16];
-    if (tid == 0) *ok_out = 1;
+    int32_t *order_dev = d_order_all ? d_order_all + ((size_t)f * 2 + side) * maxS : nullptr;
+    for (int i = tid; i < n; i += OR_THREADS) {
+        const int32_t id = (int32_t)S.orig[S.L[ix][i] >> 16];
+        order[i] = id;
+        if (order_dev) order_dev[i] = id;
+    }
+    if (tid == 0) {
+        *ok_out = 1;
+        if (ok_dev) *ok_dev = 1;
+    }
 }
 
 }  // namespace
 
-int launch_delaunay_order(const Dims &d, const int32_t *support, const int32_t *nsupport, int32_t *h_order, int32_t *h_ok, int nf, cudaStream_t s) {
+int launch_delaunay_order(const Dims &d, const int32_t *support, const int32_t *nsupport, int32_t *h_order, int32_t *h_ok, int32_t *d_order,
+                          int32_t *d_ok, int nf, cudaStream_t s) {
     if (nf <= 0) return SVB_OK;
     SVB_CUDA(cudaFuncSetAttribute(k_delaunay_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderSmem)));  // per device
-    k_delaunay_order<<<dim3(nf, 2), OR_THREADS, sizeof(OrderSmem), s>>>(support, nsupport, h_order, h_ok, d.maxS);
+    k_delaunay_order<<<dim3(nf, 2), OR_THREADS, sizeof(OrderSmem), s>>>(support, nsupport, h_order, h_ok, d_order, d_ok, d.maxS);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

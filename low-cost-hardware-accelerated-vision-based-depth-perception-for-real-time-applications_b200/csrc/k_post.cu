@@ -3,6 +3,7 @@
 // Replaces Elas::leftRightConsistencyCheck, gapInterpolation, adaptiveMean (full-resolution branch) and median
 // (src/serial_includes/elas/elas.cpp:946-1011, 1126-1295, 1297-1494, 1496-1559).  All of these are a few bytes
 // of HBM traffic per pixel; the kernels are laid out so that every global access is coalesced along image rows.
+#include "post_device.cuh"
 #include "svb_internal.h"
 
 namespace svb {
@@ -192,43 +193,6 @@ __global__ void __launch_bounds__(128) k_gap_cols(float *__restrict__ D_all, int
 // memory bound (ncu: ALU pipe 73-81 %), which is why instruction count per pixel is what is optimised here.
 // mode 0: weight = max(0, 4 - float_and(x - xc, 0x4F000000))   (the serial reference's bit-mask "abs")
 // mode 1: weight = max(0, 4 - |x - xc|)                         (the parallel reference)
-template <int MODE>
-__device__ __forceinline__ float mean_weight(float x, float xc) {
-    const float diff = __fsub_rn(x, xc);
-    const float m = MODE ? fabsf(diff) : __int_as_float(__float_as_int(diff) & 0x4F000000);
-    return fmaxf(0.f, __fsub_rn(4.f, m));
-}
-
-// x[0..10] = values at coordinates c0-4 .. c0+6 (c0 % 4 == 0); J = which of the four centres (c = c0 + J).
-// Returns true and *out if the reference writes the pixel.
-template <int MODE, int J>
-__device__ __forceinline__ bool mean8(const float (&x)[11], float *out) {
-    const float xc = x[J + 4];
-    float w[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) w[i] = mean_weight<MODE>(x[J + i], xc);
-    float wsum[4], fsum[4];
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        // window element i sits at coordinate c0 - 4 + J + i, i.e. residue (J + i) mod 4: pair p = {i0, i0 + 4}
-        constexpr int dummy = 0;
-        (void)dummy;
-        const int i0 = (p - J) & 3;
-        wsum[p] = __fadd_rn(w[i0], w[i0 + 4]);
-        fsum[p] = __fadd_rn(__fmul_rn(x[J + i0], w[i0]), __fmul_rn(x[J + i0 + 4], w[i0 + 4]));
-    }
-    const float weight_sum = __fadd_rn(__fadd_rn(__fadd_rn(wsum[0], wsum[1]), wsum[2]), wsum[3]);
-    const float factor_sum = __fadd_rn(__fadd_rn(__fadd_rn(fsum[0], fsum[1]), fsum[2]), fsum[3]);
-    if (weight_sum > 0.f) {
-        const float d = __fdiv_rn(factor_sum, weight_sum);
-        if (d >= 0.f) {
-            *out = d;
-            return true;
-        }
-    }
-    return false;
-}
-
 // Horizontal pass: tmp = (D < 0 ? -10 : 0) overwritten by the filtered value where the reference writes D_tmp.
 // (D_tmp is malloc'ed and only partly written in the reference; unwritten valid pixels are DEFINED as 0,
 // SURVEY.md finding 5.)  grid: (ceil(ceil(W/4)/128), H, nimg); a thread owns columns c0 .. c0+3
@@ -358,17 +322,6 @@ __global__ void __launch_bounds__(128) k_mean4_v(const float *__restrict__ tmp_a
 // ---- median -------------------------------------------------------------------------------------------
 // Median of 7 by a 13-exchange selection network (the reference sorts with an insertion sort, elas.cpp:1519-1528;
 // the median is a selection, so any correct method gives the same value; the inputs are never NaN).
-__device__ __forceinline__ void cswap(float &a, float &b) {
-    const float lo = fminf(a, b), hi = fmaxf(a, b);
-    a = lo;
-    b = hi;
-}
-__device__ __forceinline__ float median7(float p0, float p1, float p2, float p3, float p4, float p5, float p6) {
-    cswap(p0, p5); cswap(p0, p3); cswap(p1, p6); cswap(p2, p4); cswap(p0, p1); cswap(p3, p5); cswap(p2, p6);
-    cswap(p2, p3); cswap(p3, p6); cswap(p4, p5); cswap(p1, p4); cswap(p1, p3); cswap(p3, p4);
-    return p3;
-}
-
 // D_temp is calloc'ed (elas.cpp:1506): 0 outside [3,W-3)x[3,H-3).  A thread owns 4 consecutive columns.
 // grid: (ceil(ceil(W/4)/128), H, nimg)
 __global__ void __launch_bounds__(128) k_median_h(const float *__restrict__ D_all, float *__restrict__ tmp_all, int W, int H) {

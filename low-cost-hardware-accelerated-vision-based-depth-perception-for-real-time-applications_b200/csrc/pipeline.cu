@@ -96,9 +96,9 @@ int make_dims(const svb_params &p, int W, int H, Dims *out) {
     return SVB_OK;
 }
 
-static const char *kStageNames[ST_COUNT] = {"descriptor", "support_match", "support_filter", "d2h_support", "h2d_triangles",
+static const char *kStageNames[ST_COUNT] = {"descriptor", "support_match", "support_filter", "delaunay_device", "d2h_support", "h2d_triangles",
                                             "planes",     "grid",          "raster",         "dense_match", "lr_check",
-                                            "remove_small_segments", "gap_interpolation", "adaptive_mean", "median", "reproject"};
+                                            "remove_small_segments", "gap_interpolation", "adaptive_mean", "median", "reproject", "post_fused"};
 
 }  // namespace svb
 
@@ -171,6 +171,12 @@ int lane_create(svb_context *c, Lane &L) {
     SVB_TRY(host_alloc(&L.h_order, C * 2 * d.maxS));
     SVB_TRY(host_alloc(&L.h_order_ok, C * 2));
     memset(L.h_order_ok, 0, sizeof(int32_t) * C * 2);
+    SVB_TRY(dev_alloc(&L.d_order, C * 2 * d.maxS));
+    SVB_TRY(dev_alloc(&L.d_order_ok, C * 2));
+    SVB_CUDA(cudaMemset(L.d_order_ok, 0, sizeof(int32_t) * C * 2));
+    SVB_TRY(host_alloc(&L.h_dd_done, C * 2));
+    memset(L.h_dd_done, 0, sizeof(int32_t) * C * 2);
+    L.host_made.assign(C * 2, 0);
     return SVB_OK;
 }
 
@@ -201,6 +207,9 @@ void lane_destroy(Lane &L) {
     cudaFreeHost(L.h_ntri);
     cudaFreeHost(L.h_order);
     cudaFreeHost(L.h_order_ok);
+    cudaFree(L.d_order);
+    cudaFree(L.d_order_ok);
+    cudaFreeHost(L.h_dd_done);
     if (L.ev_a) cudaEventDestroy(L.ev_a);
     if (L.ev_done) cudaEventDestroy(L.ev_done);
     if (L.own_stream) cudaStreamDestroy(L.own_stream);
@@ -282,8 +291,19 @@ int stage_a(svb_context *c, Lane &L, const uint8_t *img1, const uint8_t *img2, i
     SVB_TRY(T.mark(ST_SUPPORT_FILTER));
     // the kernel writes the lists into the mapped pinned buffers itself: no device-to-host copy is queued
     SVB_TRY(launch_support_filter(d, c->p, L.dcan_raw, L.dcan, L.support, L.nsupport, L.h_support, L.h_nsupport, nf, L.stream));
+    SVB_TRY(T.mark(ST_DELAUNAY_DEVICE));
     // ... and the order in which the host's divide-and-conquer will meet the vertices (sort + alternating cuts)
-    if (c->gpu_order) SVB_TRY(launch_delaunay_order(d, L.support, L.nsupport, L.h_order, L.h_order_ok, nf, L.stream));
+    L.unpacked = false;
+    if (c->gpu_order) {
+        SVB_TRY(launch_delaunay_order(d, L.support, L.nsupport, L.h_order, L.h_order_ok, L.d_order, L.d_order_ok, nf, L.stream));
+        // ... and then the divide-and-conquer itself, straight into the lane's triangle arena (k_delaunay.cu); the host stage only
+        // takes the lists the device leaves to it (duplicate coordinates, more points than the launch has shared memory for)
+        if (c->delaunay_device && !c->inject[0] && !c->inject[1]) {
+            SVB_TRY(launch_delaunay_levels(d, L.support, L.nsupport, L.d_order, L.d_order_ok, L.tri[0], L.tri[1], L.h_ntri, L.h_dd_done, nf, c->dd_cap,
+                                           L.stream));
+            L.unpacked = true;
+        }
+    }
     SVB_TRY(T.mark(ST_D2H_SUPPORT));
     if (se) {
         SVB_CUDA(cudaEventRecord(se->a_end, L.stream));
@@ -295,15 +315,39 @@ int stage_a(svb_context *c, Lane &L, const uint8_t *img1, const uint8_t *img2, i
 
 // ---- host stage ----------------------------------------------------------------------------------------
 }  // namespace
-int svb::stage_host(svb_context *c, Lane &L, int nf) {
+int svb::stage_host(svb_context *c, Lane &L, int nf, bool unpacked) {
     const Dims &d = c->d;
     SVB_CUDA(cudaEventSynchronize(L.ev_a));
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<double> per_worker(c->pool->size(), 0.0);
-    // The triangle lists of a chunk are packed back to back: a triangulation of n points has at most 2n - 5 triangles,
-    // so frame f gets room for 2 n_f (or the injected list) starting at h_trioff[f]; only that much crosses PCIe.
     int32_t *h_trioff = L.h_ntri + 2 * c->chunk;
-    {
+    std::fill(L.host_made.begin(), L.host_made.end(), (uint8_t)0);
+    std::vector<int> jobs;  // 2 f + side of the lists made here
+    jobs.reserve(2 * (size_t)nf);
+    int max_n = 0;
+    if (unpacked) {
+        // The device wrote frame f's lists at triangle f * (maxT + 8) of the lane's arena and their sizes into h_ntri; what it left
+        // (h_dd_done = 0) is triangulated here into the same slot of the pinned mirror and copied up list by list.
+        for (int f = 0; f < nf; f++) {
+            int n = L.h_nsupport[f];
+            if (n < 0 || n > d.maxS) n = L.h_nsupport[f] = 0;
+            max_n = std::max(max_n, n);
+            h_trioff[f] = f * (d.maxT + 8);
+            for (int side = 0; side < 2; side++) {
+                if (c->inject[side] || L.h_dd_done[2 * f + side] != 1) {
+                    jobs.push_back(2 * f + side);
+                } else {
+                    c->stats.delaunay_lists_device++;
+                }
+                L.h_dd_done[2 * f + side] = 0;
+            }
+        }
+        h_trioff[nf] = nf * (d.maxT + 8);
+        // shared-memory capacity of the next launches follows the lists seen (a list above it is simply the host's)
+        if (max_n > c->dd_cap * 4 / 5 && c->dd_cap < 4096) c->dd_cap = std::min(4096, ((max_n * 5 / 4 + 511) / 512) * 512);
+    } else {
+        // The triangle lists of a chunk are packed back to back: a triangulation of n points has at most 2n - 5 triangles,
+        // so frame f gets room for 2 n_f (or the injected list) starting at h_trioff[f]; only that much crosses PCIe.
         int off = 0;
         for (int f = 0; f < nf; f++) {
             int n = L.h_nsupport[f];
@@ -313,6 +357,8 @@ int svb::stage_host(svb_context *c, Lane &L, int nf) {
                 if (c->inject[side]) cap = std::max(cap, (int)(c->inject_tri[side].size() / 3));
             h_trioff[f] = off;
             off += cap;
+            jobs.push_back(2 * f);
+            jobs.push_back(2 * f + 1);
         }
         h_trioff[nf] = off;  // total (h_ntri holds 3*chunk ints + slack, h_trioff[chunk] is the slack slot)
         if ((size_t)off > (size_t)c->chunk * (d.maxT + 8)) {
@@ -320,31 +366,34 @@ int svb::stage_host(svb_context *c, Lane &L, int nf) {
             return SVB_ERR_ARG;
         }
     }
-    c->pool->parallel_for(nf * 2, [&](int job, int worker) {
-        const auto w0 = std::chrono::steady_clock::now();
-        const int f = job >> 1, side = job & 1;
-        const int n = L.h_nsupport[f];
-        const int cap = h_trioff[f + 1] - h_trioff[f];
-        int32_t *out = L.h_tri[side] + (size_t)h_trioff[f] * 3;
-        int m = 0;
-        if (c->inject[side]) {
-            m = (int)(c->inject_tri[side].size() / 3);
-            if (m > cap) m = cap;
-            memcpy(out, c->inject_tri[side].data(), sizeof(int32_t) * 3 * m);
-        } else if (n >= 3) {
-            const int32_t *sup = L.h_support + (size_t)f * d.maxS * 3;
-            m = -1;
-            if (c->gpu_order && L.h_order_ok[2 * f + side] == 1)
-                m = delaunay_support_ordered(sup, n, side, L.h_order + ((size_t)f * 2 + side) * d.maxS, out, cap, c->scratch[worker]);
-            if (m < 0) m = delaunay_support(sup, n, side, out, cap, c->scratch[worker]);
-            if (m > cap) m = cap;
-        }
-        L.h_ntri[2 * f + side] = m;
-        per_worker[worker] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
-    });
+    if (!jobs.empty())
+        c->pool->parallel_for((int)jobs.size(), [&](int j, int worker) {
+            const auto w0 = std::chrono::steady_clock::now();
+            const int f = jobs[j] >> 1, side = jobs[j] & 1;
+            const int n = L.h_nsupport[f];
+            const int cap = unpacked ? d.maxT + 8 : h_trioff[f + 1] - h_trioff[f];
+            int32_t *out = L.h_tri[side] + (size_t)h_trioff[f] * 3;
+            int m = 0;
+            if (c->inject[side]) {
+                m = (int)(c->inject_tri[side].size() / 3);
+                if (m > cap) m = cap;
+                memcpy(out, c->inject_tri[side].data(), sizeof(int32_t) * 3 * m);
+            } else if (n >= 3) {
+                const int32_t *sup = L.h_support + (size_t)f * d.maxS * 3;
+                m = -1;
+                if (c->gpu_order && L.h_order_ok[2 * f + side] == 1)
+                    m = delaunay_support_ordered(sup, n, side, L.h_order + ((size_t)f * 2 + side) * d.maxS, out, cap, c->scratch[worker]);
+                if (m < 0) m = delaunay_support(sup, n, side, out, cap, c->scratch[worker]);
+                if (m > cap) m = cap;
+            }
+            L.h_ntri[2 * f + side] = m;
+            L.host_made[2 * f + side] = 1;
+            per_worker[worker] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+        });
     const auto t1 = std::chrono::steady_clock::now();
     c->stats.delaunay_ms_wall += std::chrono::duration<double, std::milli>(t1 - t0).count();
     for (double v : per_worker) c->stats.delaunay_ms_total += v;
+    c->stats.delaunay_lists_host += (int64_t)jobs.size();
     for (int f = 0; f < nf; f++) {
         c->stats.support_points += L.h_nsupport[f];
         c->stats.triangles += L.h_ntri[2 * f] + L.h_ntri[2 * f + 1];
@@ -367,9 +416,18 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, 
     for (int i = 0; i < nf; i++) max_support = L.h_nsupport[i] > max_support ? L.h_nsupport[i] : max_support;
     SVB_TRY(T.mark(ST_H2D_TRIANGLES));
     SVB_CUDA(cudaMemcpyAsync(L.ntri, L.h_ntri, sizeof(int32_t) * 3 * C, cudaMemcpyHostToDevice, L.stream));
-    const size_t tri_total = (size_t)L.h_ntri[2 * C + nf];  // packed size of this chunk's lists, in triangles
-    for (int s = 0; s < 2; s++)
-        if (tri_total) SVB_CUDA(cudaMemcpyAsync(L.tri[s], L.h_tri[s], sizeof(int32_t) * 3 * tri_total, cudaMemcpyHostToDevice, L.stream));
+    if (L.unpacked) {
+        // the device made the lists in place; only what the host stage produced goes up, list by list (normally nothing)
+        for (int i = 0; i < 2 * nf; i++)
+            if (L.host_made[i] && L.h_ntri[i] > 0) {
+                const size_t at = (size_t)L.h_ntri[2 * C + (i >> 1)] * 3;
+                SVB_CUDA(cudaMemcpyAsync(L.tri[i & 1] + at, L.h_tri[i & 1] + at, sizeof(int32_t) * 3 * (size_t)L.h_ntri[i], cudaMemcpyHostToDevice, L.stream));
+            }
+    } else {
+        const size_t tri_total = (size_t)L.h_ntri[2 * C + nf];  // packed size of this chunk's lists, in triangles
+        for (int s = 0; s < 2; s++)
+            if (tri_total) SVB_CUDA(cudaMemcpyAsync(L.tri[s], L.h_tri[s], sizeof(int32_t) * 3 * tri_total, cudaMemcpyHostToDevice, L.stream));
+    }
     SVB_TRY(T.mark(ST_PLANES));
     float *pr1 = (c->tap_mode && nf == 1) ? c->planes_ref[0] : nullptr;
     float *pr2 = (c->tap_mode && nf == 1) ? c->planes_ref[1] : nullptr;
@@ -408,8 +466,12 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, 
         SVB_TRY(tap_store(c, "D1gap", D1, DN * 4, L.stream));
         if (both) SVB_TRY(tap_store(c, "D2gap", D2, DN * 4, L.stream));
     }
+    // Tail of the chain.  Full-resolution maps outside tap mode: ONE kernel does adaptive mean, median, the final map, the u8 map
+    // and the point cloud (k_post_fused.cu); tap mode and the half-resolution chain keep the stage-by-stage kernels.
+    const bool fused = c->fused_post && !c->tap_mode && !d.sub;
+    const bool float_disp = c->points_float_disp;
     SVB_TRY(T.mark(ST_MEAN));
-    if (p.filter_adaptive_mean) {
+    if (!fused && p.filter_adaptive_mean) {
         for (int s = 0; s < passes; s++) SVB_TRY(launch_adaptive_mean(d, c->mean_mode, s ? D2 : D1, L.Dtmp, nf, L.stream));
         if (c->tap_mode && nf == 1) {
             SVB_TRY(tap_store(c, "D1mean", D1, DN * 4, L.stream));
@@ -417,7 +479,7 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, 
         }
     }
     SVB_TRY(T.mark(ST_MEDIAN));
-    if (p.filter_median) {
+    if (!fused && p.filter_median) {
         for (int s = 0; s < passes; s++) SVB_TRY(launch_median(d, s ? D2 : D1, L.Dtmp, nf, L.stream));
         if (c->tap_mode && nf == 1) {
             SVB_TRY(tap_store(c, "D1med", D1, DN * 4, L.stream));
@@ -425,13 +487,36 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, 
         }
     }
     SVB_TRY(T.mark(ST_REPROJECT));
+    if (!fused) {
+        if (out_D1) SVB_CUDA(cudaMemcpyAsync(out_D1, D1, DN * 4 * nf, cudaMemcpyDeviceToDevice, L.stream));
+        if (out_points) {
+            if (float_disp)
+                SVB_TRY(launch_reproject_float(d, c->calib, D1, out_points, nf, L.stream));
+            else
+                SVB_TRY(launch_reproject(d, c->calib, D1, L.dmap, out_points, nf, L.stream));
+        }
+    }
+    SVB_TRY(T.mark(ST_POST_FUSED));
+    if (fused) {
+        for (int s = 0; s < passes; s++) {
+            float *src = s ? D2 : D1;
+            // the final left map goes straight into the batch store when there is one; otherwise (Elas::process) it comes back into the
+            // lane's map through the scratch arena, because a tile reads its neighbours' halos and cannot work in place
+            float *dst = (s == 0 && out_D1) ? out_D1 : L.Dtmp;
+            SVB_TRY(launch_post_fused(d, p, c->mean_mode, c->calib, src, dst, (s == 0 && out_points) ? L.dmap : nullptr,
+                                      s == 0 ? out_points : nullptr, float_disp ? 1 : 0, nf, L.stream));
+            if (dst == L.Dtmp) SVB_CUDA(cudaMemcpyAsync(src, L.Dtmp, DN * 4 * nf, cudaMemcpyDeviceToDevice, L.stream));
+        }
+    }
     // Batch outputs of a frame with fewer than 3 support points: Elas::process returns without touching D (elas.cpp:64-69) and the
     // driver's maps start as zeros (stereo_vision.cu:311-312), so the frame's disparity is 0 everywhere, like svb_point_cloud_bgra
     if (out_D1 || out_points)
         for (int f = 0; f < nf; f++)
-            if (L.h_nsupport[f] < 3) SVB_CUDA(cudaMemsetAsync(D1 + (size_t)f * DN, 0, DN * 4, L.stream));
-    if (out_D1) SVB_CUDA(cudaMemcpyAsync(out_D1, D1, DN * 4 * nf, cudaMemcpyDeviceToDevice, L.stream));
-    if (out_points) SVB_TRY(launch_reproject(d, c->calib, D1, L.dmap, out_points, nf, L.stream));
+            if (L.h_nsupport[f] < 3) {
+                SVB_CUDA(cudaMemsetAsync(D1 + (size_t)f * DN, 0, DN * 4, L.stream));
+                if (out_D1) SVB_CUDA(cudaMemsetAsync(out_D1 + (size_t)f * DN, 0, DN * 4, L.stream));
+                if (out_points) SVB_TRY(launch_reproject(d, c->calib, D1 + (size_t)f * DN, L.dmap + (size_t)f * N, out_points + (size_t)f * N * 3, 1, L.stream));
+            }
     SVB_TRY(T.mark(ST_COUNT));
     if (se) se->b_done = true;
     SVB_CUDA(cudaEventRecord(L.ev_done, L.stream));
@@ -556,6 +641,11 @@ svb_context *svb_create(const svb_params *params, int width, int height, int chu
     {
         const char *g = getenv("SVB_GPU_ORDER");
         if (g && atoi(g) == 0) c->gpu_order = false;
+        const char *dd = getenv("SVB_DELAUNAY_DEVICE");
+        if (dd && atoi(dd) == 0) c->delaunay_device = false;
+        c->dd_cap = std::min(c->chunk == 1 ? 4096 : 2048, std::max(c->d.maxS, 3));  // single-frame contexts: one CTA per side, take all it can
+        const char *fp = getenv("SVB_FUSED_POST");
+        if (fp && atoi(fp) == 0) c->fused_post = false;
         const char *e = getenv("SVB_LANES");
         const int n = e ? atoi(e) : 4;
         c->n_lanes = n < 1 ? 1 : (n > MAX_LANES ? MAX_LANES : n);
@@ -724,7 +814,7 @@ int svb_process(svb_context *c, const uint8_t *I1, const uint8_t *I2, int stride
     StageEvents *se = stage_events_of(c, 0);
     SVB_TRY(stage_a(c, L, L.img[0], L.img[1], 1, se));
     if (c->tap_mode) SVB_TRY(tap_after_a(c, L));
-    SVB_TRY(stage_host(c, L, 1));
+    SVB_TRY(stage_host(c, L, 1, L.unpacked));
     c->stats.frames = 1;
     const int n = L.h_nsupport[0];
     if (c->tap_mode) {
@@ -843,8 +933,24 @@ int svb_stage_delaunay_ordered(const int32_t *support, int n, int right_image, c
     return SVB_OK;
 }
 
+// The device's share of the Delaunay stage restated on the host (no GPU needed): levels below `host_levels` built level by level in
+// 16-bit records like k_delaunay.cu, the rest by the host recursion.  `order` as for svb_stage_delaunay_ordered.
+int svb_stage_delaunay_levels(const int32_t *support, int n, int right_image, const int32_t *order, int host_levels, int32_t *tri, int cap,
+                              int *n_tri_out) {
+    if (!support || !order || !tri || n < 0 || cap < 0) return SVB_ERR_ARG;
+    DelaunayScratch scratch;
+    const int m = delaunay_support_levels(support, n, right_image ? 1 : 0, order, host_levels, tri, cap, scratch);
+    if (m < 0) {
+        set_error("svb_stage_delaunay_levels: n > 4096 or `order` is not a permutation of 0..n-1");
+        return SVB_ERR_ARG;
+    }
+    if (n_tri_out) *n_tri_out = m;
+    return SVB_OK;
+}
+
 // Host Delaunay stage exactly as the pipeline runs it: the device orders the vertices (k_order.cu), the host recurses;
-// *used_device_order tells whether the device's order was usable (0: duplicates, > 4096 points, ... -> complete host path).
+// *used_device_order: 2 = the device made the whole list (k_delaunay.cu), 1 = device vertex order + host recursion, 0 = complete host
+// path (duplicates, > 4096 points, ...).
 int svb_stage_delaunay_pipeline(svb_context *c, const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out,
                                 int *used_device_order) {
     STAGE_PROLOG();
@@ -854,16 +960,26 @@ int svb_stage_delaunay_pipeline(svb_context *c, const int32_t *support, int n, i
     SVB_CUDA(cudaMemcpyAsync(L.nsupport, L.h_nsupport, 4, cudaMemcpyHostToDevice, L.stream));
     if (n) SVB_CUDA(cudaMemcpyAsync(L.support, L.h_support, (size_t)n * 12, cudaMemcpyHostToDevice, L.stream));
     L.h_order_ok[0] = L.h_order_ok[1] = 0;
-    SVB_TRY(launch_delaunay_order(d, L.support, L.nsupport, L.h_order, L.h_order_ok, 1, L.stream));
+    L.h_dd_done[0] = L.h_dd_done[1] = 0;
+    SVB_TRY(launch_delaunay_order(d, L.support, L.nsupport, L.h_order, L.h_order_ok, L.d_order, L.d_order_ok, 1, L.stream));
+    if (c->delaunay_device)
+        SVB_TRY(launch_delaunay_levels(d, L.support, L.nsupport, L.d_order, L.d_order_ok, L.tri[0], L.tri[1], L.h_ntri, L.h_dd_done, 1, c->dd_cap, L.stream));
     SVB_CUDA(cudaStreamSynchronize(L.stream));
     const int side = right_image ? 1 : 0;
     int m = -1, used = 0;
-    if (L.h_order_ok[side] == 1) {
+    if (L.h_dd_done[side] == 1) {
+        // the device made the whole list (k_delaunay.cu)
+        m = L.h_ntri[side];
+        const int take = m < cap ? m : cap;
+        if (take > 0) SVB_CUDA(cudaMemcpy(tri, L.tri[side], sizeof(int32_t) * 3 * (size_t)take, cudaMemcpyDeviceToHost));
+        used = 2;
+    } else if (L.h_order_ok[side] == 1) {
         m = delaunay_support_ordered(L.h_support, n, side, L.h_order + (size_t)side * d.maxS, tri, cap, c->scratch[0]);
         used = m >= 0;
     }
     if (m < 0) m = delaunay_support(L.h_support, n, side, tri, cap, c->scratch[0]);
     L.h_order_ok[0] = L.h_order_ok[1] = 0;
+    L.h_dd_done[0] = L.h_dd_done[1] = 0;
     if (n_tri_out) *n_tri_out = m;
     if (used_device_order) *used_device_order = used;
     return SVB_OK;
@@ -1061,7 +1177,12 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
     const size_t N = (size_t)d.N;
     const int C = c->chunk;
     const bool from_host = h_left != nullptr;
-    const bool want_D = (flags & SVB_OUT_DISPARITY) != 0, want_P = (flags & SVB_OUT_POINTS) != 0;
+    const bool want_D = (flags & SVB_OUT_DISPARITY) != 0, want_P = (flags & (SVB_OUT_POINTS | SVB_OUT_POINTS_FLOATDISP)) != 0;
+    if ((flags & SVB_OUT_POINTS) && (flags & SVB_OUT_POINTS_FLOATDISP)) {
+        set_error("batch: SVB_OUT_POINTS and SVB_OUT_POINTS_FLOATDISP share the point-cloud store; pick one");
+        return SVB_ERR_ARG;
+    }
+    c->points_float_disp = (flags & SVB_OUT_POINTS_FLOATDISP) != 0;
     const size_t DN = (size_t)d.DN;
     if (want_P && d.sub) {
         set_error("batch: point clouds with subsampling are only defined for the single-frame generatePointCloud path");
@@ -1116,7 +1237,7 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
                 hs.cv.wait(lk, [&] { return hs.issued > k || hs.stop; });
                 if (hs.stop) return;
             }
-            const int rc = stage_host(c, c->lanes[k % LANES], frames_of(k));
+            const int rc = stage_host(c, c->lanes[k % LANES], frames_of(k), c->lanes[k % LANES].unpacked);
             std::lock_guard<std::mutex> lk(hs.mu);
             if (rc != SVB_OK) {
                 hs.err = rc;
@@ -1269,7 +1390,7 @@ int svb_point_cloud_bgra(svb_context *c, const uint8_t *left_bgra, const uint8_t
     SVB_TRY(stage_events_prepare(c, 1));
     StageEvents *se = stage_events_of(c, 0);
     SVB_TRY(stage_a(c, L, L.img[0], L.img[1], 1, se));
-    SVB_TRY(stage_host(c, L, 1));
+    SVB_TRY(stage_host(c, L, 1, L.unpacked));
     c->stats.frames = 1;
     int rc = SVB_OK;
     if (L.h_nsupport[0] < 3) {
@@ -1280,10 +1401,18 @@ int svb_point_cloud_bgra(svb_context *c, const uint8_t *left_bgra, const uint8_t
         SVB_CUDA(cudaEventRecord(c->ev_pc[1], L.stream));
         SVB_TRY(launch_reproject(d, c->calib, L.Dlr, L.dmap, c->out_points, 1, L.stream));
     } else {
-        // generateDisparityMap(): Elas::process, then convertTo(CV_8UC1, 4.0) fused with publishPointCloud()'s kernel
-        SVB_TRY(stage_b(c, L, 1, nullptr, nullptr, se));
-        SVB_CUDA(cudaEventRecord(c->ev_pc[1], L.stream));
-        SVB_TRY(launch_reproject(d, c->calib, L.Dlr, L.dmap, c->out_points, 1, L.stream));
+        // generateDisparityMap(): Elas::process, then convertTo(CV_8UC1, 4.0) and publishPointCloud()'s kernel.  At full resolution
+        // both are fused with the last filters (k_post_fused.cu), so the "point-cloud part" of times_ms is the copy of the cloud only;
+        // with subsampling the reference projects the full-size buffer whose first (W/2)*(H/2) floats hold the map: stage by stage.
+        c->points_float_disp = false;
+        if (d.sub || !c->fused_post) {
+            SVB_TRY(stage_b(c, L, 1, nullptr, nullptr, se));
+            SVB_CUDA(cudaEventRecord(c->ev_pc[1], L.stream));
+            SVB_TRY(launch_reproject(d, c->calib, L.Dlr, L.dmap, c->out_points, 1, L.stream));
+        } else {
+            SVB_TRY(stage_b(c, L, 1, nullptr, c->out_points, se));
+            SVB_CUDA(cudaEventRecord(c->ev_pc[1], L.stream));
+        }
     }
     SVB_CUDA(cudaMemcpyAsync(points_out, c->out_points, N * 24, cudaMemcpyDeviceToHost, L.stream));
     SVB_CUDA(cudaEventRecord(c->ev_pc[2], L.stream));

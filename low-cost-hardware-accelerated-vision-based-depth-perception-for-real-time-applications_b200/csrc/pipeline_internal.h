@@ -39,6 +39,11 @@ struct Lane {
     int32_t *h_support = nullptr, *h_nsupport = nullptr, *h_tri[2] = {nullptr, nullptr}, *h_ntri = nullptr;
     int32_t *h_order = nullptr;     // [chunk][2][maxS] recursion order of the Delaunay stage (k_order.cu), written by the device
     int32_t *h_order_ok = nullptr;  // [chunk][2] 1 = h_order is valid for that list
+    int32_t *d_order = nullptr;     // device copy of h_order for the device divide-and-conquer (k_delaunay.cu)
+    int32_t *d_order_ok = nullptr;  // device copy of h_order_ok
+    int32_t *h_dd_done = nullptr;   // [chunk][2] mapped host: 1 = the device triangulated that list (its count is in h_ntri), 0 = host's turn
+    std::vector<uint8_t> host_made; // [chunk][2] this chunk's lists that the host stage produced (they need an H2D copy)
+    bool unpacked = false;          // layout of this chunk's triangle lists: frame f at f * (maxT + 8) (device stage) or packed back to back
     int first_frame = -1;           // batch paths: index of the chunk's first frame in the batch (per-frame status), else -1
 };
 
@@ -91,6 +96,10 @@ struct svb_context {
     svb_stats stats;
     bool stage_timing = false;
     bool single_stream = false;
+    bool fused_post = true;         // SVB_FUSED_POST=0: stage-by-stage mean / median / reproject kernels everywhere (k_post_fused.cu otherwise)
+    bool points_float_disp = false; // SVB_OUT_POINTS_FLOATDISP of the call in flight
+    bool delaunay_device = true;    // SVB_DELAUNAY_DEVICE=0: the divide-and-conquer runs on the host for every list (k_delaunay.cu otherwise)
+    int dd_cap = 2048;              // vertex capacity the device divide-and-conquer is launched with (shared memory); follows the lists seen
     bool gpu_order = true;  // SVB_GPU_ORDER=0: the host stage sorts and partitions the vertices itself
     std::vector<svb::StageEvents> stage_ev;  // one set per chunk of the call in flight
     std::mutex mu;
@@ -99,5 +108,7 @@ struct svb_context {
 
 namespace svb {
 // host Delaunay stage of one chunk whose support lists have arrived in lane L's pinned buffers (pipeline.cu)
-int stage_host(svb_context *c, Lane &L, int nf);
+// unpacked: the layout the device divide-and-conquer writes (frame f's lists at triangle f * (maxT + 8)); only lists the device left
+// (h_dd_done = 0) or that are injected are made here.  Packed: every list is made here, back to back (one H2D copy per side).
+int stage_host(svb_context *c, Lane &L, int nf, bool unpacked = false);
 }  // namespace svb

@@ -69,6 +69,7 @@ enum StageId {
     ST_DESCRIPTOR = 0,
     ST_SUPPORT_MATCH,
     ST_SUPPORT_FILTER,
+    ST_DELAUNAY_DEVICE,  // device half of the Delaunay stage: vertex order (k_order.cu) and the lower merge levels (k_delaunay.cu)
     ST_D2H_SUPPORT,
     ST_H2D_TRIANGLES,
     ST_PLANES,
@@ -81,6 +82,7 @@ enum StageId {
     ST_MEAN,
     ST_MEDIAN,
     ST_REPROJECT,
+    ST_POST_FUSED,  // adaptive mean + median + u8 + reprojection in one kernel (k_post_fused.cu); the three stages before it are then empty
     ST_COUNT
 };
 
@@ -90,7 +92,15 @@ int launch_descriptor(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg
 // *_rows variants restrict a stage to image rows [row0, row1) / lattice rows [vc0, vc1): the row-band split (band_split.cu)
 int launch_descriptor_rows(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, int row0, int row1, cudaStream_t s);  // d.sub: even rows only
 // k_order.cu: recursion order of the host Delaunay stage for every (frame, side); h_order [nf][2][maxS], h_ok [nf][2] (mapped host memory)
-int launch_delaunay_order(const Dims &d, const int32_t *support, const int32_t *nsupport, int32_t *h_order, int32_t *h_ok, int nf, cudaStream_t s);
+// d_order / d_ok: optional device copies (same layout) for launch_delaunay_levels
+int launch_delaunay_order(const Dims &d, const int32_t *support, const int32_t *nsupport, int32_t *h_order, int32_t *h_ok, int32_t *d_order,
+                          int32_t *d_ok, int nf, cudaStream_t s);
+// k_delaunay.cu: the divide-and-conquer itself on the device, one CTA per (frame, side); lists of up to cap_n (<= 4096) points whose
+// order is usable are triangulated into tri1 / tri2 at frame f * (maxT + 8) (h_ntri = count, h_done = 1, mapped host memory),
+// the others get h_done = 0 and are left to the host stage
+size_t delaunay_levels_smem(int cap_n);
+int launch_delaunay_levels(const Dims &d, const int32_t *support, const int32_t *nsupport, const int32_t *order, const int32_t *order_ok,
+                           int32_t *tri1, int32_t *tri2, int32_t *h_ntri, int32_t *h_done, int nf, int cap_n, cudaStream_t s);
 // k_support.cu
 int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int nf,
                          cudaStream_t s);
@@ -129,12 +139,18 @@ int launch_median(const Dims &d, float *D, float *tmp, int nimg, cudaStream_t s)
 // k_ccl.cu
 int launch_remove_small_segments(const Dims &d, const svb_params &p, float *D, int32_t *labels, int32_t *sizes, int nimg, cudaStream_t s);
 // k_reproject.cu
+struct Calib;
+// k_post_fused.cu: adaptive mean -> median -> final map (+ u8 map + point cloud) in one pass; full-resolution maps only
+int launch_post_fused(const Dims &d, const svb_params &p, int mean_mode, const Calib &cal, const float *Din, float *Dout, uint8_t *dmap,
+                      double *points, int float_disp, int nimg, cudaStream_t s);
 struct Calib {
     double Q[16];  // row-major 4x4 (cv::stereoRectify's Q, stereo_vision.cu:447)
     double XR[9];  // row-major 3x3
     double XT[3];
 };
 int launch_reproject(const Dims &d, const Calib &c, const float *D, uint8_t *dmap, double *points, int nf, cudaStream_t s);
+// the float disparity itself enters Q (invalid pixels as 0): SVB_OUT_POINTS_FLOATDISP outside the fused kernel
+int launch_reproject_float(const Dims &d, const Calib &c, const float *D, double *points, int nf, cudaStream_t s);
 int launch_reproject_u8(const Calib &c, const uint8_t *dmap, double *points, int W, int H, cudaStream_t s);
 // k_convert.cu
 int launch_bgra_to_gray(const uint8_t *bgra, uint8_t *gray, int n, cudaStream_t s);

@@ -110,3 +110,19 @@ def reproject_oracle(D, Q, XR, XT):
         XT = np.asarray(XT, np.float64).reshape(3)
         pts = np.stack([XR[j, 0] * X + XR[j, 1] * Y + XR[j, 2] * Z + XT[j] for j in range(3)], 1)
     return d8, pts
+
+
+def reproject_float_oracle(D, Q, XR, XT):
+    """SVB_OUT_POINTS_FLOATDISP: the formula of projectParallel (stereo_vision.cu:188-212) with the filtered float disparity itself
+    (invalid pixels as 0) in place of the u8 value -- new relative to the reference, so numpy is the oracle."""
+    H, W = D.shape
+    x = np.tile(np.arange(W, dtype=np.float64), H)
+    y = np.repeat(np.arange(H, dtype=np.float64), W)
+    d = np.maximum(D.astype(np.float32), np.float32(0)).reshape(-1).astype(np.float64)
+    Q = np.asarray(Q, np.float64)
+    pos = [Q[j, 0] * x + Q[j, 1] * y + Q[j, 2] * d + Q[j, 3] for j in range(4)]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        X, Y, Z = pos[0] / pos[3], pos[1] / pos[3], pos[2] / pos[3]
+        XR = np.asarray(XR, np.float64).reshape(3, 3)
+        XT = np.asarray(XT, np.float64).reshape(3)
+        return np.stack([XR[j, 0] * X + XR[j, 1] * Y + XR[j, 2] * Z + XT[j] for j in range(3)], 1)

@@ -140,6 +140,25 @@ def test_host_recursion_on_a_given_vertex_order(svb, ref, seed, n):
         svb.delaunay_ordered(s, 0, np.zeros(len(s), np.int32) + len(s))  # not a permutation
 
 
+@pytest.mark.parametrize("seed,n", [(11, 3), (12, 4), (13, 5), (14, 6), (15, 7), (16, 8), (17, 9), (18, 13), (19, 50), (20, 401), (21, 1954), (22, 4096)])
+def test_level_synchronous_delaunay_matches_reference(svb, ref, seed, n):
+    """The divide-and-conquer as the DEVICE runs it (k_delaunay.cu): bottom-up, level by level, every node of a level built
+    independently straight into its final records (a subtree of c vertices owns 2c - 2 records, known in advance), in 16-bit
+    records; host_levels = how many top levels are left to the host recursion.  Restated on the host from the same source
+    (delaunay_mesh.h) -- must give the reference's triangle list, order and corner rotation included, for every split."""
+    s = lattice_support(np.random.default_rng(seed), n)
+    order = kd_order(s[:, 0].astype(np.int64), s[:, 1].astype(np.int64))
+    want = ref.delaunay(s, 0)
+    for host_levels in (0, 1, 2, 3, 5, 20):
+        got = svb.delaunay_levels(s, 0, order, host_levels)
+        assert np.array_equal(got, want), "n %d host_levels %d" % (n, host_levels)
+    # the right image (x = u - d), when it holds no duplicate coordinates
+    xr = (s[:, 0] - s[:, 2]).astype(np.int64)
+    if len(set(zip(xr.tolist(), s[:, 1].tolist()))) == len(s):
+        order_r = kd_order(xr, s[:, 1].astype(np.int64))
+        assert np.array_equal(svb.delaunay_levels(s, 1, order_r, 0), ref.delaunay(s, 1))
+
+
 def test_host_delaunay_degenerate_inputs(svb, ref):
     # all collinear (one lattice column): Triangle emits no triangle
     col = np.array([(50, 5 * i, 3) for i in range(1, 30)], np.int32)

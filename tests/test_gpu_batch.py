@@ -111,7 +111,7 @@ def test_batch_with_a_textureless_frame(svb):
         for i in (0, 1, 3):
             D1, _ = one.process(L[i], R[i])
             assert np.array_equal(ctx.batch_disparity(i), D1)
-        assert (ctx.batch_disparity(2) < 0).all()  # nothing matched: every pixel invalid
+        assert (ctx.batch_disparity(2) == 0).all()  # the driver's zero-initialised map, untouched (elas_b200.h: svb_batch_frame_support)
     finally:
         ctx.close()
         one.close()
@@ -137,12 +137,17 @@ def test_batch_is_identical_across_stream_modes_lanes_and_vertex_order(svb, gold
             ctx.set_single_stream(single_stream)
             ctx.batch_upload(Ls, Rs)
             ctx.batch_run(n, svb.OUT_DISPARITY | svb.OUT_POINTS)
+            st = ctx.stats()
+            if env.get("SVB_GPU_ORDER") == "0" or env.get("SVB_DELAUNAY_DEVICE") == "0":
+                assert st["delaunay_lists_device"] == 0 and st["delaunay_lists_host"] == 2 * n  # every list made by the host stage
+            else:
+                assert st["delaunay_lists_device"] + st["delaunay_lists_host"] == 2 * n and st["delaunay_lists_device"] >= n  # k_delaunay.cu ran
             return [ctx.batch_disparity(i) for i in range(n)], [ctx.batch_points(i) for i in (0, 7, n - 1)]
         finally:
             ctx.close()
 
     want = run(False, {})
-    for single, env in ((False, {}), (True, {}), (False, {"SVB_LANES": "6"}), (False, {"SVB_GPU_ORDER": "0"})):
+    for single, env in ((False, {}), (True, {}), (False, {"SVB_LANES": "6"}), (False, {"SVB_GPU_ORDER": "0"}), (False, {"SVB_DELAUNAY_DEVICE": "0"})):
         got = run(single, env)
         assert all(np.array_equal(a, b) for a, b in zip(got[0], want[0])), (single, env)
         assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got[1], want[1])), (single, env)
@@ -175,3 +180,59 @@ def test_batch_frame_without_support_points(svb):
     finally:
         ctx.close()
         one.close()
+
+
+@pytest.mark.parametrize("setting", ["PIPELINE", "ROBOTICS", "MIDDLEBURY"])
+def test_fused_post_chain_equals_stage_by_stage(svb, golden_meta, monkeypatch, setting):
+    """k_post_fused.cu (adaptive mean + median + final map + u8 + reprojection in one kernel) against the stage-by-stage kernels
+    (SVB_FUSED_POST=0) on the same frames: final maps and point clouds bit for bit, ragged sizes included; all three filter
+    combinations (mean + median, mean only, median only)."""
+    for (W, H, n) in ((1242, 375, 5), (333, 127, 3), (640, 241, 2)):
+        L, R = make_batch(svb, n, W, H)
+        p = svb.default_params(getattr(svb, setting), postprocess_only_left=1)
+        Q, XR, XT = np.array(golden_meta["Q"]), np.array(golden_meta["XR"]), np.array(golden_meta["XT"])
+        outs = []
+        for fused in ("1", "0"):
+            monkeypatch.setenv("SVB_FUSED_POST", fused)
+            ctx = svb.Context(p, W, H, chunk=2)
+            try:
+                ctx.set_calibration(Q, XR, XT)
+                ctx.batch_upload(L, R)
+                ctx.batch_run(n, svb.OUT_DISPARITY | svb.OUT_POINTS)
+                outs.append(([ctx.batch_disparity(i) for i in range(n)], [ctx.batch_points(i) for i in range(n)], ctx.stats()["kernel_launches"]))
+            finally:
+                ctx.close()
+        monkeypatch.delenv("SVB_FUSED_POST")
+        assert outs[0][2] < outs[1][2]  # fewer launches: the fused kernel really ran
+        for i in range(n):
+            assert np.array_equal(outs[0][0][i], outs[1][0][i]), (W, H, i)
+            assert np.array_equal(outs[0][1][i], outs[1][1][i], equal_nan=True), (W, H, i)
+
+
+def test_float_disparity_point_cloud(svb, golden_meta, monkeypatch):
+    """SVB_OUT_POINTS_FLOATDISP: the float disparity enters Q without the 4x u8 quantisation that clips at 63.75 px.
+    Fused and stage-by-stage kernels against the numpy formula; the u8 drop-in path is unchanged next to it."""
+    W, H, n = 640, 240, 3
+    L, R = make_batch(svb, n, W, H)
+    Q, XR, XT = np.array(golden_meta["Q"]), np.array(golden_meta["XR"]), np.array(golden_meta["XT"])
+    p = svb.default_params(svb.PIPELINE)
+    for fused in ("1", "0"):
+        monkeypatch.setenv("SVB_FUSED_POST", fused)
+        ctx = svb.Context(p, W, H, chunk=2)
+        try:
+            ctx.set_calibration(Q, XR, XT)
+            ctx.batch_upload(L, R)
+            ctx.batch_run(n, svb.OUT_DISPARITY | svb.OUT_POINTS_FLOATDISP)
+            for i in range(n):
+                D1 = ctx.batch_disparity(i)
+                want = parity.reproject_float_oracle(D1, Q, XR, XT)
+                got = ctx.batch_points(i)
+                assert np.array_equal(got, want, equal_nan=True), (fused, i)
+            with pytest.raises(svb.SvbError):
+                ctx.batch_run(n, svb.OUT_POINTS | svb.OUT_POINTS_FLOATDISP)
+            ctx.batch_run(n, svb.OUT_DISPARITY | svb.OUT_POINTS)
+            _, want8 = parity.reproject_oracle(ctx.batch_disparity(0), Q, XR, XT)
+            assert np.array_equal(ctx.batch_points(0), want8, equal_nan=True)
+        finally:
+            ctx.close()
+    monkeypatch.delenv("SVB_FUSED_POST")

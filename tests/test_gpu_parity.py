@@ -366,14 +366,17 @@ def test_device_vertex_order_feeds_the_same_triangulation(svb, ref):
     ctx = svb.Context(svb.default_params(svb.MIDDLEBURY), 1242, 375)
     try:
         for seed, n, expect_device in [(1, 3, True), (2, 4, True), (3, 7, True), (4, 50, True), (5, 400, True), (6, 2500, True),
-                                       (8, 4096, True), (7, 6000, False)]:
+                                       (8, 4096, True), (9, 5, True), (10, 6, True), (11, 9, True), (12, 13, True),
+                                       (13, 1001, True), (14, 1954, True), (7, 6000, False)]:
             s = H.lattice_support(np.random.default_rng(seed), n)
             for side in (0, 1):
                 want = ref.delaunay(s, side)
                 got, used = ctx.delaunay_pipeline(s, side)
                 assert np.array_equal(got, want), "seed %d n %d side %d" % (seed, n, side)
                 if side == 0 or not expect_device:
-                    assert used == (expect_device and len(s) <= 4096), (seed, n, side, used)
+                    assert (used > 0) == (expect_device and len(s) <= 4096), (seed, n, side, used)
+                    if used:
+                        assert used == 2, (seed, n, side, used)  # the whole divide-and-conquer ran on the device (k_delaunay.cu)
         # duplicates in the right image: flagged by the device, resolved by the host like the reference does
         dup = np.array([(100, 50, 10), (95, 50, 5), (200, 80, 20), (60, 120, 1), (300, 20, 9), (110, 50, 20)], np.int32)
         got, used = ctx.delaunay_pipeline(dup, 1)
