@@ -164,6 +164,9 @@ int svb_stage_reproject(svb_context *ctx, const float *D, const double *Q16, con
 int svb_set_calibration(svb_context *ctx, const double *Q16, const double *XR9, const double *XT3);
 /* copy n frames (tight W*H u8 each) into the device-resident input store */
 int svb_batch_upload(svb_context *ctx, const uint8_t *left, const uint8_t *right, int n_frames);
+/* the same from BGRA frames (height x width x 4 bytes each, what sv.py passes to generatePointCloud, sv.py:185-188): uploaded in groups
+ * and converted on the device like cv::cvtColor(BGRA2GRAY) (stereo_vision.cu:346-347) */
+int svb_batch_upload_bgra(svb_context *ctx, const uint8_t *left_bgra, const uint8_t *right_bgra, int n_frames);
 /* run the whole path on the resident inputs; results stay resident.  flags: SVB_OUT_* */
 /* SVB_OUT_POINTS: the drop-in point cloud (u8 disparity x4 as in generateDisparityMap, stereo_vision.cu:324, clips at 63.75 px);
  * SVB_OUT_POINTS_FLOATDISP (opt-in, instead of SVB_OUT_POINTS): the filtered FLOAT disparity enters Q, no quantisation and no clip --
@@ -175,6 +178,10 @@ int svb_batch_run(svb_context *ctx, int n_frames, int flags);
  * delivers in that case -- disparity 0 everywhere (the driver's maps are zero-initialised, stereo_vision.cu:311-312) and
  * the point cloud of that map -- and it is counted in svb_stats::frames_failed. */
 int svb_batch_frame_support(svb_context *ctx, int32_t *nsupport_out, int n_frames);
+/* Zero-copy access to the resident results of the last batch call: DEVICE pointers, D1 = n_frames x H x W float,
+ * points = n_frames x H x W x 3 double, on CUDA device *device; NULL for an output the call did not produce.  Valid until the next
+ * batch call on this context. */
+int svb_batch_device_ptrs(svb_context *ctx, float **D1_dev, double **points_dev, int *n_frames, int *device);
 int svb_batch_download_disparity(svb_context *ctx, int frame, float *D1_out);
 int svb_batch_download_points(svb_context *ctx, int frame, double *points_out);
 /* end to end from pinned or pageable HOST buffers: H2D inputs, run, D2H outputs, all inside */

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libelas_b200.so")
+# SVB_LIB_DIR selects another build of the same library (lib_guard: the bounds-asserting build, csrc/Makefile GUARD=1)
+LIB_PATH = os.path.join(os.environ.get("SVB_LIB_DIR") or os.path.join(PKG_DIR, "lib"), "libelas_b200.so")
 
 ROBOTICS, MIDDLEBURY, PIPELINE = 0, 1, 2
 OUT_DISPARITY, OUT_POINTS, OUT_POINTS_FLOATDISP = 1, 2, 4
@@ -136,6 +137,8 @@ def load():
         "svb_stage_reproject": [vp, vp, vp, vp, vp, vp, vp],
         "svb_set_calibration": [vp, vp, vp, vp],
         "svb_batch_upload": [vp, vp, vp, C.c_int],
+        "svb_batch_upload_bgra": [vp, vp, vp, C.c_int],
+        "svb_batch_device_ptrs": [vp, vp, vp, vp, vp],
         "svb_batch_run": [vp, C.c_int, C.c_int],
         "svb_batch_frame_support": [vp, vp, C.c_int],
         "svb_batch_download_disparity": [vp, C.c_int, vp],
@@ -595,6 +598,19 @@ class Context:
         n = left.shape[0]
         self._chk(self.lib.svb_batch_upload(self.h, _ptr(left), _ptr(right), n))
         return n
+
+    def batch_upload_bgra(self, left_bgra, right_bgra):
+        left_bgra = np.ascontiguousarray(left_bgra, np.uint8)
+        right_bgra = np.ascontiguousarray(right_bgra, np.uint8)
+        n = left_bgra.shape[0]
+        self._chk(self.lib.svb_batch_upload_bgra(self.h, _ptr(left_bgra), _ptr(right_bgra), n))
+        return n
+
+    def batch_device_ptrs(self):
+        """(D1 device pointer or 0, points device pointer or 0, frames, device) of the last batch call's resident results."""
+        d1, pts, n, dev = C.c_void_p(0), C.c_void_p(0), C.c_int(0), C.c_int(0)
+        self._chk(self.lib.svb_batch_device_ptrs(self.h, C.byref(d1), C.byref(pts), C.byref(n), C.byref(dev)))
+        return d1.value or 0, pts.value or 0, n.value, dev.value
 
     def batch_run(self, n, flags=OUT_POINTS):
         self._chk(self.lib.svb_batch_run(self.h, n, flags))

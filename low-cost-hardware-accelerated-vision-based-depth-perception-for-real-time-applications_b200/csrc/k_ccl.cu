@@ -23,8 +23,10 @@ namespace {
 __device__ __forceinline__ bool similar(float a, float b, float thr) { return a >= 0.f && b >= 0.f && fabsf(__fsub_rn(a, b)) <= thr; }
 
 __device__ __forceinline__ int find_root(const int32_t *labels, int i) {
+    SVB_GUARD_ASSERT(i >= 0);
     int p = labels[i];
     while (p != i) {
+        SVB_GUARD_ASSERT(p >= 0 && p < i);  // labels only ever point towards smaller indices
         i = p;
         p = labels[i];
     }
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(2 * TW) k_ccl_tile(const float *__restrict__ D
             const float dl = sD[idx - 1], dul = sD[idx - TW - 1];
             if (similar(d, dl, thr) && similar(du, dul, thr) && similar(dl, dul, thr)) continue;
         }
+        SVB_GUARD_ASSERT(idx - TW >= 0 && idx < TH * TW && sL[idx] >= 0 && sL[idx - TW] >= 0);
         unite(sL, idx, idx - TW);
     }
     __syncthreads();
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(256) k_ccl_borders(const float *__restrict__ D
     } else {
         return;
     }
+    SVB_GUARD_ASSERT(p >= 0 && p < W * H && q >= 0 && q < W * H && labels[p] >= 0 && labels[q] >= 0);
     unite(labels, labels[p], labels[q]);  // both pixels are valid: their labels are local roots
 }
 

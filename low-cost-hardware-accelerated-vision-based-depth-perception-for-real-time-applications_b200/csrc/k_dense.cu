@@ -30,6 +30,7 @@ struct DenseArgs {
     int Dw, DN, shift;  // disparity map width / size and log2 of the pixel step (1 with subsampling: map pixel (x,y) = image (2x,2y))
     unsigned grid_magic;  // ceil(2^32 / grid_size)
     int P[8];
+    const uint8_t *desc_lo[2], *desc_hi[2];  // the descriptor arenas including their guard bands (range asserts of the guard build)
     unsigned bias;  // Dims::cost_bias: keeps SAD + P >= 0 in the unsigned key
     unsigned long long *evals;  // COUNT variant only: number of evaluated hypotheses (elas.cpp:759-793)
 };
@@ -44,6 +45,10 @@ __device__ __forceinline__ unsigned sad16_acc(const uint4 &a, const uint4 &b, un
 }
 
 // base + idx as one IMAD.WIDE (FMA pipe) instead of a 4-instruction 64-bit LEA sequence on the ALU pipe
+// guard build: a descriptor load must stay inside the arena (frames + zero-filled guard bands)
+#define SVB_GUARD_DESC(ptr, side) \
+    SVB_GUARD_ASSERT((const uint8_t *)(ptr) >= a.desc_lo[side] && (const uint8_t *)(ptr) + 16 <= a.desc_hi[side])
+
 __device__ __forceinline__ const uint4 *desc_at(const uint4 *base, int idx) {
     unsigned long long r;
     asm("mad.wide.s32 %0, %1, 16, %2;" : "=l"(r) : "r"(idx), "l"(base));
@@ -102,6 +107,8 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     const int gy = a.grid_size == 1 ? v : (int)__umulhi((unsigned)v, a.grid_magic);    // u, v >= 0: equals the float floor (elas.cpp:744-745)
     const uint32_t *cell = a.grid[SIDE] + (size_t)uf * (unsigned)(a.gw * a.gh * a.gwords) + (unsigned)((gy * a.gw + gx) * a.gwords);
     const int o = in ? __ldg(a.owner[SIDE] + fDN + (unsigned)pix) : -1;
+    SVB_GUARD_DESC(desc_at(own, rowW + uc), SIDE);
+    SVB_GUARD_ASSERT(!in || (pix >= 0 && pix < a.DN));
     const uint4 c = __ldg(desc_at(own, rowW + uc));
     uint4 m4_first = __ldg(reinterpret_cast<const uint4 *>(cell));
     const uint4 k128 = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
@@ -145,6 +152,8 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
                 uni ^= bit1;
                 const int d0 = (w << 5) + (31 - __clz(bit0));
                 const int d1 = bit1 ? (w << 5) + (31 - __clz(bit1)) : d0;
+                SVB_GUARD_DESC(desc_at(po, SIDE ? d0 : -d0), SIDE ^ 1);
+                SVB_GUARD_DESC(desc_at(po, SIDE ? d1 : -d1), SIDE ^ 1);
                 const uint4 o0 = __ldg(desc_at(po, SIDE ? d0 : -d0));
                 const uint4 o1 = __ldg(desc_at(po, SIDE ? d1 : -d1));
                 const unsigned cand0 = (sad16_acc(c, o0, a.bias) << 13) + (unsigned)d0;
@@ -169,7 +178,10 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
             const int d = (int)((unsigned)d_plane + (unsigned)k);
             okb[k + RADIUS] = (unsigned)(d - lo3) <= span;
             ob[k + RADIUS] = make_uint4(0u, 0u, 0u, 0u);
-            if (okb[k + RADIUS]) ob[k + RADIUS] = __ldg(pb + (SIDE ? k : -k));
+            if (okb[k + RADIUS]) {
+                SVB_GUARD_DESC(pb + (SIDE ? k : -k), SIDE ^ 1);
+                ob[k + RADIUS] = __ldg(pb + (SIDE ? k : -k));
+            }
             if (COUNT) n_hyp += okb[k + RADIUS] ? 1u : 0u;
         }
 #pragma unroll
@@ -187,6 +199,7 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
             if (COUNT) n_hyp += ok ? 1u : 0u;
             const int ds = ok ? d : 0;
             const unsigned seed = a.bias + ((unsigned)a.P[k < 0 ? -k : k] & prior_on);
+            SVB_GUARD_DESC(desc_at(po, SIDE ? ds : -ds), SIDE ^ 1);
             const unsigned cost = sad16_acc(c, __ldg(desc_at(po, SIDE ? ds : -ds)), seed);
             const unsigned cand = (cost << 13) + (0x1000u + (unsigned)ds);
             key = min(key, ok ? cand : 0xFFFFFFFFu);
@@ -247,6 +260,10 @@ int launch_dense_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, 
     a.plane_radius = d.plane_radius;
     for (int i = 0; i < 8; i++) a.P[i] = d.P[i];
     a.bias = (unsigned)d.cost_bias;
+    for (int sd = 0; sd < 2; sd++) {
+        a.desc_lo[sd] = a.desc[sd] - d.desc_pad;
+        a.desc_hi[sd] = a.desc[sd] + (size_t)nf * d.N * 16 + d.desc_pad;
+    }
     a.row0 = row0;
     a.Dw = d.Dw;
     a.DN = d.DN;

@@ -81,10 +81,12 @@ __device__ __forceinline__ void gap_line(float *line, int stride, int n, int *pr
         const int nx = above ? (k * 32 + __ffs(above) - 1) : ncarry;
         if (u < n && !valid) {
             const int p = prev[u];
+            SVB_GUARD_ASSERT(p >= -1 && p < u && nx < n && (nx < 0 || nx > u));
             float fill = 0.f;
             bool do_fill = false;
             if (p >= 0 && nx >= 0) {
                 if (nx - p - 1 <= gap_width) {
+                    SVB_GUARD_ASSERT(p >= 0 && p < n && nx >= 0 && nx < n);
                     fill = gap_fill_value(line[p * stride], line[nx * stride]);
                     do_fill = true;
                 }

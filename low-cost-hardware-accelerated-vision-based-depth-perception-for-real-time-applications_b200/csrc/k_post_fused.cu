@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(PF_THREADS, TH == 32 ? 4 : 2) k_post_fused(con
             const int r = i >> 5, g = i & 31;
             if (g == 0 || g == 31) continue;  // centres j = 4g .. 4g+3 need taps j-4 .. j+6
             const float *row = A + r * PF_SW + 4 * g;
+            SVB_GUARD_ASSERT(row - 4 >= A && row + 8 <= A + RH * PF_SW);
             const float4 lo = *reinterpret_cast<const float4 *>(row - 4), mid = *reinterpret_cast<const float4 *>(row),
                          hi = *reinterpret_cast<const float4 *>(row + 4);
             // D_copy (elas.cpp:1313-1316: invalid -> -10) is the identity here: every negative value of a map that went through the
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(PF_THREADS, TH == 32 ? 4 : 2) k_post_fused(con
             const int u = x0 - 8 + j, r0 = 4 * rg, v0 = y0 - 8 + r0;
             if (u < 3 || u >= W - 3) continue;
             float x[11];
+            SVB_GUARD_ASSERT(r0 - 4 >= 0 && r0 + 6 < RH);
 #pragma unroll
             for (int k = 0; k < 11; k++) x[k] = B[(r0 - 4 + k) * PF_SW + j];
             float rr;
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(PF_THREADS, TH == 32 ? 4 : 2) k_post_fused(con
         for (int k = 0; k < 4; k++) res[k] = A[(r0 + k) * PF_SW + j];
         if (a.has_median && col_in) {
             float x[10];
+            SVB_GUARD_ASSERT(r0 - 3 >= 4 && r0 + 6 < RH - 4);
 #pragma unroll
             for (int k = 0; k < 10; k++) x[k] = B[(r0 - 3 + k) * PF_SW + j];
 #pragma unroll
@@ -258,9 +261,10 @@ int launch_post_fused(const Dims &d, const svb_params &p, int mean_mode, const C
     a.has_median = p.filter_median ? 1 : 0;
     a.float_disp = float_disp;
     a.cal = cal;
-    // tile height: 64 rows (halo overhead 80 / 64) unless the map is so small that 32-row tiles are needed to fill the GPU
+    // 32-row tiles: four CTAs per SM.  64-row tiles (SVB_PF_TH=64) execute 10 % fewer instructions (halo 80/64 instead of 48/32) but only
+    // two CTAs fit an SM, and the kernel is bound by issue latency, not by the instruction count: 11.3 vs 9.3 us per frame measured.
     static const int th_env = getenv("SVB_PF_TH") ? atoi(getenv("SVB_PF_TH")) : 0;
-    const bool tall = th_env ? th_env == 64 : (long long)nimg * d.H * d.W >= 4ll * 1000 * 1000;
+    const bool tall = th_env == 64;
     if (mean_mode == SVB_MEAN_TRUE_ABS) return tall ? launch_tile<1, 64>(a, nimg, s) : launch_tile<1, 32>(a, nimg, s);
     return tall ? launch_tile<0, 64>(a, nimg, s) : launch_tile<0, 32>(a, nimg, s);
 }

@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(128) k_raster(const int32_t *__restrict__ supp
     if (i >= ntri_all[2 * f + side]) return;
     const int32_t *support = support_all + (size_t)f * maxS * 3;
     const int32_t *tri = (side ? tri2_all : tri1_all) + ((size_t)trioff_all[f] + i) * 3;
+    SVB_GUARD_ASSERT(tri[0] >= 0 && tri[0] < maxS && tri[1] >= 0 && tri[1] < maxS && tri[2] >= 0 && tri[2] < maxS);
     int32_t *owner = (side ? owner2_all : owner1_all) + (size_t)f * Dw * Dh;  // owner map has the disparity map's size
 
     float tu[3], tv[3];
@@ -244,10 +245,16 @@ __global__ void __launch_bounds__(128) k_raster(const int32_t *__restrict__ supp
             // rows are clipped to [row0, row1): the whole image, or this device's band in the row-band split
             const int v_lo = max(max(min(v_1, v_2), 0), row0), v_hi = min(min(max(v_1, v_2), H), row1);
             if (!sub) {
-                for (int v = v_lo; v < v_hi; v++) atomicMax(owner + (size_t)v * W + u, i);
+                for (int v = v_lo; v < v_hi; v++) {
+                    SVB_GUARD_ASSERT(u >= 0 && u < W && v >= 0 && v < H);
+                    atomicMax(owner + (size_t)v * W + u, i);
+                }
             } else if ((u >> 1) < Dw) {
                 for (int v = (v_lo + 1) & ~1; v < v_hi; v += 2)
-                    if ((v >> 1) < Dh) atomicMax(owner + (size_t)(v >> 1) * Dw + (u >> 1), i);
+                    if ((v >> 1) < Dh) {
+                        SVB_GUARD_ASSERT(u >= 0 && v >= 0);
+                        atomicMax(owner + (size_t)(v >> 1) * Dw + (u >> 1), i);
+                    }
             }
         }
     }

@@ -50,7 +50,10 @@ __device__ __forceinline__ unsigned sad16_acc(const uint4 &a, const uint4 &b, un
 // One pass over the patch: every lane holds one candidate (u, v) of image `own`; returns its disparity or -1.
 template <bool right_image, bool COUNT>
 __device__ __forceinline__ int match_pass(const uint4 *__restrict__ own, const uint4 *__restrict__ oth, int u, int v, bool has, int W, int H,
-                                          int disp_min, int disp_max, int support_texture, float support_threshold, unsigned &n_hyp) {
+                                          int disp_min, int disp_max, int support_texture, float support_threshold, unsigned &n_hyp,
+                                          const uint4 *oth_lo, const uint4 *oth_hi) {
+    (void)oth_lo;
+    (void)oth_hi;
     // candidate validity and disparity range (elas.cpp:279,296-300,318-327)
     bool ok = has && u >= 5 && u <= W - 6 && v >= 5 && v <= H - 6;
     if (ok) ok = (int)texture16(__ldg(own + (size_t)v * W + u)) >= support_texture;
@@ -86,10 +89,12 @@ __device__ __forceinline__ int match_pass(const uint4 *__restrict__ own, const u
     // rounded up to a multiple of 4; the extra steps evaluate out-of-range hypotheses (rejected by drel > span) on
     // columns that still lie inside the frame (row v+2 <= H-4, so a few descriptors past its end are the next row).
     const uint4 *pt = ot + wxlo, *pb = ob + wxlo;
+    SVB_GUARD_ASSERT(pt - 2 >= oth_lo && pb + 2 <= oth_hi);
     uint4 t0 = __ldg(pt - 2), t1 = __ldg(pt - 1), t2 = __ldg(pt), t3 = __ldg(pt + 1);
     uint4 b0 = __ldg(pb - 2), b1 = __ldg(pb - 1), b2 = __ldg(pb), b3 = __ldg(pb + 1);
 #define SVB_MATCH_STEP(TK, BK, OFF)                                                        \
     {                                                                                      \
+        SVB_GUARD_ASSERT(pt + 2 + OFF >= oth_lo && pb + 2 + OFF + 1 <= oth_hi);            \
         const uint4 tn = __ldg(pt + 2 + OFF), bn = __ldg(pb + 2 + OFF);                    \
         unsigned e = sad16_acc(a0, TK, 0u);                                                \
         e = sad16_acc(a1, tn, e);                                                          \
@@ -127,7 +132,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(SM_WARPS * 32) k_support_match(const uint8_t *__restrict__ desc1, const uint8_t *__restrict__ desc2,
                                                                  int16_t *__restrict__ dcan_raw, int W, int H, int cw, int ch, int step,
                                                                  int disp_min, int disp_max, int support_texture, float support_threshold,
-                                                                 int lr_threshold, int vc0, int vc1, unsigned long long *evals) {
+                                                                 int lr_threshold, int vc0, int vc1, unsigned long long *evals, size_t pad, int nf) {
     // lattice rows vc0 .. vc1-1 (1 .. ch-1 for a whole frame; a sub-range in the row-band split)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int pu = (cw - 1 + PATCH_U - 1) / PATCH_U, pv = (vc1 - vc0 + PATCH_V - 1) / PATCH_V;
@@ -145,9 +150,13 @@ __global__ void __launch_bounds__(SM_WARPS * 32) k_support_match(const uint8_t *
 
     // forward: candidate in the left image, search the right image (elas.cpp:403)
     unsigned n_hyp = 0u;
-    const int d = match_pass<false, COUNT>(d1, d2, u, v, has, W, H, disp_min, disp_max, support_texture, support_threshold, n_hyp);
+    // arenas including their guard bands (range asserts of the guard build only)
+    const uint4 *lo1 = reinterpret_cast<const uint4 *>(desc1 - pad), *hi1 = reinterpret_cast<const uint4 *>(desc1 + (size_t)nf * W * H * 16 + pad);
+    const uint4 *lo2 = reinterpret_cast<const uint4 *>(desc2 - pad), *hi2 = reinterpret_cast<const uint4 *>(desc2 + (size_t)nf * W * H * 16 + pad);
+    const int d = match_pass<false, COUNT>(d1, d2, u, v, has, W, H, disp_min, disp_max, support_texture, support_threshold, n_hyp, lo2, hi2);
     // backward: the match (u-d, v) as a candidate of the right image, search the left image (elas.cpp:406)
-    const int dback = match_pass<true, COUNT>(d2, d1, u - d, v, has && d >= 0, W, H, disp_min, disp_max, support_texture, support_threshold, n_hyp);
+    const int dback = match_pass<true, COUNT>(d2, d1, u - d, v, has && d >= 0, W, H, disp_min, disp_max, support_texture, support_threshold, n_hyp, lo1,
+                                              hi1);
     if (COUNT) {
         const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, n_hyp);
         if (lane == 0) atomicAdd(evals, (unsigned long long)tot);
@@ -454,10 +463,10 @@ int launch_support_match_rows(const Dims &d, const svb_params &p, const uint8_t 
     dim3 grid((patches + SM_WARPS - 1) / SM_WARPS, nf);
     if (d.evals)
         k_support_match<true><<<grid, SM_WARPS * 32, 0, s>>>(desc1, desc2, dcan_raw, d.W, d.H, d.cw, d.ch, d.step, p.disp_min, p.disp_max,
-                                                             p.support_texture, p.support_threshold, p.lr_threshold, vc0, vc1, d.evals);
+                                                             p.support_texture, p.support_threshold, p.lr_threshold, vc0, vc1, d.evals, d.desc_pad, nf);
     else
         k_support_match<false><<<grid, SM_WARPS * 32, 0, s>>>(desc1, desc2, dcan_raw, d.W, d.H, d.cw, d.ch, d.step, p.disp_min, p.disp_max,
-                                                              p.support_texture, p.support_threshold, p.lr_threshold, vc0, vc1, nullptr);
+                                                              p.support_texture, p.support_threshold, p.lr_threshold, vc0, vc1, nullptr, d.desc_pad, nf);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

@@ -86,6 +86,7 @@ int make_dims(const svb_params &p, int W, int H, Dims *out) {
         minP = d.P[delta] < minP ? d.P[delta] : minP;
         maxP = d.P[delta] > maxP ? d.P[delta] : maxP;
     }
+    d.desc_pad = ((size_t)p.disp_max + W + 1024) * 16;
     d.cost_bias = minP < -16 ? -minP : 16;
     if ((long long)4080 + maxP + d.cost_bias >= (1 << 19) || minP < -(1 << 18)) {
         set_error("prior table out of range for the packed matching key (P in [%d, %d]; gamma=%g beta=%g sigma=%g)", minP, maxP, p.gamma, p.beta,
@@ -140,7 +141,7 @@ int lane_create(svb_context *c, Lane &L) {
         SVB_TRY(dev_alloc(&L.img[s], C * N));
         {
             // zero-filled guard bands of (disp_max + W + 1024) descriptors in front of and behind the descriptor arena
-            const size_t pad = ((size_t)c->p.disp_max + d.W + 1024) * 16;
+            const size_t pad = d.desc_pad;
             SVB_TRY(dev_alloc(&L.desc_base[s], C * N * 16 + 2 * pad));
             SVB_CUDA(cudaMemset(L.desc_base[s], 0, C * N * 16 + 2 * pad));
             L.desc[s] = L.desc_base[s] + pad;
@@ -683,6 +684,7 @@ void svb_destroy(svb_context *c) {
         cudaFree(c->planes_ref[s]);
         cudaFree(c->in_img[s]);
         cudaFree(c->bgra[s]);
+        cudaFree(c->bgra_batch[s]);
     }
     for (int i = 0; i < 4; i++)
         if (c->ev_pc[i]) cudaEventDestroy(c->ev_pc[i]);
@@ -1171,6 +1173,65 @@ int svb_batch_upload(svb_context *c, const uint8_t *left, const uint8_t *right, 
     return SVB_OK;
 }
 
+// The input side of generatePointCloud for a whole batch: BGRA frames (height x width x 4 bytes, what sv.py hands over, sv.py:185-188)
+// go up in groups of `chunk` frames and are converted to gray on the device (cv::cvtColor(BGRA2GRAY), stereo_vision.cu:346-347) straight
+// into the resident input store.
+int svb_batch_upload_bgra(svb_context *c, const uint8_t *left_bgra, const uint8_t *right_bgra, int n_frames) {
+    if (!c || !left_bgra || !right_bgra || n_frames < 1) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SVB_CUDA(cudaSetDevice(c->device));
+    const size_t N = (size_t)c->d.N;
+    if (!(c->in_img[0] && c->in_frames >= (size_t)n_frames)) {
+        for (int s = 0; s < 2; s++) {
+            if (c->in_img[s]) cudaFree(c->in_img[s]);
+            c->in_img[s] = nullptr;
+        }
+        c->in_frames = 0;
+        for (int s = 0; s < 2; s++) SVB_TRY(dev_alloc(&c->in_img[s], (size_t)n_frames * N));
+        c->in_frames = n_frames;
+    }
+    const int G = c->chunk;  // frames per staging group
+    if (c->bgra_batch_frames < (size_t)G) {
+        for (int s = 0; s < 2; s++) {
+            if (c->bgra_batch[s]) cudaFree(c->bgra_batch[s]);
+            c->bgra_batch[s] = nullptr;
+        }
+        c->bgra_batch_frames = 0;
+        for (int s = 0; s < 2; s++) SVB_TRY(dev_alloc(&c->bgra_batch[s], (size_t)G * N * 4));
+        c->bgra_batch_frames = G;
+    }
+    cudaStream_t st = c->lanes[0].stream;
+    for (int f0 = 0; f0 < n_frames; f0 += G) {
+        const int nf = std::min(G, n_frames - f0);
+        const uint8_t *src[2] = {left_bgra, right_bgra};
+        for (int s = 0; s < 2; s++) {
+            SVB_CUDA(cudaMemcpyAsync(c->bgra_batch[s], src[s] + (size_t)f0 * N * 4, (size_t)nf * N * 4, cudaMemcpyHostToDevice, st));
+            // one launch converts the whole group: frames are contiguous in both the staging buffer and the store
+            if ((size_t)nf * N > 0x7FFFFFFFull) {
+                set_error("svb_batch_upload_bgra: group of %d frames too large for one conversion launch", nf);
+                return SVB_ERR_ARG;
+            }
+            SVB_TRY(launch_bgra_to_gray(c->bgra_batch[s], c->in_img[s] + (size_t)f0 * N, (int)((size_t)nf * N), st));
+        }
+    }
+    SVB_CUDA(cudaStreamSynchronize(st));
+    return SVB_OK;
+}
+
+// Device pointers of the last batch call's resident results, so that a consumer on the same GPU (another CUDA library, a renderer, the
+// next stage of a perception stack) reads them in place instead of paying 13 MB of PCIe per frame: D1 = n_frames x (H x W) float,
+// points = n_frames x (H x W) x {x, y, z} double (either may come back NULL when the call did not produce it).  Valid until the next
+// batch call on this context or svb_destroy; work of the producing call is complete when svb_batch_run returns.
+int svb_batch_device_ptrs(svb_context *c, float **D1_dev, double **points_dev, int *n_frames, int *device) {
+    if (!c) return SVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (D1_dev) *D1_dev = c->last_want_D ? c->out_D1 : nullptr;
+    if (points_dev) *points_dev = c->last_want_P ? c->out_points : nullptr;
+    if (n_frames) *n_frames = (int)c->stats.frames;
+    if (device) *device = c->device;
+    return SVB_OK;
+}
+
 // Shared driver of the resident and the host-buffer (e2e) batch paths.
 static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h_left, const uint8_t *h_right, float *h_D1, double *h_points) {
     const Dims &d = c->d;
@@ -1183,6 +1244,8 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
         return SVB_ERR_ARG;
     }
     c->points_float_disp = (flags & SVB_OUT_POINTS_FLOATDISP) != 0;
+    c->last_want_D = want_D;
+    c->last_want_P = want_P;
     const size_t DN = (size_t)d.DN;
     if (want_P && d.sub) {
         set_error("batch: point clouds with subsampling are only defined for the single-frame generatePointCloud path");

@@ -84,6 +84,9 @@ struct svb_context {
     // generatePointCloud path: BGRA staging on the device
     uint8_t *bgra[2] = {nullptr, nullptr};
     cudaEvent_t ev_pc[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t *bgra_batch[2] = {nullptr, nullptr};  // svb_batch_upload_bgra: staging for `chunk` BGRA frames per side
+    size_t bgra_batch_frames = 0;
+    bool last_want_D = false, last_want_P = false;  // outputs of the last batch call (svb_batch_device_ptrs)
     // resident batch stores
     uint8_t *in_img[2] = {nullptr, nullptr};
     size_t in_frames = 0;

@@ -40,6 +40,24 @@ extern thread_local long long g_launch_counter;  // kernels launched by this lib
         }                                                                                           \
     } while (0)
 
+// ---- guard build (make GUARD=1 -> lib_guard/libelas_b200.so) ----------------------------------------------------------------
+// Every load / store whose index the kernels do not test at run time ("loads never need a guard" arguments in k_dense.cu,
+// k_support.cu, k_prior.cu, the shared-memory tiles of k_post.cu / k_ccl.cu / k_post_fused.cu) asserts its range in this build and
+// traps with file:line; `pytest -m gpu` is run against it once per round (profiles/rNN_guard_pytest.log).  The product build
+// compiles the macro away.
+#ifdef SVB_GUARD
+#define SVB_GUARD_ASSERT(cond)                                                         \
+    do {                                                                               \
+        if (!(cond)) {                                                                 \
+            printf("SVB_GUARD %s:%d: %s violated (block %d,%d,%d thread %d)\n", __FILE__, __LINE__, #cond, (int)blockIdx.x, (int)blockIdx.y, \
+                   (int)blockIdx.z, (int)threadIdx.x);                                 \
+            __trap();                                                                  \
+        }                                                                              \
+    } while (0)
+#else
+#define SVB_GUARD_ASSERT(cond) ((void)0)
+#endif
+
 // ---- geometry derived from (params, width, height) ---------------------------------------------
 struct Dims {
     int W, H, N;          // image size, N = W*H
@@ -51,6 +69,7 @@ struct Dims {
     int maxT;             // capacity of one triangle list (2*maxS is an upper bound for a planar triangulation)
     int plane_radius;     // elas.cpp:832
     int P[8];             // prior table P[|d - d_plane|] for deltas 0..plane_radius (elas.cpp:831)
+    size_t desc_pad;      // bytes of zero-filled guard band in front of and behind every descriptor arena (the matchers' unguarded loads)
     int cost_bias;        // added to every matching cost so that SAD + P stays >= 0 in the unsigned packed key: max(16, -min P)
     // optional device counters (svb_set_eval_counting): [0] support-matching hypotheses (64-byte SADs), [1] dense-matching
     // hypotheses (16-byte SADs), counted the way the reference evaluates them; nullptr = the kernels without counting

@@ -236,3 +236,47 @@ def test_float_disparity_point_cloud(svb, golden_meta, monkeypatch):
         finally:
             ctx.close()
     monkeypatch.delenv("SVB_FUSED_POST")
+
+
+def test_bgra_batch_input_and_device_pointers(svb, golden_meta):
+    """SURVEY.md 8f-2: (1) a batch of BGRA frames, converted on the device, gives what the gray path gives on cv::cvtColor's output
+    (svb_stage_bgra_to_gray is pinned to cv2 elsewhere); (2) svb_batch_device_ptrs hands out the resident results: read back through
+    the CUDA runtime (cudaMemcpy on the raw pointers), they are the maps and clouds the download calls return."""
+    import ctypes as C
+
+    W, H, n = 640, 240, 5
+    L, R = make_batch(svb, n, W, H)
+    rng = np.random.default_rng(5)
+    # BGRA frames whose gray conversion is NOT trivially one of the channels
+    Lb = np.stack([np.stack([L[i], np.roll(L[i], 1, 1), rng.integers(0, 255, (H, W), dtype=np.uint8), np.full((H, W), 255, np.uint8)], -1) for i in range(n)])
+    Rb = np.stack([np.stack([R[i], np.roll(R[i], 1, 1), rng.integers(0, 255, (H, W), dtype=np.uint8), np.full((H, W), 255, np.uint8)], -1) for i in range(n)])
+    Q = np.array(golden_meta["Q"])
+    ctx = svb.Context(svb.default_params(svb.PIPELINE), W, H, chunk=2)
+    try:
+        ctx.set_calibration(Q)
+        Lg = np.stack([ctx.bgra_to_gray(Lb[i]) for i in range(n)])
+        Rg = np.stack([ctx.bgra_to_gray(Rb[i]) for i in range(n)])
+        assert not np.array_equal(Lg, L)
+        ctx.batch_upload(Lg, Rg)
+        ctx.batch_run(n, svb.OUT_DISPARITY | svb.OUT_POINTS)
+        want = [ctx.batch_disparity(i) for i in range(n)]
+        ctx.batch_upload_bgra(Lb, Rb)
+        ctx.batch_run(n, svb.OUT_DISPARITY | svb.OUT_POINTS)
+        for i in range(n):
+            assert np.array_equal(ctx.batch_disparity(i), want[i]), i
+        d1, pts, frames, dev = ctx.batch_device_ptrs()
+        assert d1 and pts and frames == n and dev >= 0
+        rt = C.CDLL("libcudart.so.12")
+        rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        got_D = np.zeros((n, H, W), np.float32)
+        got_P = np.zeros((n, H * W, 3), np.float64)
+        assert rt.cudaMemcpy(got_D.ctypes.data, d1, got_D.nbytes, 2) == 0  # cudaMemcpyDeviceToHost
+        assert rt.cudaMemcpy(got_P.ctypes.data, pts, got_P.nbytes, 2) == 0
+        for i in range(n):
+            assert np.array_equal(got_D[i], want[i])
+            assert np.array_equal(got_P[i], ctx.batch_points(i), equal_nan=True)
+        ctx.batch_run(n, svb.OUT_DISPARITY)
+        d1, pts, _, _ = ctx.batch_device_ptrs()
+        assert d1 and not pts
+    finally:
+        ctx.close()
