@@ -12,8 +12,11 @@
 //                global index of its LOCAL root; local roots start as their own parents in the global forest;
 //   2. borders : only the edges that cross tile borders (1/16 of the vertical, 1/128 of the horizontal ones) are united
 //                in global memory, and only between local roots -- a few thousand nodes instead of W*H;
-//   3. totals  : every local root adds its size to its global root;
-//   4. prune   : pixels whose global root counts < speckle_size become -10.
+//   3. totals  : every local root adds its size to its global root.  The tile kernel leaves a compact list of its local roots (a few
+//                per tile) and writes sizes only AT roots, so this step touches a few thousand entries instead of scanning two W*H maps;
+//   4. prune   : pixels whose global root counts < speckle_size become -10 (step 3 leaves every tile-local root pointing straight at
+//                its root, so a pixel gets there in one hop).  Fusing this step into the row pass of the gap interpolation was tried
+//                and measured slower (one warp per row cannot hide the lookup latency the way one thread per pixel does).
 #include "svb_internal.h"
 
 namespace svb {
@@ -58,10 +61,13 @@ constexpr int TW = 128, TH = 2 * RPB;  // tile: 128 columns x 16 rows, 256 threa
 // grid: (ceil(W/TW), ceil(H/TH), nimg).  labels: -1 for invalid pixels, else the global index (v*W + u) of the pixel's
 // tile-local root; sizes = size of the tile-local component at its local root, 0 everywhere else.
 __global__ void __launch_bounds__(2 * TW) k_ccl_tile(const float *__restrict__ D_all, int32_t *__restrict__ labels_all,
-                                                    int32_t *__restrict__ sizes_all, int W, int H, float thr) {
+                                                    int32_t *__restrict__ sizes_all, int32_t *__restrict__ roots_all, int32_t *__restrict__ counts_all,
+                                                    int W, int H, float thr) {
     __shared__ float sD[TH * TW];
     __shared__ int sL[TH * TW];
     __shared__ int sS[TH * TW];
+    __shared__ int s_nroots;
+    if (threadIdx.x == 0) s_nroots = 0;
     const size_t img = (size_t)blockIdx.z * (unsigned)(W * H);
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int c = threadIdx.x & (TW - 1), r0 = (threadIdx.x >> 7) * RPB, lane = threadIdx.x & 31;
@@ -120,6 +126,9 @@ __global__ void __launch_bounds__(2 * TW) k_ccl_tile(const float *__restrict__ D
     __syncthreads();
     int32_t *labels = labels_all + img;
     int32_t *sizes = sizes_all + img;
+    // this tile's list of local roots: room for every pixel of the tile (worst case: no two neighbours similar)
+    const int tile_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    int32_t *roots = roots_all + (size_t)tile_id * (TW * TH);
 #pragma unroll
     for (int k = 0; k < RPB; k++) {
         const int r = r0 + k, v = y0 + r, idx = r * TW + c;
@@ -131,8 +140,13 @@ __global__ void __launch_bounds__(2 * TW) k_ccl_tile(const float *__restrict__ D
             label = (y0 + rr) * W + x0 + rc;
         }
         labels[g] = label;
-        sizes[g] = root[k] == idx ? sS[idx] : 0;  // > 0 marks a tile-local root
+        if (root[k] == idx) {  // a tile-local root: its size is only ever read at this index
+            sizes[g] = sS[idx];
+            roots[atomicAdd(&s_nroots, 1)] = (int32_t)g;
+        }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) counts_all[tile_id] = s_nroots;
 }
 
 // Edges across tile borders: rows v = TH, 2 TH, ... (against v - 1) and columns u = TW, 2 TW, ... (against u - 1).
@@ -168,20 +182,26 @@ __global__ void __launch_bounds__(256) k_ccl_borders(const float *__restrict__ D
     unite(labels, labels[p], labels[q]);  // both pixels are valid: their labels are local roots
 }
 
-// Every tile-local root adds its size to the root of its component.
-__global__ void __launch_bounds__(128) k_ccl_totals(const int32_t *__restrict__ labels_all, int32_t *__restrict__ sizes_all, int W, int H) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= W) return;
-    const size_t img = (size_t)blockIdx.z * (unsigned)(W * H);
-    const int32_t *labels = labels_all + img;
+// Every tile-local root adds its size to the root of its component: one warp per tile walks the tile's root list.
+// grid: (ceil(tiles / 8), nimg), 256 threads; tiles = tiles of ONE image
+__global__ void __launch_bounds__(256) k_ccl_totals(int32_t *__restrict__ labels_all, int32_t *__restrict__ sizes_all,
+                                                   const int32_t *__restrict__ roots_all, const int32_t *__restrict__ counts_all, int tiles, int W, int H) {
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= tiles) return;
+    const size_t img = (size_t)blockIdx.y * (unsigned)(W * H);
+    int32_t *labels = labels_all + img;
     int32_t *sizes = sizes_all + img;
-    const int v_end = min((int)(blockIdx.y + 1) * RPB, H);
-#pragma unroll 4
-    for (int v = blockIdx.y * RPB; v < v_end; v++) {
-        const int idx = v * W + u;
-        const int n = sizes[idx];
-        if (n <= 0 || labels[idx] == idx) continue;  // not a local root, or a local root that is also its component's root
-        atomicAdd(sizes + find_root(labels, idx), n);  // nobody else touches sizes[idx]: idx is not a global root
+    const int tile_id = blockIdx.y * tiles + t;
+    const int32_t *roots = roots_all + (size_t)tile_id * (TW * TH);
+    const int n = counts_all[tile_id];
+    for (int i = lane; i < n; i += 32) {
+        const int g = roots[i];
+        if (labels[g] == g) continue;  // also the root of its whole component: its size entry is the accumulator
+        const int root = find_root(labels, g);
+        atomicAdd(sizes + root, sizes[g]);  // nobody else touches sizes[g]: g is not a global root
+        // path compression: from here on every tile-local root points straight at the root of its component, so a pixel finds it in
+        // ONE hop (pixel -> local root -> global root).  Racing walkers read either the old parent or the root: both are ancestors.
+        labels[g] = root;
     }
 }
 
@@ -198,7 +218,7 @@ __global__ void __launch_bounds__(128) k_ccl_prune(float *__restrict__ D_all, co
         const int r = labels[idx];
         if (r < 0) {
             if (1 < min_size) D_all[img + (unsigned)idx] = -10.f;
-        } else if (sizes_all[img + (unsigned)find_root(labels, r)] < min_size) {
+        } else if (sizes_all[img + (unsigned)labels[r]] < min_size) {  // r is a tile-local root; k_ccl_totals compressed its path
             D_all[img + (unsigned)idx] = -10.f;
         }
     }
@@ -206,25 +226,45 @@ __global__ void __launch_bounds__(128) k_ccl_prune(float *__restrict__ D_all, co
 
 }  // namespace
 
-int launch_remove_small_segments(const Dims &d, const svb_params &p, float *D, int32_t *labels, int32_t *sizes, int nimg, cudaStream_t s) {
+int ccl_tiles_per_image(const Dims &d) { return ((d.Dw + TW - 1) / TW) * ((d.Dh + TH - 1) / TH); }
+
+int ccl_min_size(const Dims &d, const svb_params &p) {
+    // elas.cpp:1017-1022: at half resolution a speckle is sqrt(speckle_size) * 2 pixels
+    return d.sub ? (int)(sqrtf((float)p.speckle_size) * 2) : p.speckle_size;
+}
+
+// labels / sizes: one int per pixel and image; roots: one int per pixel and image (per-tile root lists); counts: one int per tile
+int launch_ccl_label(const Dims &d, const svb_params &p, const float *D, int32_t *labels, int32_t *sizes, int32_t *roots, int32_t *counts, int nimg,
+                     cudaStream_t s) {
     if (nimg <= 0) return SVB_OK;
     const int W = d.Dw, H = d.Dh;
-    // elas.cpp:1017-1022: at half resolution a speckle is sqrt(speckle_size) * 2 pixels
-    const int min_size = d.sub ? (int)(sqrtf((float)p.speckle_size) * 2) : p.speckle_size;
     dim3 tiles((W + TW - 1) / TW, (H + TH - 1) / TH, nimg);
-    k_ccl_tile<<<tiles, 2 * TW, 0, s>>>(D, labels, sizes, W, H, p.speckle_sim_threshold);
+    k_ccl_tile<<<tiles, 2 * TW, 0, s>>>(D, labels, sizes, roots, counts, W, H, p.speckle_sim_threshold);
     SVB_LAUNCH_CHECK();
     const int border_edges = ((H - 1) / TH) * W + ((W - 1) / TW) * H;
     if (border_edges > 0) {
         k_ccl_borders<<<dim3((border_edges + 255) / 256, nimg), 256, 0, s>>>(D, labels, W, H, p.speckle_sim_threshold);
         SVB_LAUNCH_CHECK();
     }
-    dim3 grid((W + 127) / 128, (H + RPB - 1) / RPB, nimg);
-    k_ccl_totals<<<grid, 128, 0, s>>>(labels, sizes, W, H);
-    SVB_LAUNCH_CHECK();
-    k_ccl_prune<<<grid, 128, 0, s>>>(D, labels, sizes, W, H, min_size);
+    const int per_image = (int)(tiles.x * tiles.y);
+    k_ccl_totals<<<dim3((per_image + 7) / 8, nimg), 256, 0, s>>>(labels, sizes, roots, counts, per_image, W, H);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
+}
+
+int launch_ccl_prune(const Dims &d, const svb_params &p, float *D, const int32_t *labels, const int32_t *sizes, int nimg, cudaStream_t s) {
+    if (nimg <= 0) return SVB_OK;
+    const int W = d.Dw, H = d.Dh;
+    dim3 grid((W + 127) / 128, (H + RPB - 1) / RPB, nimg);
+    k_ccl_prune<<<grid, 128, 0, s>>>(D, labels, sizes, W, H, ccl_min_size(d, p));
+    SVB_LAUNCH_CHECK();
+    return SVB_OK;
+}
+
+int launch_remove_small_segments(const Dims &d, const svb_params &p, float *D, int32_t *labels, int32_t *sizes, int32_t *roots, int32_t *counts,
+                                 int nimg, cudaStream_t s) {
+    SVB_TRY(launch_ccl_label(d, p, D, labels, sizes, roots, counts, nimg, s));
+    return launch_ccl_prune(d, p, D, labels, sizes, nimg, s);
 }
 
 }  // namespace svb

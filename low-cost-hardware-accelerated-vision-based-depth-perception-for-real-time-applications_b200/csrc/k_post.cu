@@ -109,11 +109,11 @@ __device__ __forceinline__ void gap_line(float *line, int stride, int n, int *pr
     }
 }
 
-// grid: (ceil(H/GAP_WARPS), nimg); dynamic smem: GAP_WARPS * Wpad int32
+// grid: (ceil(H/warps), nimg); dynamic smem: warps * Wpad int32
 __global__ void __launch_bounds__(GAP_WARPS * 32) k_gap_rows(float *__restrict__ D_all, int W, int H, int gap_width, int add_corners, int Wpad) {
     extern __shared__ int s_prev[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int v = blockIdx.x * GAP_WARPS + wid;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int v = blockIdx.x * warps + wid;
     if (v >= H) return;
     gap_line(D_all + ((size_t)blockIdx.y * H + v) * W, 1, W, s_prev + wid * Wpad, lane, gap_width, add_corners);
 }
@@ -395,24 +395,35 @@ int launch_lr_check_rows(const Dims &d, const svb_params &p, const float *D1in, 
     return SVB_OK;
 }
 
-int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s) {
-    if (nimg <= 0) return SVB_OK;
+namespace {
+
+int gap_width_of(const Dims &d, const svb_params &p) { return d.sub ? p.ipol_gap_width / 2 + 1 : p.ipol_gap_width; }  // elas.cpp:1131-1135
+
+int launch_gap_rows(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s) {
     const int W = d.Dw, H = d.Dh;
-    const int gap_width = d.sub ? p.ipol_gap_width / 2 + 1 : p.ipol_gap_width;  // elas.cpp:1131-1135
     const int Wpad = (W + 31) & ~31;
-    {
-        dim3 grid((H + GAP_WARPS - 1) / GAP_WARPS, nimg);
-        const size_t smem_rows = (size_t)GAP_WARPS * Wpad * sizeof(int);
-        if (smem_rows > 48 * 1024) {  // 4K-wide rows: opt in to large dynamic shared memory
-            cudaError_t e = cudaFuncSetAttribute(k_gap_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows);
-            if (e != cudaSuccess) {
-                set_error("cudaFuncSetAttribute(k_gap_rows, %zu): %s", smem_rows, cudaGetErrorString(e));
-                return SVB_ERR_CUDA;
-            }
+    const int warps = GAP_WARPS;  // 4 warps x 8192 px x 4 B = 128 KB at the largest supported width
+    const size_t smem = (size_t)warps * Wpad * sizeof(int);
+    static size_t configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && dev >= 0 && dev < 64 && configured[dev] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(k_gap_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(k_gap_rows, %zu): %s", smem, cudaGetErrorString(e));
+            return SVB_ERR_CUDA;
         }
-        k_gap_rows<<<grid, GAP_WARPS * 32, smem_rows, s>>>(D, W, H, gap_width, p.add_corners, Wpad);
-        SVB_LAUNCH_CHECK();
+        configured[dev] = smem;
     }
+    dim3 grid((H + warps - 1) / warps, nimg);
+    k_gap_rows<<<grid, warps * 32, smem, s>>>(D, W, H, gap_width_of(d, p), p.add_corners, Wpad);
+    SVB_LAUNCH_CHECK();
+    return SVB_OK;
+}
+
+int launch_gap_cols(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s) {
+    const int W = d.Dw, H = d.Dh;
+    const int gap_width = gap_width_of(d, p);
     const int Hpad = (H + 31) & ~31;
     int GC_COLS = 16;
     size_t smem = (size_t)H * (GC_COLS + 1) * sizeof(float) + (size_t)GC_WARPS * Hpad * sizeof(int);
@@ -421,13 +432,18 @@ int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStrea
         smem = (size_t)H * (GC_COLS + 1) * sizeof(float) + (size_t)GC_WARPS * Hpad * sizeof(int);
     }
     if (smem <= 200 * 1024) {
-        if (smem > 48 * 1024) {
+        static size_t configured[64][2] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const int which = GC_COLS == 16 ? 0 : 1;
+        if (smem > 48 * 1024 && dev >= 0 && dev < 64 && configured[dev][which] < smem) {
             cudaError_t e = GC_COLS == 16 ? cudaFuncSetAttribute(k_gap_cols_strip<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                           : cudaFuncSetAttribute(k_gap_cols_strip<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) {
                 set_error("cudaFuncSetAttribute(k_gap_cols_strip): %s", cudaGetErrorString(e));
                 return SVB_ERR_CUDA;
             }
+            configured[dev][which] = smem;
         }
         dim3 grid((W + GC_COLS - 1) / GC_COLS, nimg);
         if (GC_COLS == 16)
@@ -437,12 +453,18 @@ int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStrea
         SVB_LAUNCH_CHECK();
         return SVB_OK;
     }
-    {
-        dim3 grid((W + 127) / 128, nimg);
-        k_gap_cols<<<grid, 128, 0, s>>>(D, W, H, gap_width, p.add_corners);
-        SVB_LAUNCH_CHECK();
-    }
+    dim3 grid((W + 127) / 128, nimg);
+    k_gap_cols<<<grid, 128, 0, s>>>(D, W, H, gap_width, p.add_corners);
+    SVB_LAUNCH_CHECK();
     return SVB_OK;
+}
+
+}  // namespace
+
+int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s) {
+    if (nimg <= 0) return SVB_OK;
+    SVB_TRY(launch_gap_rows(d, p, D, nimg, s));
+    return launch_gap_cols(d, p, D, nimg, s);
 }
 
 int launch_adaptive_mean(const Dims &d, int mean_mode, float *D, float *tmp, int nimg, cudaStream_t s) {

@@ -165,6 +165,8 @@ int lane_create(svb_context *c, Lane &L) {
     SVB_TRY(dev_alloc(&L.Dtmp, 2 * C * N));
     SVB_TRY(dev_alloc(&L.labels, 2 * C * N));
     SVB_TRY(dev_alloc(&L.sizes, 2 * C * N));
+    SVB_TRY(dev_alloc(&L.ccl_roots, 2 * C * (size_t)ccl_tiles_per_image(d) * 2048));  // per-tile root lists: room for every pixel of a 128 x 16 tile
+    SVB_TRY(dev_alloc(&L.ccl_counts, 2 * C * (size_t)ccl_tiles_per_image(d)));
     SVB_TRY(dev_alloc(&L.dmap, C * N));
     SVB_TRY(host_alloc(&L.h_support, C * d.maxS * 3));
     SVB_TRY(host_alloc(&L.h_nsupport, C));
@@ -202,6 +204,8 @@ void lane_destroy(Lane &L) {
     cudaFree(L.Dtmp);
     cudaFree(L.labels);
     cudaFree(L.sizes);
+    cudaFree(L.ccl_roots);
+    cudaFree(L.ccl_counts);
     cudaFree(L.dmap);
     cudaFreeHost(L.h_support);
     cudaFreeHost(L.h_nsupport);
@@ -456,7 +460,8 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, 
     // needs the left and right blocks to be adjacent: true when nf == chunk, otherwise run the sides separately
     const int passes = both ? 2 : 1;
     SVB_TRY(T.mark(ST_SEGMENTS));
-    for (int s = 0; s < passes; s++) SVB_TRY(launch_remove_small_segments(d, p, s ? D2 : D1, L.labels, L.sizes, nf, L.stream));
+    for (int s = 0; s < passes; s++)
+        SVB_TRY(launch_remove_small_segments(d, p, s ? D2 : D1, L.labels, L.sizes, L.ccl_roots, L.ccl_counts, nf, L.stream));
     if (c->tap_mode && nf == 1) {
         SVB_TRY(tap_store(c, "D1seg", D1, DN * 4, L.stream));
         if (both) SVB_TRY(tap_store(c, "D2seg", D2, DN * 4, L.stream));
@@ -1074,7 +1079,7 @@ static int stage_inplace(svb_context *c, float *D, int which) {
     STAGE_PROLOG();
     if (!D) return SVB_ERR_ARG;
     SVB_CUDA(cudaMemcpyAsync(L.Dlr, D, (size_t)d.DN * 4, cudaMemcpyHostToDevice, L.stream));
-    if (which == 0) SVB_TRY(launch_remove_small_segments(d, c->p, L.Dlr, L.labels, L.sizes, 1, L.stream));
+    if (which == 0) SVB_TRY(launch_remove_small_segments(d, c->p, L.Dlr, L.labels, L.sizes, L.ccl_roots, L.ccl_counts, 1, L.stream));
     if (which == 1) SVB_TRY(launch_gap(d, c->p, L.Dlr, 1, L.stream));
     if (which == 2) SVB_TRY(launch_adaptive_mean(d, c->mean_mode, L.Dlr, L.Dtmp, 1, L.stream));
     if (which == 3) SVB_TRY(launch_median(d, L.Dlr, L.Dtmp, 1, L.stream));

@@ -34,6 +34,7 @@ struct Lane {
     float *Dlr = nullptr;   // [2][chunk][N]
     float *Dtmp = nullptr;  // [2][chunk][N]
     int32_t *labels = nullptr, *sizes = nullptr;  // [2][chunk][N]
+    int32_t *ccl_roots = nullptr, *ccl_counts = nullptr;  // per-tile lists of tile-local roots and their lengths (k_ccl.cu)
     uint8_t *dmap = nullptr;
     // pinned host
     int32_t *h_support = nullptr, *h_nsupport = nullptr, *h_tri[2] = {nullptr, nullptr}, *h_ntri = nullptr;

@@ -156,7 +156,14 @@ int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStrea
 int launch_adaptive_mean(const Dims &d, int mean_mode, float *D, float *tmp, int nimg, cudaStream_t s);
 int launch_median(const Dims &d, float *D, float *tmp, int nimg, cudaStream_t s);
 // k_ccl.cu
-int launch_remove_small_segments(const Dims &d, const svb_params &p, float *D, int32_t *labels, int32_t *sizes, int nimg, cudaStream_t s);
+// labels, sizes, roots: one int32 per pixel and image; counts: one per 128 x 16 tile and image (ccl_tiles_per_image)
+int ccl_tiles_per_image(const Dims &d);
+int ccl_min_size(const Dims &d, const svb_params &p);
+int launch_ccl_label(const Dims &d, const svb_params &p, const float *D, int32_t *labels, int32_t *sizes, int32_t *roots, int32_t *counts, int nimg,
+                     cudaStream_t s);
+int launch_ccl_prune(const Dims &d, const svb_params &p, float *D, const int32_t *labels, const int32_t *sizes, int nimg, cudaStream_t s);
+int launch_remove_small_segments(const Dims &d, const svb_params &p, float *D, int32_t *labels, int32_t *sizes, int32_t *roots, int32_t *counts,
+                                 int nimg, cudaStream_t s);
 // k_reproject.cu
 struct Calib;
 // k_post_fused.cu: adaptive mean -> median -> final map (+ u8 map + point cloud) in one pass; full-resolution maps only

@@ -18,8 +18,7 @@ def latest(pattern):
     return json.loads(open(files[-1]).read().strip().splitlines()[-1])
 
 
-def test_default_bench_line_has_the_contract_keys():
-    d = latest("r01?_bench_default.json")
+def check_b200_line(d):
     for k in REQUIRED:
         assert k in d, k
     assert d["n_gpus"] == 1 and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
@@ -35,11 +34,51 @@ def test_default_bench_line_has_the_contract_keys():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
-def test_reference_arm_line():
-    d = latest("r01?_bench_reference.json")
+def test_default_bench_line_has_the_contract_keys():
+    check_b200_line(latest("r0*_bench_default.json"))
+
+
+def check_reference_line(d):
     assert d["impl"] == "reference" and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_reference_arm_line():
+    check_reference_line(latest("r0*_bench_reference.json"))
+
+
+def test_reference_arm_runs_live_and_never_maps_the_product_library():
+    """`bench.py --impl reference` for real (CPU only, one frame per core): the printed line obeys the contract, names the SAME
+    config.workload as the b200 arm (bench.WORKLOAD), and the process that timed the reference did not map libelas_b200.so (its
+    synthetic inputs come from the standalone libsvb_synth.so)."""
+    import bench
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-frames-per-core", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    check_reference_line(d)
+    assert d["config"]["workload"] == bench.WORKLOAD
+    assert d["product_library_mapped"] is False
+    assert d["metric"] == bench.METRIC and d["unit"] == bench.UNIT and d["higher_is_better"] is True
+
+
+@__import__("pytest").mark.gpu
+def test_b200_arm_runs_live():
+    """The product arm for real on the GPU box (a small batch so that it takes seconds): contract keys, the shared workload string,
+    launches counted, and the fused / device stages present in the stage table."""
+    import bench
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--batch", "64", "--e2e-batch", "64",
+                        "--cpu-seconds", "2"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    check_b200_line(d)
+    assert d["config"]["workload"] == bench.WORKLOAD
+    assert "post_fused" in d["stages"] and "delaunay_device" in d["stages"]
+    assert d["host_delaunay"]["lists_device"] > 0
+    assert d["roofline"]["bound_actual"] and d["roofline"]["sad_floor"]["frac_of_floor"] > 0
 
 
 def test_bench_parses_its_flags():

@@ -7,7 +7,8 @@ import json
 import sys
 
 STAGE_OF = [("k_descriptor", "descriptor"), ("k_support_match", "support_match"), ("k_dcan_border", "support_match"),
-            ("k_support_filter", "support_filter"), ("k_delaunay_order", "support_filter"), ("k_planes", "planes"), ("k_grid", "grid"), ("k_raster", "raster"),
+            ("k_support_filter", "support_filter"), ("k_incon_first_sweep", "support_filter"), ("k_delaunay_order", "delaunay_device"),
+            ("k_delaunay_levels", "delaunay_device"), ("k_post_fused", "post_fused"), ("PostFusedArgs", "post_fused"), ("k_planes", "planes"), ("k_grid", "grid"), ("k_raster", "raster"),
             ("k_dense", "dense_match"), ("DenseArgs", "dense_match"), ("k_lr_check", "lr_check"), ("k_ccl", "remove_small_segments"),
             ("k_gap", "gap_interpolation"), ("k_mean", "adaptive_mean"), ("k_median", "median"), ("k_reproject", "reproject")]
 
