@@ -256,19 +256,19 @@ int delaunay_xy(const int32_t *x, const int32_t *y, int n, int32_t *tri_out, int
     return count;
 }
 
-int delaunay_support_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int32_t *tri_out, int cap,
+int delaunay_support_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int m, int32_t *tri_out, int cap,
                              DelaunayScratch &scratch) {
-    if (n < 3) return 0;
-    // arena (int32 units): [{x,y} sentinel + n][records 8 R]
-    const size_t max_records = 1 + (size_t)4 * n + 16;
-    const size_t need = 2 * (size_t)(n + 1) + (size_t)n + 8 * max_records + 2;
+    if (m < 3 || m > n) return m < 3 && m >= 0 ? 0 : -1;
+    // arena (int32 units): [{x,y} sentinel + m][records 8 R]
+    const size_t max_records = 1 + (size_t)4 * m + 16;
+    const size_t need = 2 * (size_t)(m + 1) + 8 * max_records + 2;
     if (scratch.storage.size() < need) scratch.storage.resize(need);
     int32_t *base = scratch.storage.data();
     base += ((uintptr_t)base & 7) ? 1 : 0;
     Pt *P = (Pt *)base + 1;
-    int32_t *R = (int32_t *)(P + n);
+    int32_t *R = (int32_t *)(P + m);
     P[-1] = Pt{0, 0};
-    for (int i = 0; i < n; i++) {
+    for (int i = 0; i < m; i++) {
         const int id = order[i];
         if ((unsigned)id >= (unsigned)n) return -1;
         const int32_t *sp = support + 3 * id;
@@ -280,9 +280,9 @@ int delaunay_support_ordered(const int32_t *support, int n, int right_image, con
     mesh.ntri = 0;
     mesh.make();  // record 0: outer space
     int hullleft, hullright;
-    mesh.recurse(0, n, 0, 0, 1, -1, hullleft, hullright);
+    mesh.recurse(0, m, 0, 0, 1, -1, hullleft, hullright);
     int count = 0;
-    for (int t = 1; t < 2 * n - 1; t++) {
+    for (int t = 1; t < 2 * m - 1; t++) {
         const int32_t *r = R + 8 * t + 4;
         const int a = r[1], b = r[2], c = r[0];
         if ((a | b | c) < 0) continue;

@@ -21,7 +21,8 @@ int delaunay_support(const int32_t *support, int n, int right_image, int32_t *tr
 // Same, starting from the recursion order computed on the device (k_order.cu): order[i] = index into `support` of the
 // i-th vertex after the lexicographic sort and the alternating-axis partition of a DUPLICATE-FREE point set.
 // Returns -1 if `order` is not usable (the caller then runs delaunay_support).
-int delaunay_support_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int32_t *tri_out, int cap,
+// m = number of entries of `order` (n, or fewer when the device has already removed duplicate coordinates the way the reference does).
+int delaunay_support_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int m, int32_t *tri_out, int cap,
                              DelaunayScratch &scratch);
 
 // The device's share of the stage, restated on the host (tests, no GPU needed): the levels of the recursion tree from the leaves up

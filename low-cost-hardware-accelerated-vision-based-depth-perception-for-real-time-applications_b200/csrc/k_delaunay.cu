@@ -15,8 +15,8 @@
 // 64 per chunk.  The finished list (live records in creation order, ghosts dropped: triangle.cpp:7449-7500) is written to the
 // frame's slot of the device triangle arena; nothing but two counters per list crosses PCIe.
 //
-// Lists the vertex-order kernel flagged (duplicate coordinates, where the survivor depends on the reference's randomised sort; more
-// than 4096 points) or that exceed this launch's shared-memory capacity are left to the host stage (host_delaunay.cpp).
+// Lists the vertex-order kernel flagged (more than 4096 points, coordinates outside its key range) or that exceed this launch's
+// shared-memory capacity are left to the host stage (host_delaunay.cpp).  Duplicate coordinates are resolved by k_order.cu.
 #include "delaunay_mesh.h"
 #include "svb_internal.h"
 
@@ -38,8 +38,9 @@ __global__ void __launch_bounds__(DD_THREADS) k_delaunay_levels(const int32_t *_
     Pt *P = reinterpret_cast<Pt *>(dd_smem) + 1;  // P[-1]: the NULL vertex (its coordinates are read, never used)
     uint16_t *R = reinterpret_cast<uint16_t *>(dd_smem + sizeof(Pt) * (size_t)(cap_n + 1));
     const int f = blockIdx.x, side = blockIdx.y, tid = threadIdx.x;
-    const int n = nsupport_all[f];
-    if (n < 3 || n > cap_n || n > maxS || order_ok_all[2 * f + side] != 1) {  // uniform: the host stage takes this list
+    // vertices that take part: the whole list, or the survivors of the reference's duplicate removal (k_order.cu); 0 = list not usable
+    const int n = order_ok_all[2 * f + side];
+    if (n < 3 || n > cap_n || n > maxS || n > nsupport_all[f]) {  // uniform: the host stage takes this list
         if (tid == 0) h_done[2 * f + side] = 0;
         return;
     }

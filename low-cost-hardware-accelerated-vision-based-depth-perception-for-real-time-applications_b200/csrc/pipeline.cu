@@ -177,6 +177,9 @@ int lane_create(svb_context *c, Lane &L) {
     SVB_TRY(dev_alloc(&L.d_order, C * 2 * d.maxS));
     SVB_TRY(dev_alloc(&L.d_order_ok, C * 2));
     SVB_CUDA(cudaMemset(L.d_order_ok, 0, sizeof(int32_t) * C * 2));
+    SVB_TRY(dev_alloc(&L.dup_count, C * 2));
+    SVB_CUDA(cudaMemset(L.dup_count, 0, sizeof(int32_t) * C * 2));
+    SVB_TRY(dev_alloc(&L.dup_keys, C * 2 * delaunay_dup_keys_per_list()));
     SVB_TRY(host_alloc(&L.h_dd_done, C * 2));
     memset(L.h_dd_done, 0, sizeof(int32_t) * C * 2);
     L.host_made.assign(C * 2, 0);
@@ -215,6 +218,8 @@ void lane_destroy(Lane &L) {
     cudaFree(L.d_order);
     cudaFree(L.d_order_ok);
     cudaFreeHost(L.h_dd_done);
+    cudaFree(L.dup_count);
+    cudaFree(L.dup_keys);
     if (L.ev_a) cudaEventDestroy(L.ev_a);
     if (L.ev_done) cudaEventDestroy(L.ev_done);
     if (L.own_stream) cudaStreamDestroy(L.own_stream);
@@ -284,6 +289,17 @@ int tap_store(svb_context *c, const char *name, const void *dev_src, size_t byte
     return SVB_OK;
 }
 
+// Lists with duplicate coordinates (two thirds of the right-image lists of real frames): the reference keeps whichever duplicate its
+// randomised quicksort leaves first, so someone has to replay that sort -- a sequential job.  On the device it costs about 1.4 ms of
+// latency per chunk (k_replay_vertexsort, hidden only in part), on the host about 0.3 ms of CPU per frame for the whole list.  Which is
+// better depends on how many host threads this context has: SVB_DELAUNAY_DUPS=device|host decides, the default is the host stage when
+// it has at least 8 worker threads (one GPU on a 16-core box), the device otherwise (8 GPUs sharing 32 cores).
+bool dups_on_device(const svb_context *c) {
+    if (c->dups_policy == 1) return true;
+    if (c->dups_policy == 2) return false;
+    return c->pool && c->pool->size() < 8;
+}
+
 // ---- stage A: images (device) -> support lists (device + pinned host) ------------------------------
 int stage_a(svb_context *c, Lane &L, const uint8_t *img1, const uint8_t *img2, int nf, StageEvents *se) {
     const Dims &d = c->d;
@@ -300,7 +316,8 @@ int stage_a(svb_context *c, Lane &L, const uint8_t *img1, const uint8_t *img2, i
     // ... and the order in which the host's divide-and-conquer will meet the vertices (sort + alternating cuts)
     L.unpacked = false;
     if (c->gpu_order) {
-        SVB_TRY(launch_delaunay_order(d, L.support, L.nsupport, L.h_order, L.h_order_ok, L.d_order, L.d_order_ok, nf, L.stream));
+        SVB_TRY(launch_delaunay_order(d, L.support, L.nsupport, L.h_order, L.h_order_ok, L.d_order, L.d_order_ok, dups_on_device(c) ? L.dup_count : nullptr,
+                                      dups_on_device(c) ? L.dup_keys : nullptr, nf, L.stream));
         // ... and then the divide-and-conquer itself, straight into the lane's triangle arena (k_delaunay.cu); the host stage only
         // takes the lists the device leaves to it (duplicate coordinates, more points than the launch has shared memory for)
         if (c->delaunay_device && !c->inject[0] && !c->inject[1]) {
@@ -386,8 +403,9 @@ int svb::stage_host(svb_context *c, Lane &L, int nf, bool unpacked) {
             } else if (n >= 3) {
                 const int32_t *sup = L.h_support + (size_t)f * d.maxS * 3;
                 m = -1;
-                if (c->gpu_order && L.h_order_ok[2 * f + side] == 1)
-                    m = delaunay_support_ordered(sup, n, side, L.h_order + ((size_t)f * 2 + side) * d.maxS, out, cap, c->scratch[worker]);
+                const int nv = L.h_order_ok[2 * f + side];  // vertices in the device's order (duplicates already removed), 0 = not usable
+                if (c->gpu_order && nv >= 3)
+                    m = delaunay_support_ordered(sup, n, side, L.h_order + ((size_t)f * 2 + side) * d.maxS, nv, out, cap, c->scratch[worker]);
                 if (m < 0) m = delaunay_support(sup, n, side, out, cap, c->scratch[worker]);
                 if (m > cap) m = cap;
             }
@@ -650,6 +668,9 @@ svb_context *svb_create(const svb_params *params, int width, int height, int chu
         const char *dd = getenv("SVB_DELAUNAY_DEVICE");
         if (dd && atoi(dd) == 0) c->delaunay_device = false;
         c->dd_cap = std::min(c->chunk == 1 ? 4096 : 2048, std::max(c->d.maxS, 3));  // single-frame contexts: one CTA per side, take all it can
+        const char *dp = getenv("SVB_DELAUNAY_DUPS");
+        if (dp && !strcmp(dp, "device")) c->dups_policy = 1;
+        if (dp && !strcmp(dp, "host")) c->dups_policy = 2;
         const char *fp = getenv("SVB_FUSED_POST");
         if (fp && atoi(fp) == 0) c->fused_post = false;
         const char *e = getenv("SVB_LANES");
@@ -931,7 +952,7 @@ int svb_stage_delaunay(const int32_t *support, int n, int right_image, int32_t *
 int svb_stage_delaunay_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int32_t *tri, int cap, int *n_tri_out) {
     if (!support || !order || !tri || n < 0 || cap < 0) return SVB_ERR_ARG;
     DelaunayScratch scratch;
-    const int m = delaunay_support_ordered(support, n, right_image ? 1 : 0, order, tri, cap, scratch);
+    const int m = delaunay_support_ordered(support, n, right_image ? 1 : 0, order, n, tri, cap, scratch);
     if (m < 0) {
         set_error("svb_stage_delaunay_ordered: `order` is not a permutation of 0..n-1");
         return SVB_ERR_ARG;
@@ -968,7 +989,8 @@ int svb_stage_delaunay_pipeline(svb_context *c, const int32_t *support, int n, i
     if (n) SVB_CUDA(cudaMemcpyAsync(L.support, L.h_support, (size_t)n * 12, cudaMemcpyHostToDevice, L.stream));
     L.h_order_ok[0] = L.h_order_ok[1] = 0;
     L.h_dd_done[0] = L.h_dd_done[1] = 0;
-    SVB_TRY(launch_delaunay_order(d, L.support, L.nsupport, L.h_order, L.h_order_ok, L.d_order, L.d_order_ok, 1, L.stream));
+    SVB_TRY(launch_delaunay_order(d, L.support, L.nsupport, L.h_order, L.h_order_ok, L.d_order, L.d_order_ok, dups_on_device(c) ? L.dup_count : nullptr,
+                                  dups_on_device(c) ? L.dup_keys : nullptr, 1, L.stream));
     if (c->delaunay_device)
         SVB_TRY(launch_delaunay_levels(d, L.support, L.nsupport, L.d_order, L.d_order_ok, L.tri[0], L.tri[1], L.h_ntri, L.h_dd_done, 1, c->dd_cap, L.stream));
     SVB_CUDA(cudaStreamSynchronize(L.stream));
@@ -980,8 +1002,8 @@ int svb_stage_delaunay_pipeline(svb_context *c, const int32_t *support, int n, i
         const int take = m < cap ? m : cap;
         if (take > 0) SVB_CUDA(cudaMemcpy(tri, L.tri[side], sizeof(int32_t) * 3 * (size_t)take, cudaMemcpyDeviceToHost));
         used = 2;
-    } else if (L.h_order_ok[side] == 1) {
-        m = delaunay_support_ordered(L.h_support, n, side, L.h_order + (size_t)side * d.maxS, tri, cap, c->scratch[0]);
+    } else if (L.h_order_ok[side] >= 3) {
+        m = delaunay_support_ordered(L.h_support, n, side, L.h_order + (size_t)side * d.maxS, L.h_order_ok[side], tri, cap, c->scratch[0]);
         used = m >= 0;
     }
     if (m < 0) m = delaunay_support(L.h_support, n, side, tri, cap, c->scratch[0]);

@@ -42,6 +42,8 @@ struct Lane {
     int32_t *h_order_ok = nullptr;  // [chunk][2] 1 = h_order is valid for that list
     int32_t *d_order = nullptr;     // device copy of h_order for the device divide-and-conquer (k_delaunay.cu)
     int32_t *d_order_ok = nullptr;  // device copy of h_order_ok
+    int32_t *dup_count = nullptr;   // [chunk][2] k_order.cu: -1 = list flagged for the vertex-sort replay, then the number of distinct vertices
+    unsigned long long *dup_keys = nullptr;  // [chunk][2][4096] sorted, de-duplicated keys of the flagged lists
     int32_t *h_dd_done = nullptr;   // [chunk][2] mapped host: 1 = the device triangulated that list (its count is in h_ntri), 0 = host's turn
     std::vector<uint8_t> host_made; // [chunk][2] this chunk's lists that the host stage produced (they need an H2D copy)
     bool unpacked = false;          // layout of this chunk's triangle lists: frame f at f * (maxT + 8) (device stage) or packed back to back
@@ -103,6 +105,7 @@ struct svb_context {
     bool fused_post = true;         // SVB_FUSED_POST=0: stage-by-stage mean / median / reproject kernels everywhere (k_post_fused.cu otherwise)
     bool points_float_disp = false; // SVB_OUT_POINTS_FLOATDISP of the call in flight
     bool delaunay_device = true;    // SVB_DELAUNAY_DEVICE=0: the divide-and-conquer runs on the host for every list (k_delaunay.cu otherwise)
+    int dups_policy = 0;            // lists with duplicate coordinates: 0 = by host thread count, 1 = device, 2 = host (SVB_DELAUNAY_DUPS)
     int dd_cap = 2048;              // vertex capacity the device divide-and-conquer is launched with (shared memory); follows the lists seen
     bool gpu_order = true;  // SVB_GPU_ORDER=0: the host stage sorts and partitions the vertices itself
     std::vector<svb::StageEvents> stage_ev;  // one set per chunk of the call in flight

@@ -112,8 +112,11 @@ int launch_descriptor(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg
 int launch_descriptor_rows(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, int row0, int row1, cudaStream_t s);  // d.sub: even rows only
 // k_order.cu: recursion order of the host Delaunay stage for every (frame, side); h_order [nf][2][maxS], h_ok [nf][2] (mapped host memory)
 // d_order / d_ok: optional device copies (same layout) for launch_delaunay_levels
+// dup_count [nf][2] / dup_keys [nf][2][delaunay_dup_keys_per_list()]: optional device scratch; with it, lists with duplicate coordinates
+// are sorted and de-duplicated on the device exactly like the reference does it, without it they are flagged for the host
+size_t delaunay_dup_keys_per_list();
 int launch_delaunay_order(const Dims &d, const int32_t *support, const int32_t *nsupport, int32_t *h_order, int32_t *h_ok, int32_t *d_order,
-                          int32_t *d_ok, int nf, cudaStream_t s);
+                          int32_t *d_ok, int32_t *dup_count, unsigned long long *dup_keys, int nf, cudaStream_t s);
 // k_delaunay.cu: the divide-and-conquer itself on the device, one CTA per (frame, side); lists of up to cap_n (<= 4096) points whose
 // order is usable are triangulated into tri1 / tri2 at frame f * (maxT + 8) (h_ntri = count, h_done = 1, mapped host memory),
 // the others get h_done = 0 and are left to the host stage

@@ -358,12 +358,16 @@ def test_hypothesis_counters_match_instrumented_reference(svb, kitti_gray, setti
         ctx.close()
 
 
-def test_device_vertex_order_feeds_the_same_triangulation(svb, ref):
-    """k_order.cu + delaunay_support_ordered against the reference's triangulator on random lattices, both sides; lists the
-    device must hand back to the host (duplicate coordinates, more than 4096 points) still give the reference's output."""
+@pytest.mark.parametrize("dups", ["device", "host"])
+def test_device_vertex_order_feeds_the_same_triangulation(svb, ref, monkeypatch, dups):
+    """The Delaunay stage as the pipeline runs it -- vertex order (k_order.cu, including the replay of the reference's randomised sort
+    for lists with duplicate coordinates) and divide-and-conquer (k_delaunay.cu) on the device -- against the reference's triangulator
+    on random lattices, both sides; a list the device hands back to the host (more than 4096 points) still gives the reference's output."""
     import test_cabi_host as H
 
+    monkeypatch.setenv("SVB_DELAUNAY_DUPS", dups)  # who replays the reference's sort for lists with duplicate coordinates
     ctx = svb.Context(svb.default_params(svb.MIDDLEBURY), 1242, 375)
+    monkeypatch.delenv("SVB_DELAUNAY_DUPS")
     try:
         for seed, n, expect_device in [(1, 3, True), (2, 4, True), (3, 7, True), (4, 50, True), (5, 400, True), (6, 2500, True),
                                        (8, 4096, True), (9, 5, True), (10, 6, True), (11, 9, True), (12, 13, True),
@@ -373,16 +377,30 @@ def test_device_vertex_order_feeds_the_same_triangulation(svb, ref):
                 want = ref.delaunay(s, side)
                 got, used = ctx.delaunay_pipeline(s, side)
                 assert np.array_equal(got, want), "seed %d n %d side %d" % (seed, n, side)
-                if side == 0 or not expect_device:
+                xs = s[:, 0] - s[:, 2] if side else s[:, 0]
+                has_dups = len(set(zip(xs.tolist(), s[:, 1].tolist()))) < len(s)
+                if has_dups and dups == "host":
+                    assert used == 0, (seed, n, side, used)  # flagged by the device, made by the host stage
+                else:
                     assert (used > 0) == (expect_device and len(s) <= 4096), (seed, n, side, used)
                     if used:
-                        assert used == 2, (seed, n, side, used)  # the whole divide-and-conquer ran on the device (k_delaunay.cu)
-        # duplicates in the right image: flagged by the device, resolved by the host like the reference does
+                        # the whole stage ran on the device (k_order.cu + k_delaunay.cu) -- also for the right image, where x = u - d
+                        # collides for many of these lists and the survivor is whatever the reference's randomised sort leaves first
+                        assert used == 2, (seed, n, side, used)
+            if n >= 400:
+                xr = s[:, 0] - s[:, 2]
+                assert len(set(zip(xr.tolist(), s[:, 1].tolist()))) < len(s), "the generator is expected to produce duplicates in the right image"
+        # a small list with duplicates in the right image
         dup = np.array([(100, 50, 10), (95, 50, 5), (200, 80, 20), (60, 120, 1), (300, 20, 9), (110, 50, 20)], np.int32)
         got, used = ctx.delaunay_pipeline(dup, 1)
-        assert not used and np.array_equal(got, ref.delaunay(dup, 1))
+        assert used == (2 if dups == "device" else 0) and np.array_equal(got, ref.delaunay(dup, 1))
         got, used = ctx.delaunay_pipeline(dup, 0)
-        assert used and np.array_equal(got, ref.delaunay(dup, 0))
+        assert used == 2 and np.array_equal(got, ref.delaunay(dup, 0))
+        # a single distinct vertex is left after the duplicate removal: no triangle (the reference's triangulator itself crashes on this
+        # input, so there is nothing to compare with)
+        one = np.array([(100, 50, 10), (95, 50, 5), (105, 50, 15)], np.int32)
+        got, used = ctx.delaunay_pipeline(one, 1)
+        assert len(got) == 0
         # collinear input: no triangles either way
         col = np.array([(50, 5 * i, 3) for i in range(1, 30)], np.int32)
         got, used = ctx.delaunay_pipeline(col, 0)
