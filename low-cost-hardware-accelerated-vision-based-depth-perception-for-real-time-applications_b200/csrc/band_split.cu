@@ -180,7 +180,7 @@ int svb_band_process(svb_band_group *g, const uint8_t *I1, const uint8_t *I2, in
         const int i0 = std::max(g->r0[b] - 3, 0), i1 = std::min(g->r1[b] + 3, H);
         const uint8_t *src[2] = {I1, I2};
         for (int s = 0; s < 2; s++)
-            SVB_CUDA(cudaMemcpy2DAsync(L.img[s] + (size_t)i0 * W, W, src[s] + (size_t)i0 * stride, stride, W, i1 - i0, cudaMemcpyHostToDevice,
+            SVB_CUDA(cudaMemcpy2DAsync(L.img[s] + (size_t)i0 * d.bpl, d.bpl, src[s] + (size_t)i0 * stride, stride, W, i1 - i0, cudaMemcpyHostToDevice,
                                        L.stream));
         for (int s = 0; s < 2; s++) SVB_TRY(launch_descriptor_rows(d, L.img[s], L.desc[s], 1, g->r0[b], g->r1[b], L.stream));
         SVB_CUDA(cudaEventRecord(g->ev_desc[b], L.stream));

@@ -57,6 +57,8 @@ int make_dims(const svb_params &p, int W, int H, Dims *out) {
     d.W = W;
     d.H = H;
     d.N = W * H;
+    d.bpl = W + 15 - (W - 1) % 16;  // elas.cpp:37
+    d.IN = (size_t)d.bpl * H;
     d.sub = p.subsampling ? 1 : 0;
     d.Dw = d.sub ? W / 2 : W;
     d.Dh = d.sub ? H / 2 : H;
@@ -138,7 +140,8 @@ int lane_create(svb_context *c, Lane &L) {
     SVB_CUDA(cudaEventCreateWithFlags(&L.ev_a, cudaEventDisableTiming));
     SVB_CUDA(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
     for (int s = 0; s < 2; s++) {
-        SVB_TRY(dev_alloc(&L.img[s], C * N));
+        SVB_TRY(dev_alloc(&L.img[s], C * d.IN));
+        SVB_CUDA(cudaMemset(L.img[s], 0, C * d.IN));  // the padding columns are never written again
         {
             // zero-filled guard bands of (disp_max + W + 1024) descriptors in front of and behind the descriptor arena
             const size_t pad = d.desc_pad;
@@ -189,6 +192,7 @@ int lane_create(svb_context *c, Lane &L) {
 void lane_destroy(Lane &L) {
     for (int s = 0; s < 2; s++) {
         cudaFree(L.img[s]);
+        cudaFree(L.img_tight[s]);
         cudaFree(L.desc_base[s]);
         cudaFree(L.tri[s]);
         cudaFree(L.rec[s]);
@@ -836,8 +840,8 @@ int svb_process(svb_context *c, const uint8_t *I1, const uint8_t *I2, int stride
     Lane &L = c->lanes[0];
     const size_t N = (size_t)d.N, C = (size_t)c->chunk;
     // elas.cpp:33-50: rows are copied out of the caller's stride
-    SVB_CUDA(cudaMemcpy2DAsync(L.img[0], d.W, I1, stride, d.W, d.H, cudaMemcpyHostToDevice, L.stream));
-    SVB_CUDA(cudaMemcpy2DAsync(L.img[1], d.W, I2, stride, d.W, d.H, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpy2DAsync(L.img[0], d.bpl, I1, stride, d.W, d.H, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpy2DAsync(L.img[1], d.bpl, I2, stride, d.W, d.H, cudaMemcpyHostToDevice, L.stream));
     SVB_TRY(stage_events_prepare(c, 1));
     StageEvents *se = stage_events_of(c, 0);
     SVB_TRY(stage_a(c, L, L.img[0], L.img[1], 1, se));
@@ -915,7 +919,7 @@ int64_t svb_tap(svb_context *c, const char *name, void *dst, int64_t cap) {
 int svb_stage_descriptor(svb_context *c, const uint8_t *I, int stride, uint8_t *desc_out) {
     STAGE_PROLOG();
     if (!I || !desc_out || stride < d.W) return SVB_ERR_ARG;
-    SVB_CUDA(cudaMemcpy2DAsync(L.img[0], d.W, I, stride, d.W, d.H, cudaMemcpyHostToDevice, L.stream));
+    SVB_CUDA(cudaMemcpy2DAsync(L.img[0], d.bpl, I, stride, d.W, d.H, cudaMemcpyHostToDevice, L.stream));
     SVB_TRY(launch_descriptor(d, L.img[0], L.desc[0], 1, L.stream));
     SVB_CUDA(cudaMemcpyAsync(desc_out, L.desc[0], N * 16, cudaMemcpyDeviceToHost, L.stream));
     SVB_CUDA(cudaStreamSynchronize(L.stream));
@@ -1192,11 +1196,15 @@ int svb_batch_upload(svb_context *c, const uint8_t *left, const uint8_t *right, 
             c->in_img[s] = nullptr;
         }
         c->in_frames = 0;
-        for (int s = 0; s < 2; s++) SVB_TRY(dev_alloc(&c->in_img[s], (size_t)n_frames * N));
+        for (int s = 0; s < 2; s++) {
+            SVB_TRY(dev_alloc(&c->in_img[s], (size_t)n_frames * c->d.IN));
+            SVB_CUDA(cudaMemset(c->in_img[s], 0, (size_t)n_frames * c->d.IN));
+        }
         c->in_frames = n_frames;
     }
-    SVB_CUDA(cudaMemcpy(c->in_img[0], left, (size_t)n_frames * N, cudaMemcpyHostToDevice));
-    SVB_CUDA(cudaMemcpy(c->in_img[1], right, (size_t)n_frames * N, cudaMemcpyHostToDevice));
+    // tight rows on the host, Dims::bpl bytes per line on the device; the rows of consecutive frames follow one another in both
+    SVB_CUDA(cudaMemcpy2D(c->in_img[0], c->d.bpl, left, c->d.W, c->d.W, (size_t)n_frames * c->d.H, cudaMemcpyHostToDevice));
+    SVB_CUDA(cudaMemcpy2D(c->in_img[1], c->d.bpl, right, c->d.W, c->d.W, (size_t)n_frames * c->d.H, cudaMemcpyHostToDevice));
     return SVB_OK;
 }
 
@@ -1214,7 +1222,10 @@ int svb_batch_upload_bgra(svb_context *c, const uint8_t *left_bgra, const uint8_
             c->in_img[s] = nullptr;
         }
         c->in_frames = 0;
-        for (int s = 0; s < 2; s++) SVB_TRY(dev_alloc(&c->in_img[s], (size_t)n_frames * N));
+        for (int s = 0; s < 2; s++) {
+            SVB_TRY(dev_alloc(&c->in_img[s], (size_t)n_frames * c->d.IN));
+            SVB_CUDA(cudaMemset(c->in_img[s], 0, (size_t)n_frames * c->d.IN));
+        }
         c->in_frames = n_frames;
     }
     const int G = c->chunk;  // frames per staging group
@@ -1233,12 +1244,8 @@ int svb_batch_upload_bgra(svb_context *c, const uint8_t *left_bgra, const uint8_
         const uint8_t *src[2] = {left_bgra, right_bgra};
         for (int s = 0; s < 2; s++) {
             SVB_CUDA(cudaMemcpyAsync(c->bgra_batch[s], src[s] + (size_t)f0 * N * 4, (size_t)nf * N * 4, cudaMemcpyHostToDevice, st));
-            // one launch converts the whole group: frames are contiguous in both the staging buffer and the store
-            if ((size_t)nf * N > 0x7FFFFFFFull) {
-                set_error("svb_batch_upload_bgra: group of %d frames too large for one conversion launch", nf);
-                return SVB_ERR_ARG;
-            }
-            SVB_TRY(launch_bgra_to_gray(c->bgra_batch[s], c->in_img[s] + (size_t)f0 * N, (int)((size_t)nf * N), st));
+            // one launch converts the whole group: the rows of its frames follow one another in the staging buffer and in the store
+            SVB_TRY(launch_bgra_to_gray(c->bgra_batch[s], c->in_img[s] + (size_t)f0 * c->d.IN, c->d.W, nf * c->d.H, c->d.bpl, st));
         }
     }
     SVB_CUDA(cudaStreamSynchronize(st));
@@ -1303,11 +1310,18 @@ static int batch_drive(svb_context *c, int n_frames, int flags, const uint8_t *h
         const size_t off = (size_t)k * C * N;
         L.first_frame = k * C;
         if (from_host) {
-            SVB_CUDA(cudaMemcpyAsync(L.img[0], h_left + off, nf * N, cudaMemcpyHostToDevice, L.stream));
-            SVB_CUDA(cudaMemcpyAsync(L.img[1], h_right + off, nf * N, cudaMemcpyHostToDevice, L.stream));
+            // over PCIe as ONE contiguous transfer per side (a pitched host-to-device copy is issued row by row and measured 15 % slower
+            // end to end), then re-pitched to Dims::bpl bytes per line on the device
+            const uint8_t *h_src[2] = {h_left + off, h_right + off};
+            for (int s = 0; s < 2; s++) {
+                if (!L.img_tight[s]) SVB_TRY(dev_alloc(&L.img_tight[s], (size_t)C * N));
+                SVB_CUDA(cudaMemcpyAsync(L.img_tight[s], h_src[s], (size_t)nf * N, cudaMemcpyHostToDevice, L.stream));
+                SVB_CUDA(cudaMemcpy2DAsync(L.img[s], d.bpl, L.img_tight[s], d.W, d.W, (size_t)nf * d.H, cudaMemcpyDeviceToDevice, L.stream));
+            }
             return stage_a(c, L, L.img[0], L.img[1], nf, stage_events_of(c, k));
         }
-        return stage_a(c, L, c->in_img[0] + off, c->in_img[1] + off, nf, stage_events_of(c, k));
+        const size_t off_dev = (size_t)k * C * d.IN;
+        return stage_a(c, L, c->in_img[0] + off_dev, c->in_img[1] + off_dev, nf, stage_events_of(c, k));
     };
     // The host stage runs on its own thread, one chunk ahead of the launches: while this thread queues stage B of
     // chunk k and stage A of chunk k + LANES, the Delaunay workers already triangulate chunk k + 1.  `issued` counts
@@ -1475,8 +1489,8 @@ int svb_point_cloud_bgra(svb_context *c, const uint8_t *left_bgra, const uint8_t
     SVB_CUDA(cudaMemcpyAsync(c->bgra[1], right_bgra, N * 4, cudaMemcpyHostToDevice, L.stream));
     SVB_CUDA(cudaEventRecord(c->ev_pc[0], L.stream));
     // imgCallback_video(): cvtColor(BGRA2GRAY) of both images (stereo_vision.cu:346-347)
-    SVB_TRY(launch_bgra_to_gray(c->bgra[0], L.img[0], d.N, L.stream));
-    SVB_TRY(launch_bgra_to_gray(c->bgra[1], L.img[1], d.N, L.stream));
+    SVB_TRY(launch_bgra_to_gray(c->bgra[0], L.img[0], d.W, d.H, d.bpl, L.stream));
+    SVB_TRY(launch_bgra_to_gray(c->bgra[1], L.img[1], d.W, d.H, d.bpl, L.stream));
     SVB_TRY(stage_events_prepare(c, 1));
     StageEvents *se = stage_events_of(c, 0);
     SVB_TRY(stage_a(c, L, L.img[0], L.img[1], 1, se));
@@ -1527,8 +1541,8 @@ int svb_stage_bgra_to_gray(svb_context *c, const uint8_t *bgra, uint8_t *gray_ou
     if (!bgra || !gray_out) return SVB_ERR_ARG;
     if (!c->bgra[0]) SVB_TRY(dev_alloc(&c->bgra[0], N * 4));
     SVB_CUDA(cudaMemcpyAsync(c->bgra[0], bgra, N * 4, cudaMemcpyHostToDevice, L.stream));
-    SVB_TRY(launch_bgra_to_gray(c->bgra[0], L.img[0], d.N, L.stream));
-    SVB_CUDA(cudaMemcpyAsync(gray_out, L.img[0], N, cudaMemcpyDeviceToHost, L.stream));
+    SVB_TRY(launch_bgra_to_gray(c->bgra[0], L.img[0], d.W, d.H, d.bpl, L.stream));
+    SVB_CUDA(cudaMemcpy2DAsync(gray_out, d.W, L.img[0], d.bpl, d.W, d.H, cudaMemcpyDeviceToHost, L.stream));
     SVB_CUDA(cudaStreamSynchronize(L.stream));
     return SVB_OK;
 }

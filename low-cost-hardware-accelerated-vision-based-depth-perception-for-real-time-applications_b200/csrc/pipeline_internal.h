@@ -19,7 +19,8 @@ struct Lane {
     cudaStream_t stream = nullptr;      // the stream the lane's work is issued on (own_stream, or lane 0's in single-stream mode)
     cudaEvent_t ev_a = nullptr, ev_done = nullptr;
     // device
-    uint8_t *img[2] = {nullptr, nullptr};
+    uint8_t *img[2] = {nullptr, nullptr};        // [chunk][H][bpl]
+    uint8_t *img_tight[2] = {nullptr, nullptr};  // [chunk][H][W] landing buffer of the host-buffer batch path (allocated on first use)
     uint8_t *desc[2] = {nullptr, nullptr};       // = desc_base + padding: the dense matcher's unguarded loads may run a few
     uint8_t *desc_base[2] = {nullptr, nullptr};  //   hundred descriptors past either end of the arena (k_dense.cu)
     int16_t *dcan_raw = nullptr, *dcan = nullptr;

@@ -61,6 +61,9 @@ extern thread_local long long g_launch_counter;  // kernels launched by this lib
 // ---- geometry derived from (params, width, height) ---------------------------------------------
 struct Dims {
     int W, H, N;          // image size, N = W*H
+    int bpl;              // bytes per line of every device-resident input image: W rounded up to 16 (the reference's own padding,
+                          // elas.cpp:37) -- what lets the descriptor kernel fetch its tiles with TMA (row strides must be 16-byte multiples)
+    size_t IN;            // bytes per input image on the device: bpl * H
     int sub;              // param.subsampling: disparities only for even (u, v), maps are (W/2) x (H/2) (elas.h:81-83)
     int Dw, Dh, DN;       // disparity map size: W x H, or W/2 x H/2 with subsampling; DN = Dw*Dh
     int step, cw, ch;     // candidate grid (elas.cpp:376-386)
@@ -107,6 +110,7 @@ enum StageId {
 
 // ---- kernel launchers (each one is batched: `nimg`/`nf` independent images or frames) ----------
 // k_descriptor.cu
+// img: nimg images of d.IN bytes each, d.bpl bytes per line
 int launch_descriptor(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, cudaStream_t s);
 // *_rows variants restrict a stage to image rows [row0, row1) / lattice rows [vc0, vc1): the row-band split (band_split.cu)
 int launch_descriptor_rows(const Dims &d, const uint8_t *img, uint8_t *desc, int nimg, int row0, int row1, cudaStream_t s);  // d.sub: even rows only
@@ -182,6 +186,7 @@ int launch_reproject(const Dims &d, const Calib &c, const float *D, uint8_t *dma
 int launch_reproject_float(const Dims &d, const Calib &c, const float *D, double *points, int nf, cudaStream_t s);
 int launch_reproject_u8(const Calib &c, const uint8_t *dmap, double *points, int W, int H, cudaStream_t s);
 // k_convert.cu
-int launch_bgra_to_gray(const uint8_t *bgra, uint8_t *gray, int n, cudaStream_t s);
+// bgra: rows x W pixels, tight; gray: rows of `pitch` bytes (rows may span several frames stored back to back)
+int launch_bgra_to_gray(const uint8_t *bgra, uint8_t *gray, int W, int rows, int pitch, cudaStream_t s);
 
 }  // namespace svb
