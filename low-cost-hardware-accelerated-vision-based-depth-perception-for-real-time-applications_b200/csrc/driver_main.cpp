@@ -19,6 +19,7 @@
 #include <sys/stat.h>
 
 #include <chrono>
+#include <future>
 #include <string>
 #include <vector>
 
@@ -306,10 +307,28 @@ int main(int argc, const char **argv) {
     }
     const bool resize = W != inW || H != inH;
     double FPS = 0;
+    // imageLoop reads and decodes frame i+1 while frame i is on the GPU (the reference's loop is synchronous, stereo_vision.cu:645-697;
+    // the per-frame timer starts behind imread there as well, so the printed FPS figures mean the same thing)
+    struct DecodedPair {
+        std::vector<uint8_t> l, r;
+        bool ok = false;
+    };
+    auto decode_pair = [&o, inW, inH](unsigned i) {
+        DecodedPair d;
+        d.ok = load_bgra(frame_path(o.kitti_path, "image_02", i), inW, inH, &d.l) && load_bgra(frame_path(o.kitti_path, "image_03", i), inW, inH, &d.r);
+        return d;
+    };
+    std::future<DecodedPair> ahead;
+    if (max_files > 0) ahead = std::async(std::launch::async, decode_pair, 0u);
     for (unsigned i = 0; i < max_files; i++) {
-        if (!load_bgra(frame_path(o.kitti_path, "image_02", i), inW, inH, resize ? &left_in : &left) ||
-            !load_bgra(frame_path(o.kitti_path, "image_03", i), inW, inH, resize ? &right_in : &right))
+        DecodedPair cur = ahead.get();
+        if (i + 1 < max_files) ahead = std::async(std::launch::async, decode_pair, i + 1);
+        if (!cur.ok) {
+            if (ahead.valid()) ahead.wait();
             break;
+        }
+        (resize ? left_in : left).swap(cur.l);
+        (resize ? right_in : right).swap(cur.r);
         const auto t0 = std::chrono::steady_clock::now();  // start_timer(t_start) after imread (:664)
         if (resize) {  // resize(left_img, left_img_OLD, out_img_size) (:665,676)
             left.resize(N * 4);

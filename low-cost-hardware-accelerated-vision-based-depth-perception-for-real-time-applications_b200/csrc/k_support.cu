@@ -491,12 +491,16 @@ int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dca
     SVB_LAUNCH_CHECK();
     const size_t smem = ((size_t)d.cw * d.ch * sizeof(int16_t) + 3) & ~(size_t)3;  // whole 32-bit words: the sweep marks cells with word atomics
     if (smem <= 200 * 1024) {
-        if (smem > 48 * 1024) {  // opt in to large dynamic shared memory (per device, so not cached in a static)
+        static bool configured[64] = {};  // per device: opt in to large dynamic shared memory once, not on every launch
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (smem > 48 * 1024 && dev >= 0 && dev < 64 && !configured[dev]) {
             cudaError_t e = cudaFuncSetAttribute(k_support_filter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) {
                 set_error("cudaFuncSetAttribute(k_support_filter): %s", cudaGetErrorString(e));
                 return SVB_ERR_CUDA;
             }
+            configured[dev] = true;
         }
         k_support_filter<true><<<nf, SF_THREADS, smem, s>>>(dcan, support, nsupport, h_support, h_nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
                                                             p.incon_threshold, p.incon_min_support, p.add_corners, d.maxS);

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Large-batch determinism check: the same 512 frames through the multi-lane pipeline twice, through the single-stream
-pipeline, and with the device vertex order off; every disparity map and point cloud must agree bit for bit."""
+"""Large-batch determinism check: the same 512 frames through the multi-lane pipeline twice, through the single-stream pipeline,
+with the device vertex order off, with the whole Delaunay stage on the host, with the stage-by-stage tail kernels, and -- on the
+reference's own frames, where two thirds of the right-image lists hold duplicate coordinates -- with the vertex-sort replay on the
+device and on the host; every disparity map and point cloud must agree bit for bit."""
 import hashlib
 import os
 import sys
@@ -43,6 +45,18 @@ b = run(False)
 c = run(True)
 d = run(False, {"SVB_GPU_ORDER": "0"})
 e = run(False, {"SVB_LANES": "6"})
-print("multi-lane", a[:16], b[:16], "single-stream", c[:16], "host vertex order", d[:16], "6 lanes", e[:16])
-assert a == b == c == d == e, "outputs differ between runs"
-print("stress_determinism: OK (%d frames)" % n)
+f = run(False, {"SVB_DELAUNAY_DEVICE": "0"})
+g = run(False, {"SVB_FUSED_POST": "0"})
+print("multi-lane", a[:16], b[:16], "single-stream", c[:16], "host vertex order", d[:16], "6 lanes", e[:16], "host Delaunay", f[:16], "unfused tail", g[:16])
+assert a == b == c == d == e == f == g, "outputs differ between runs"
+# the reference's own frames (duplicate coordinates in the right image)
+z = np.load(os.path.join(ROOT, "tests", "golden", "kitti_gray.npz"))
+npairs = len([k for k in z.files if k.startswith("L")])
+n = (min(n, 252) // npairs) * npairs
+Ls = np.ascontiguousarray(np.stack([z["L%d" % (i % npairs)] for i in range(n)]))
+Rs = np.ascontiguousarray(np.stack([z["R%d" % (i % npairs)] for i in range(n)]))
+k = [run(False, {"SVB_DELAUNAY_DUPS": "device"}), run(False, {"SVB_DELAUNAY_DUPS": "host"}), run(True, {"SVB_DELAUNAY_DUPS": "device"}),
+     run(False, {"SVB_DELAUNAY_DEVICE": "0"})]
+print("kitti_mini: replay on device", k[0][:16], "on host", k[1][:16], "single-stream", k[2][:16], "host Delaunay", k[3][:16])
+assert len(set(k)) == 1, "kitti outputs differ between runs"
+print("stress_determinism: OK (%d synthetic + %d kitti frames)" % (len(pairs), n))
