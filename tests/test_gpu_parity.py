@@ -496,3 +496,50 @@ def test_non_preset_prior_parameters(svb, ref, kitti_gray, gamma, beta, sigma, s
         assert_float_bar(res)
     finally:
         ctx.close()
+
+
+def _random_params(rng):
+    """A random point of Elas::parameters' space (elas.h:58-83) inside what the reference itself handles."""
+    sigma = float(rng.choice([0.7, 1.0, 1.5]))
+    sradius = float(rng.choice([2.0, 3.0]))
+    return dict(
+        disp_min=int(rng.choice([0, 0, 2])), disp_max=int(rng.choice([63, 127, 255])),
+        support_threshold=float(rng.choice([0.8, 0.85, 0.95])), support_texture=int(rng.choice([5, 10, 20])),
+        candidate_stepsize=int(rng.choice([3, 5, 7])), incon_window_size=int(rng.choice([3, 5])), incon_threshold=int(rng.choice([3, 5, 7])),
+        incon_min_support=int(rng.choice([3, 5])), add_corners=int(rng.integers(0, 2)), grid_size=int(rng.choice([12, 20, 31])),
+        beta=float(rng.choice([0.02, 0.03])), gamma=float(rng.choice([3.0, 5.0, 8.0])), sigma=sigma, sradius=sradius,
+        match_texture=int(rng.choice([0, 1, 4])), lr_threshold=int(rng.choice([1, 2, 3])), speckle_sim_threshold=float(rng.choice([1.0, 2.0])),
+        speckle_size=int(rng.choice([50, 200, 400])), ipol_gap_width=int(rng.choice([3, 7, 5000])), filter_median=int(rng.integers(0, 2)),
+        filter_adaptive_mean=int(rng.integers(0, 2)), postprocess_only_left=int(rng.integers(0, 2)), subsampling=0)
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_random_parameter_sets_against_the_oracle(svb, ref, kitti_gray, seed):
+    """Elas::parameters is a public drop-in struct: a dozen random parameter sets (lattice step, grid size, windows, thresholds,
+    prior shape and plane radius, filters on / off, corners, gap width, both-map post-processing) on a real frame and on a ragged
+    synthetic one, with and without subsampling, final maps bit for bit against the oracle; the raw integer maps too (tap mode) for
+    every third set."""
+    rng = np.random.default_rng(1000 + seed)
+    over = _random_params(rng)
+    if seed % 4 == 3:
+        over["subsampling"] = 1  # half-resolution maps (elas.h:81-83)
+    if seed % 2 == 0:
+        L, R = kitti_gray["L%d" % (seed % 21)], kitti_gray["R%d" % (seed % 21)]
+        L, R = np.ascontiguousarray(L[40:300, 100:900]), np.ascontiguousarray(R[40:300, 100:900])  # 800 x 260 crop
+    else:
+        L, R = svb.synth_pair(50 + seed, 517, 203, seed & 2)
+    H, W = L.shape
+    p = svb.default_params(svb.ROBOTICS, **over)
+    p_ref = ref.params(0, **over)
+    ctx = svb.Context(p, W, H)
+    try:
+        want1, want2, _ = ref.process(p_ref, L, R)
+        if seed % 3 == 0:
+            res, _, (D1, D2) = parity.staged_parity(ctx, ref, p_ref, L, R, inject=False)
+            assert_all_equal(res)
+        else:
+            D1, D2 = ctx.process(L, R)
+        assert np.array_equal(D1, parity.half(want1, ctx)), over
+        assert np.array_equal(D2, parity.half(want2, ctx)), over
+    finally:
+        ctx.close()
