@@ -213,7 +213,7 @@ int svb_band_process(svb_band_group *g, const uint8_t *I1, const uint8_t *I2, in
                           g));
     }
     SVB_TRY(launch_dcan_border(d, L0.dcan_raw, 1, L0.stream));
-    SVB_TRY(launch_support_filter(d, p, L0.dcan_raw, L0.dcan, L0.support, L0.nsupport, L0.h_support, L0.h_nsupport, 1, L0.stream));
+    SVB_TRY(launch_support_filter(d, p, L0.dcan_raw, L0.dcan, L0.support, L0.nsupport, L0.h_support, L0.h_nsupport, L0.sf_changed, 1, L0.stream));
     SVB_CUDA(cudaEventRecord(L0.ev_a, L0.stream));
     // ---- 6: host Delaunay -----------------------------------------------------------------------------------
     c0->stats.delaunay_ms_total = c0->stats.delaunay_ms_wall = 0;

@@ -3,6 +3,8 @@
 //
 // Replaces Elas::computeMatchingDisparity / computeSupportMatches / removeInconsistentSupportPoints /
 // removeRedundantSupportPoints / addCornerSupportPoints (src/serial_includes/elas/elas.cpp:152-440).
+#include <stdlib.h>
+
 #include "svb_internal.h"
 
 namespace svb {
@@ -267,12 +269,22 @@ __global__ void __launch_bounds__(256) k_incon_first_sweep(const int16_t *__rest
 
 // SMEM = true: the lattice lives in shared memory (2 bytes per cell; every frame size up to about 1080p at step 5);
 // SMEM = false: it is worked on in place in the global dcan array (4K frames).
+// phases: which parts of the filter chain this launch runs.  Small lattices do everything in one launch; large ones (4K frames) run
+// the sweeps and the redundant-point passes as multi-CTA kernels (below) and use this kernel for what is left:
+//   SF_PH_MARK | SF_PH_SWEEP  inconsistent points to the fixpoint (SF_PH_MARK: first mark the windows of the cells the first sweep removed;
+//                             without it the marks of bit `first_bit` are already in place -- the multi-CTA sweeps were cut off before
+//                             the fixpoint, `unconverged` != 0)
+//   SF_PH_FINAL               flags -> final lattice values;   SF_PH_REDUNDANT  vertical, then horizontal redundant-point pass
+//   SF_PH_COMPACT             ordered compaction, corner points, host copy
+constexpr int SF_PH_MARK = 1, SF_PH_SWEEP = 2, SF_PH_FINAL = 4, SF_PH_REDUNDANT = 8, SF_PH_COMPACT = 16, SF_PH_ALL = 31;
+
 template <bool SMEM>
 __global__ void __launch_bounds__(SF_THREADS) k_support_filter(int16_t *__restrict__ dcan_all,
                                                                int32_t *__restrict__ support_all, int32_t *__restrict__ nsupport_all,
                                                                int32_t *__restrict__ h_support_all, int32_t *__restrict__ h_nsupport_all, int W,
                                                                int H, int cw, int ch, int step, int incon_window, int incon_threshold,
-                                                               int incon_min_support, int add_corners, int maxS) {
+                                                               int incon_min_support, int add_corners, int maxS, int phases, int first_bit,
+                                                               const int32_t *__restrict__ unconverged, int unconverged_stride) {
     extern __shared__ int16_t s_lattice[];
     const int f = blockIdx.x;
     const int tid = threadIdx.x;
@@ -285,6 +297,8 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(int16_t *__restri
     __shared__ int s_warp_tot[SF_THREADS / 32];
     __shared__ int s_base;
     __shared__ unsigned long long s_best[4];
+    // the last multi-CTA sweep removed nothing: the fixpoint is reached, nothing to do
+    if (phases == SF_PH_SWEEP && unconverged && unconverged[f * unconverged_stride] == 0) return;
 
     // dcan already holds the result of the first sweep (k_incon_first_sweep): raw values, SF_REMOVED where it struck
     if (SMEM) {
@@ -298,17 +312,18 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(int16_t *__restri
     // The removals of the first sweep mark their windows here.
     // in global memory the flag atomics act in L2: the cells are read around L1 for as long as flags are in play
     auto cell = [&](int idx) -> int { return SMEM ? (int)work[idx] : (int)__ldcg(work + idx); };
-    int cur_bit = SF_MARK_A, next_bit = SF_MARK_B;
-    for (int i = tid; i < cells; i += SF_THREADS) {
-        const int e = cell(i);
-        if (e < 0 || !(e & SF_REMOVED)) continue;
-        const int v = i / cw, u = i - v * cw;
-        for (int v2 = max(v - incon_window, 0); v2 <= min(v + incon_window, ch - 1); v2++)
-            for (int u2 = max(u - incon_window, 0); u2 <= min(u + incon_window, cw - 1); u2++)
-                if (cell(v2 * cw + u2) >= 0) cell_set(work + v2 * cw + u2, cur_bit);
-    }
+    int cur_bit = first_bit, next_bit = first_bit == SF_MARK_A ? SF_MARK_B : SF_MARK_A;
+    if (phases & SF_PH_MARK)
+        for (int i = tid; i < cells; i += SF_THREADS) {
+            const int e = cell(i);
+            if (e < 0 || !(e & SF_REMOVED)) continue;
+            const int v = i / cw, u = i - v * cw;
+            for (int v2 = max(v - incon_window, 0); v2 <= min(v + incon_window, ch - 1); v2++)
+                for (int u2 = max(u - incon_window, 0); u2 <= min(u + incon_window, cw - 1); u2++)
+                    if (cell(v2 * cw + u2) >= 0) cell_set(work + v2 * cw + u2, cur_bit);
+        }
     __syncthreads();
-    while (true) {
+    while (phases & SF_PH_SWEEP) {
         if (tid == 0) s_changed = 0;
         __syncthreads();
         for (int i = tid; i < cells; i += SF_THREADS) {
@@ -344,46 +359,56 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(int16_t *__restri
         cur_bit = next_bit;
         next_bit = t;
     }
-    for (int i = tid; i < cells; i += SF_THREADS) {
-        const int e = cell(i);
-        if (e >= 0) work[i] = (e & SF_REMOVED) ? (int16_t)-1 : (int16_t)(e & SF_VALUE);
-    }
+    if (phases & SF_PH_FINAL)
+        for (int i = tid; i < cells; i += SF_THREADS) {
+            const int e = cell(i);
+            if (e >= 0) work[i] = (e & SF_REMOVED) ? (int16_t)-1 : (int16_t)(e & SF_VALUE);
+        }
     __syncthreads();
 
     // ---- redundant points: vertical pass (columns independent), then horizontal pass (rows independent) ----
-    for (int u = tid; u < cw; u += SF_THREADS) redundant_line(work, u, cw, ch);
-    __syncthreads();
-    for (int v = tid; v < ch; v += SF_THREADS) redundant_line(work, v * cw, 1, cw);
-    __syncthreads();
+    if (phases & SF_PH_REDUNDANT) {
+        for (int u = tid; u < cw; u += SF_THREADS) redundant_line(work, u, cw, ch);
+        __syncthreads();
+        for (int v = tid; v < ch; v += SF_THREADS) redundant_line(work, v * cw, 1, cw);
+        __syncthreads();
+    }
     if (SMEM)
         for (int i = tid; i < cells; i += SF_THREADS) dcan[i] = work[i];
+    if (!(phases & SF_PH_COMPACT)) return;
 
     // ---- ordered compaction: u_can outer, v_can inner, both from 1 (elas.cpp:424-428) ----
-    const int inner = ch - 1;
-    const int total = (cw - 1) * inner;
+    // Column-wise: a thread counts the surviving cells of its lattice column, one block-wide exclusive scan over the columns gives
+    // every column its place in the list, and the thread writes its column's points in v order.  (A scan over the flattened cells
+    // needs cells / 1024 block-wide steps: 324 of them at 4K.)
     if (tid == 0) s_base = 0;
     __syncthreads();
     const int lane = tid & 31, wid = tid >> 5;
-    for (int start = 0; start < total; start += SF_THREADS) {
-        const int i = start + tid;
-        int uc = 0, vc = 0, dd = -1;
-        if (i < total) {
-            uc = 1 + i / inner;
-            vc = 1 + i - (uc - 1) * inner;
-            dd = work[vc * cw + uc];
+    for (int u0 = 1; u0 < cw; u0 += SF_THREADS) {
+        const int uc = u0 + tid;
+        int cnt = 0;
+        if (uc < cw)
+            for (int vc = 1; vc < ch; vc++) cnt += work[vc * cw + uc] >= 0 ? 1 : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
         }
-        const bool keep = dd >= 0;
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-        if (lane == 0) s_warp_tot[wid] = __popc(bal);
+        if (lane == 31) s_warp_tot[wid] = incl;
         __syncthreads();
-        int off = s_base;
+        int off = s_base + incl - cnt;
         for (int w = 0; w < wid; w++) off += s_warp_tot[w];
-        if (keep) {
-            const int pos = off + __popc(bal & ((1u << lane) - 1u));
-            support[3 * pos + 0] = uc * step;
-            support[3 * pos + 1] = vc * step;
-            support[3 * pos + 2] = dd;
-        }
+        if (uc < cw && cnt > 0)
+            for (int vc = 1; vc < ch; vc++) {
+                const int dd = work[vc * cw + uc];
+                if (dd >= 0) {
+                    support[3 * off + 0] = uc * step;
+                    support[3 * off + 1] = vc * step;
+                    support[3 * off + 2] = dd;
+                    off++;
+                }
+            }
         __syncthreads();
         if (tid == 0) {
             int t = 0;
@@ -445,6 +470,97 @@ __global__ void __launch_bounds__(SF_THREADS) k_support_filter(int16_t *__restri
     }
 }
 
+
+// ---- multi-CTA form of the lattice filters for lattices that do not fit one CTA's shared memory (4K frames: 768 x 432 cells) ----
+// The same fixpoint iteration as in k_support_filter, one kernel launch per sweep (the launch boundary is the grid-wide barrier), on
+// the lattice in global memory; flags are read around L1 (__ldcg) because the flag atomics act in L2.
+// grid: (ceil(cells / 256), nf)
+__global__ void __launch_bounds__(256) k_incon_mark(int16_t *__restrict__ dcan_all, int cw, int ch, int incon_window) {
+    const int cells = cw * ch;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    int16_t *work = dcan_all + (size_t)blockIdx.y * (unsigned)cells;
+    const int e = __ldcg(work + i);
+    if (e < 0 || !(e & SF_REMOVED)) return;
+    const int v = i / cw, u = i - v * cw;
+    for (int v2 = max(v - incon_window, 0); v2 <= min(v + incon_window, ch - 1); v2++)
+        for (int u2 = max(u - incon_window, 0); u2 <= min(u + incon_window, cw - 1); u2++)
+            if (__ldcg(work + v2 * cw + u2) >= 0) cell_set(work + v2 * cw + u2, SF_MARK_A);
+}
+
+// One sweep: cells marked `cur_bit` are re-examined; changed[f * stride + it] = 1 if the sweep removed something (then the next one
+// has work).  A sweep whose predecessor changed nothing returns at once.
+__global__ void __launch_bounds__(256) k_incon_sweep(int16_t *__restrict__ dcan_all, int32_t *__restrict__ changed, int stride, int it, int cw, int ch,
+                                                    int incon_window, int incon_threshold, int incon_min_support) {
+    const int f = blockIdx.y;
+    if (it > 0 && changed[f * stride + it - 1] == 0) return;
+    const int cells = cw * ch;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    int16_t *work = dcan_all + (size_t)f * (unsigned)cells;
+    const int cur_bit = (it & 1) ? SF_MARK_B : SF_MARK_A, next_bit = (it & 1) ? SF_MARK_A : SF_MARK_B;
+    const int e = __ldcg(work + i);
+    if (e < 0 || (e & SF_REMOVED) || !(e & cur_bit)) return;
+    cell_clear(work + i, cur_bit);
+    const int dc = e & SF_VALUE;
+    const int v = i / cw, u = i - v * cw;
+    const int u_lo = max(u - incon_window, 0), u_hi = min(u + incon_window, cw - 1);
+    const int v_lo = max(v - incon_window, 0), v_hi = min(v + incon_window, ch - 1);
+    int support_cnt = 0;
+    for (int v2 = v_lo; v2 <= v_hi && support_cnt < incon_min_support; v2++)
+        for (int u2 = u_lo; u2 <= u_hi; u2++) {
+            const int e2 = __ldcg(work + v2 * cw + u2);
+            if (e2 < 0) continue;
+            if (abs(dc - (e2 & SF_VALUE)) > incon_threshold) continue;
+            if ((e2 & SF_REMOVED) && precedes_colmajor(u2, v2, u, v)) continue;
+            support_cnt++;
+        }
+    if (support_cnt < incon_min_support) {
+        changed[f * stride + it] = 1;
+        cell_set(work + i, SF_REMOVED);
+        for (int v2 = v_lo; v2 <= v_hi; v2++)
+            for (int u2 = u_lo; u2 <= u_hi; u2++)
+                if (__ldcg(work + v2 * cw + u2) >= 0) cell_set(work + v2 * cw + u2, next_bit);
+    }
+}
+
+// Final lattice values + vertical redundant-point pass: a CTA stages RV_COLS lattice columns in shared memory (a walk along a column
+// in global memory pays an L2 round trip per step: 432 dependent loads per column at 4K), one thread per column.
+// grid: (ceil(cw / RV_COLS), nf), RV_COLS threads; dynamic smem: ch * RV_COLS int16
+constexpr int RV_COLS = 32;
+__global__ void __launch_bounds__(RV_COLS) k_lattice_vertical(int16_t *__restrict__ dcan_all, int cw, int ch) {
+    extern __shared__ int16_t s_strip[];
+    int16_t *dcan = dcan_all + (size_t)blockIdx.y * (unsigned)(cw * ch);
+    const int u = blockIdx.x * RV_COLS + threadIdx.x;
+    const bool in = u < cw;
+    for (int v = 0; v < ch; v++) {
+        int e = in ? (int)dcan[v * cw + u] : -1;
+        if (e >= 0) e = (e & SF_REMOVED) ? -1 : (e & SF_VALUE);  // the inconsistent-point filter's verdict
+        s_strip[v * RV_COLS + threadIdx.x] = (int16_t)e;
+    }
+    if (!in) return;
+    redundant_line(s_strip, threadIdx.x, RV_COLS, ch);
+    for (int v = 0; v < ch; v++) dcan[v * cw + u] = s_strip[v * RV_COLS + threadIdx.x];
+}
+
+// Horizontal redundant-point pass: RH_ROWS lattice rows per CTA in shared memory, one thread per row; the row stride is an odd number
+// of 32-bit words so that the 32 threads, which all stand at the same column, hit different banks.
+// grid: (ceil(ch / RH_ROWS), nf), RH_ROWS threads; dynamic smem: RH_ROWS * stride int16
+constexpr int RH_ROWS = 16;
+__global__ void __launch_bounds__(RH_ROWS) k_lattice_horizontal(int16_t *__restrict__ dcan_all, int cw, int ch, int stride) {
+    extern __shared__ int16_t s_rows[];
+    int16_t *dcan = dcan_all + (size_t)blockIdx.y * (unsigned)(cw * ch);
+    const int v0 = blockIdx.x * RH_ROWS;
+    const int rows = min(RH_ROWS, ch - v0);
+    for (int r = 0; r < rows; r++)
+        for (int u = threadIdx.x; u < cw; u += RH_ROWS) s_rows[r * stride + u] = dcan[(v0 + r) * cw + u];
+    __syncthreads();
+    if ((int)threadIdx.x < rows) redundant_line(s_rows, threadIdx.x * stride, 1, cw);
+    __syncthreads();
+    for (int r = 0; r < rows; r++)
+        for (int u = threadIdx.x; u < cw; u += RH_ROWS) dcan[(v0 + r) * cw + u] = s_rows[r * stride + u];
+}
+
 }  // namespace
 
 int launch_dcan_border(const Dims &d, int16_t *dcan_raw, int nf, cudaStream_t s) {
@@ -478,7 +594,7 @@ int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc
 }
 
 int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dcan_raw, int16_t *dcan, int32_t *support, int32_t *nsupport,
-                          int32_t *h_support, int32_t *h_nsupport, int nf, cudaStream_t s) {
+                          int32_t *h_support, int32_t *h_nsupport, int32_t *changed, int nf, cudaStream_t s) {
     if (nf <= 0) return SVB_OK;
     if (p.disp_max > SF_VALUE) {
         set_error("support filter: disp_max %d too large for the lattice cell encoding", p.disp_max);
@@ -490,7 +606,10 @@ int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dca
                                                                              p.incon_min_support);
     SVB_LAUNCH_CHECK();
     const size_t smem = ((size_t)d.cw * d.ch * sizeof(int16_t) + 3) & ~(size_t)3;  // whole 32-bit words: the sweep marks cells with word atomics
-    if (smem <= 200 * 1024) {
+    // SVB_SF_MULTI=1 sends every lattice down the multi-CTA path, SVB_SF_SWEEPS=n (1 .. 8) cuts its sweeps short so that the one-CTA
+    // finisher has work: what the tests use to exercise both on small frames
+    static const bool force_multi = getenv("SVB_SF_MULTI") && atoi(getenv("SVB_SF_MULTI")) != 0;
+    if (smem <= 200 * 1024 && !force_multi) {
         static bool configured[64] = {};  // per device: opt in to large dynamic shared memory once, not on every launch
         int dev = 0;
         cudaGetDevice(&dev);
@@ -503,11 +622,50 @@ int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dca
             configured[dev] = true;
         }
         k_support_filter<true><<<nf, SF_THREADS, smem, s>>>(dcan, support, nsupport, h_support, h_nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
-                                                            p.incon_threshold, p.incon_min_support, p.add_corners, d.maxS);
-    } else {
-        k_support_filter<false><<<nf, SF_THREADS, 0, s>>>(dcan, support, nsupport, h_support, h_nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
-                                                          p.incon_threshold, p.incon_min_support, p.add_corners, d.maxS);
+                                                            p.incon_threshold, p.incon_min_support, p.add_corners, d.maxS, SF_PH_ALL, SF_MARK_A, nullptr, 0);
+        SVB_LAUNCH_CHECK();
+        return SVB_OK;
     }
+    // ---- large lattices (4K): sweeps and redundant-point passes as multi-CTA kernels, k_support_filter for what is left ----
+    if (!changed) {
+        set_error("support filter: a lattice of %d x %d cells needs the sweep scratch buffer", d.cw, d.ch);
+        return SVB_ERR_ARG;
+    }
+    const int cells = d.cw * d.ch;
+    const dim3 cgrid((cells + 255) / 256, nf);
+    constexpr int STRIDE = 8;  // per frame: one "this sweep removed something" flag per sweep
+    static_assert(STRIDE <= SUPPORT_FILTER_SCRATCH_INTS, "scratch size");
+    static const int sweeps_env = getenv("SVB_SF_SWEEPS") ? atoi(getenv("SVB_SF_SWEEPS")) : STRIDE;
+    const int SWEEPS = sweeps_env < 1 ? 1 : (sweeps_env > STRIDE ? STRIDE : sweeps_env);
+    SVB_CUDA(cudaMemsetAsync(changed, 0, sizeof(int32_t) * STRIDE * (size_t)nf, s));
+    k_incon_mark<<<cgrid, 256, 0, s>>>(dcan, d.cw, d.ch, p.incon_window_size);
+    SVB_LAUNCH_CHECK();
+    for (int it = 0; it < SWEEPS; it++) {
+        k_incon_sweep<<<cgrid, 256, 0, s>>>(dcan, changed, STRIDE, it, d.cw, d.ch, p.incon_window_size, p.incon_threshold, p.incon_min_support);
+        SVB_LAUNCH_CHECK();
+    }
+    // not at the fixpoint after SWEEPS sweeps (the last one still removed cells; marks of bit SWEEPS & 1 are pending): one CTA per
+    // frame finishes the iteration
+    k_support_filter<false><<<nf, SF_THREADS, 0, s>>>(dcan, support, nsupport, h_support, h_nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
+                                                      p.incon_threshold, p.incon_min_support, p.add_corners, d.maxS, SF_PH_SWEEP,
+                                                      (SWEEPS & 1) ? SF_MARK_B : SF_MARK_A, changed + SWEEPS - 1, STRIDE);
+    SVB_LAUNCH_CHECK();
+    {
+        const size_t sm = (size_t)d.ch * RV_COLS * sizeof(int16_t);
+        if (sm > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k_lattice_vertical, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_lattice_vertical<<<dim3((d.cw + RV_COLS - 1) / RV_COLS, nf), RV_COLS, sm, s>>>(dcan, d.cw, d.ch);
+        SVB_LAUNCH_CHECK();
+    }
+    {
+        int stride = (d.cw + 1) & ~1;           // int16 units, even
+        if (((stride / 2) & 1) == 0) stride += 2;  // an odd number of 32-bit words
+        const size_t sm = (size_t)RH_ROWS * stride * sizeof(int16_t);
+        if (sm > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k_lattice_horizontal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_lattice_horizontal<<<dim3((d.ch + RH_ROWS - 1) / RH_ROWS, nf), RH_ROWS, sm, s>>>(dcan, d.cw, d.ch, stride);
+        SVB_LAUNCH_CHECK();
+    }
+    k_support_filter<false><<<nf, SF_THREADS, 0, s>>>(dcan, support, nsupport, h_support, h_nsupport, d.W, d.H, d.cw, d.ch, d.step, p.incon_window_size,
+                                                      p.incon_threshold, p.incon_min_support, p.add_corners, d.maxS, SF_PH_COMPACT, SF_MARK_A, nullptr, 0);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

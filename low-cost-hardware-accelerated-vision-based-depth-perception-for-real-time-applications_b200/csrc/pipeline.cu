@@ -159,6 +159,7 @@ int lane_create(svb_context *c, Lane &L) {
     SVB_TRY(dev_alloc(&L.dcan, C * d.cw * d.ch + 2));  // + 2: the filters set flag bits with 32-bit atomics on the word holding a cell
     SVB_TRY(dev_alloc(&L.support, C * d.maxS * 3));
     SVB_TRY(dev_alloc(&L.nsupport, C));
+    SVB_TRY(dev_alloc(&L.sf_changed, C * SUPPORT_FILTER_SCRATCH_INTS));
     SVB_TRY(dev_alloc(&L.ntri, C * 3));
     L.trioff = L.ntri + 2 * C;
     SVB_TRY(dev_alloc(&L.grid_tmp, C * 2 * d.gw * d.gh * d.gwords));
@@ -204,6 +205,7 @@ void lane_destroy(Lane &L) {
     cudaFree(L.dcan);
     cudaFree(L.support);
     cudaFree(L.nsupport);
+    cudaFree(L.sf_changed);
     cudaFree(L.ntri);
     cudaFree(L.grid_tmp);
     cudaFree(L.Draw);
@@ -315,7 +317,7 @@ int stage_a(svb_context *c, Lane &L, const uint8_t *img1, const uint8_t *img2, i
     SVB_TRY(launch_support_match(d, c->p, L.desc[0], L.desc[1], L.dcan_raw, nf, L.stream));
     SVB_TRY(T.mark(ST_SUPPORT_FILTER));
     // the kernel writes the lists into the mapped pinned buffers itself: no device-to-host copy is queued
-    SVB_TRY(launch_support_filter(d, c->p, L.dcan_raw, L.dcan, L.support, L.nsupport, L.h_support, L.h_nsupport, nf, L.stream));
+    SVB_TRY(launch_support_filter(d, c->p, L.dcan_raw, L.dcan, L.support, L.nsupport, L.h_support, L.h_nsupport, L.sf_changed, nf, L.stream));
     SVB_TRY(T.mark(ST_DELAUNAY_DEVICE));
     // ... and the order in which the host's divide-and-conquer will meet the vertices (sort + alternating cuts)
     L.unpacked = false;
@@ -933,7 +935,7 @@ int svb_stage_support(svb_context *c, const uint8_t *desc1, const uint8_t *desc2
     SVB_CUDA(cudaMemcpyAsync(L.desc[0], desc1, N * 16, cudaMemcpyHostToDevice, L.stream));
     SVB_CUDA(cudaMemcpyAsync(L.desc[1], desc2, N * 16, cudaMemcpyHostToDevice, L.stream));
     SVB_TRY(launch_support_match(d, c->p, L.desc[0], L.desc[1], L.dcan_raw, 1, L.stream));
-    SVB_TRY(launch_support_filter(d, c->p, L.dcan_raw, L.dcan, L.support, L.nsupport, L.h_support, L.h_nsupport, 1, L.stream));
+    SVB_TRY(launch_support_filter(d, c->p, L.dcan_raw, L.dcan, L.support, L.nsupport, L.h_support, L.h_nsupport, L.sf_changed, 1, L.stream));
     const size_t cb = (size_t)d.cw * d.ch * 2;
     if (dcan_raw) SVB_CUDA(cudaMemcpyAsync(dcan_raw, L.dcan_raw, cb, cudaMemcpyDeviceToHost, L.stream));
     if (dcan) SVB_CUDA(cudaMemcpyAsync(dcan, L.dcan, cb, cudaMemcpyDeviceToHost, L.stream));

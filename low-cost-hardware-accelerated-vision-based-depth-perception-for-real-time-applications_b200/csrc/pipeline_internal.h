@@ -25,6 +25,7 @@ struct Lane {
     uint8_t *desc_base[2] = {nullptr, nullptr};  //   hundred descriptors past either end of the arena (k_dense.cu)
     int16_t *dcan_raw = nullptr, *dcan = nullptr;
     int32_t *support = nullptr, *nsupport = nullptr;
+    int32_t *sf_changed = nullptr;  // per-sweep flags of the multi-CTA lattice filter (k_support.cu)
     int32_t *tri[2] = {nullptr, nullptr};
     int32_t *ntri = nullptr;    // [2*chunk] triangle counts (2f + side), then [chunk] first triangle of frame f in tri[]
     int32_t *trioff = nullptr;  // = ntri + 2*chunk

@@ -133,9 +133,11 @@ int launch_support_match(const Dims &d, const svb_params &p, const uint8_t *desc
 int launch_dcan_border(const Dims &d, int16_t *dcan_raw, int nf, cudaStream_t s);
 int launch_support_match_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int nf, int vc0,
                               int vc1, cudaStream_t s);
-// h_support / h_nsupport: device-accessible (mapped pinned) host copies written by the kernel itself, may be null
+// h_support / h_nsupport: device-accessible (mapped pinned) host copies written by the kernel itself, may be null;
+// changed: device scratch of SUPPORT_FILTER_SCRATCH_INTS int32 per frame (per-sweep flags of the multi-CTA path for large lattices)
+constexpr int SUPPORT_FILTER_SCRATCH_INTS = 10;
 int launch_support_filter(const Dims &d, const svb_params &p, const int16_t *dcan_raw, int16_t *dcan, int32_t *support, int32_t *nsupport,
-                          int32_t *h_support, int32_t *h_nsupport, int nf, cudaStream_t s);
+                          int32_t *h_support, int32_t *h_nsupport, int32_t *changed, int nf, cudaStream_t s);
 // k_prior.cu
 // tri1 / tri2 hold the frames' triangle lists packed back to back: frame f starts at triangle trioff[f] (both sides)
 int launch_planes(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,

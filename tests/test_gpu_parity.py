@@ -4,6 +4,8 @@
 Bars (BASELINE.json north_star): bit-exact descriptors, support matches and pre-filter integer disparities; the
 filtered float disparity within 1e-3 px on >= 99.9 % of valid pixels with an identical invalid mask (the
 kernels actually reproduce it bit for bit, which is what is asserted); point cloud within 1e-4 relative."""
+import os
+
 import numpy as np
 import pytest
 
@@ -543,3 +545,43 @@ def test_random_parameter_sets_against_the_oracle(svb, ref, kitti_gray, seed):
         assert np.array_equal(D2, parity.half(want2, ctx)), over
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("sweeps", ["8", "1"])
+def test_multi_cta_lattice_filters(svb, ref, kitti_gray, monkeypatch, sweeps):
+    """The large-lattice form of the order-dependent lattice filters (one launch per fixpoint sweep, strip kernels for the two
+    redundant-point passes, column-wise compaction: what 4K frames use) forced onto KITTI-size and ragged frames: candidate lattice,
+    support list and everything downstream against the oracle.  sweeps = 1 cuts the multi-CTA sweeps short so that the one-CTA
+    finisher has to complete the fixpoint iteration."""
+    monkeypatch.setenv("SVB_SF_MULTI", "1")
+    monkeypatch.setenv("SVB_SF_SWEEPS", sweeps)
+    import subprocess
+    import sys
+    import textwrap
+
+    # the switches are read once per process: run the check in a fresh interpreter
+    code = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import numpy as np
+        from conftest import load_binding
+        import parity
+        from oracle.ref import RefElas
+        svb = load_binding().binding
+        ref = RefElas()
+        z = np.load(%r)
+        cases = [(z["L3"], z["R3"], svb.default_params(svb.PIPELINE), ref.pipeline_params()),
+                 (z["L11"], z["R11"], svb.default_params(svb.ROBOTICS), ref.params(0))]
+        Ls, Rs = svb.synth_pair(31, 517, 203, 1)
+        cases.append((Ls, Rs, svb.default_params(svb.MIDDLEBURY), ref.params(1)))
+        for L, R, p, p_ref in cases:
+            ctx = svb.Context(p, L.shape[1], L.shape[0])
+            res, t, _ = parity.staged_parity(ctx, ref, p_ref, L, R, inject=False)
+            bad = {k: v for k, v in res.items() if isinstance(v, dict) and not v["equal"]}
+            assert not bad, bad
+            ctx.close()
+        print("multi-CTA lattice filters: OK")
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
+            os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kitti_gray.npz"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

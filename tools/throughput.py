@@ -23,6 +23,8 @@ p = svb.default_params(svb.PIPELINE, disp_max=dm)
 ctx = svb.Context(p, W, H, chunk=chunk)
 ctx.set_calibration(np.array([[1, 0, 0, -W / 2.0], [0, 1, 0, -H / 2.0], [0, 0, 0, 0.58 * W], [0, 0, 1.8616, 0]]))
 ctx.set_stage_timing(True)
+if os.environ.get("SVB_SINGLE_STREAM") == "1":  # every lane on one stream: the stage times are then exact (no overlap between kernels)
+    ctx.set_single_stream(True)
 ctx.batch_upload(Ls, Rs)
 flags = svb.OUT_DISPARITY | svb.OUT_POINTS
 ctx.batch_run(n, flags)
