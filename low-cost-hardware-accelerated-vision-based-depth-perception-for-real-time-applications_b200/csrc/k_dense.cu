@@ -168,27 +168,30 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     const unsigned span = hi2 >= lo2 ? (unsigned)(hi2 - lo2) : 0u;
     const int lo3 = hi2 >= lo2 ? lo2 : 0x40000000;  // empty interval: nothing passes the unsigned range test
     if (RADIUS > 0) {
-        // the band's descriptors sit at consecutive addresses around pb = po -+ d_plane: loads with immediate offsets,
-        // predicated on the hypothesis being admissible (an inadmissible d may point anywhere; it is never dereferenced)
-        const uint4 *pb = desc_at(po, SIDE ? d_plane : -d_plane);
+        // The band's descriptors sit at consecutive addresses around pb = po -+ d_plane: loads with immediate offsets, all issued up
+        // front and unconditionally.  For the ADDRESS the plane disparity is clamped to [-8, disp_max + 8]: a band with any admissible
+        // hypothesis has d_plane within the radius of [0, disp_max], where the clamp is the identity, and every other band is discarded
+        // by okb anyway -- but its loads now stay within disp_max + 11 descriptors of po, i.e. inside the arena's guard bands
+        // (Dims::desc_pad), so they need neither a predicate nor zeroed destination registers.
+        const int d_addr = min(max(d_plane, -8), a.disp_max + 8);
+        const uint4 *pb = desc_at(po, SIDE ? d_addr : -d_addr);
         uint4 ob[2 * RADIUS + 1];
         bool okb[2 * RADIUS + 1];
 #pragma unroll
         for (int k = -RADIUS; k <= RADIUS; k++) {
             const int d = (int)((unsigned)d_plane + (unsigned)k);
             okb[k + RADIUS] = (unsigned)(d - lo3) <= span;
-            ob[k + RADIUS] = make_uint4(0u, 0u, 0u, 0u);
-            if (okb[k + RADIUS]) {
-                SVB_GUARD_DESC(pb + (SIDE ? k : -k), SIDE ^ 1);
-                ob[k + RADIUS] = __ldg(pb + (SIDE ? k : -k));
-            }
+            SVB_GUARD_DESC(pb + (SIDE ? k : -k), SIDE ^ 1);
+            ob[k + RADIUS] = __ldg(pb + (SIDE ? k : -k));
             if (COUNT) n_hyp += okb[k + RADIUS] ? 1u : 0u;
         }
+        unsigned seed[RADIUS + 1];  // bias + prior of |k| (the prior only where both planes are valid, elas.cpp:910)
+#pragma unroll
+        for (int k = 0; k <= RADIUS; k++) seed[k] = a.bias + ((unsigned)a.P[k] & prior_on);
 #pragma unroll
         for (int k = -RADIUS; k <= RADIUS; k++) {
-            const unsigned seed = a.bias + ((unsigned)a.P[k < 0 ? -k : k] & prior_on);
             const unsigned dk = (unsigned)d_plane + (unsigned)(0x1000 + k);  // phase bit + d
-            const unsigned cand = (sad16_acc(c, ob[k + RADIUS], seed) << 13) + dk;
+            const unsigned cand = (sad16_acc(c, ob[k + RADIUS], seed[k < 0 ? -k : k]) << 13) + dk;
             key = min(key, okb[k + RADIUS] ? cand : 0xFFFFFFFFu);
         }
     } else {
