@@ -28,7 +28,9 @@
 #include "delaunay_mesh.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace svb {
 
@@ -239,7 +241,28 @@ int delaunay_xy(const int32_t *x, const int32_t *y, int n, int32_t *tri_out, int
     mesh.ntri = 0;
     mesh.make();  // record 0: outer space
     int hullleft, hullright;
-    mesh.recurse(0, m, 0, 0, 1, -1, hullleft, hullright);
+    int par_depth = -1;
+    if (scratch.par_threads > 1 && m >= 2048) {
+        // the 2^par_depth subtrees of one depth on threads of their own, each straight into its own record range
+        par_depth = 1;
+        while (par_depth < 2 && (2 << par_depth) <= scratch.par_threads) par_depth++;  // four subtrees: more threads cost more than they gain (measured)
+        std::vector<std::thread> threads;
+        for (int k = 0; k < (1 << par_depth); k++) {
+            const DelaunayNode nd = delaunay_node_at(m, par_depth, k);
+            if (!nd.exists) continue;
+            threads.emplace_back([nd, par_depth, P2, R] {
+                Mesh sub;
+                sub.P = P2;
+                sub.R = R;
+                sub.ntri = 0;
+                int fl, fr;
+                sub.recurse(nd.first, nd.count, nd.axis, par_depth, nd.b, -1, fl, fr);
+                sub.store_node_result(nd.b, nd.count, fl, fr);
+            });
+        }
+        for (auto &t : threads) t.join();
+    }
+    mesh.recurse(0, m, 0, 0, 1, par_depth, hullleft, hullright);
 
     int count = 0;
     for (int t = 1; t < 2 * m - 1; t++) {

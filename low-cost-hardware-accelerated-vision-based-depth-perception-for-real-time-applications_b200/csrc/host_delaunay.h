@@ -11,6 +11,10 @@ namespace svb {
 // Reusable scratch memory so that the per-frame stage performs no heap allocation in steady state.
 struct DelaunayScratch {
     std::vector<int32_t> storage;  // coordinates (with a sentinel in front), triangle records, sort arrays
+    // > 1: a large list (>= 2048 vertices) may use that many threads of its own: the subtrees of one recursion depth write disjoint,
+    // pre-determined record ranges (delaunay_mesh.h), so they are built concurrently and the levels above are merged afterwards.
+    // What one 4K frame needs (two lists of 14 700 points and nothing else to overlap with); batches parallelise over lists instead.
+    int par_threads = 1;
 };
 
 // support: n x {u,v,d}.  Left image (right_image = 0) triangulates (u,v), right image (u-d,v).

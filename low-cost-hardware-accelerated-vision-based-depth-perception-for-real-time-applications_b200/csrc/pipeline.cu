@@ -394,9 +394,12 @@ int svb::stage_host(svb_context *c, Lane &L, int nf, bool unpacked) {
             return SVB_ERR_ARG;
         }
     }
+    // fewer lists than threads (one 4K frame): a large list may spread its subtrees over the threads that would idle otherwise
+    const int par_threads = jobs.empty() ? 1 : std::max(1, c->pool->size() / (int)jobs.size());
     if (!jobs.empty())
         c->pool->parallel_for((int)jobs.size(), [&](int j, int worker) {
             const auto w0 = std::chrono::steady_clock::now();
+            c->scratch[worker].par_threads = par_threads;
             const int f = jobs[j] >> 1, side = jobs[j] & 1;
             const int n = L.h_nsupport[f];
             const int cap = unpacked ? d.maxT + 8 : h_trioff[f + 1] - h_trioff[f];
@@ -949,6 +952,7 @@ int svb_stage_support(svb_context *c, const uint8_t *desc1, const uint8_t *desc2
 int svb_stage_delaunay(const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out) {
     if (!support || !tri || n < 0 || cap < 0) return SVB_ERR_ARG;
     DelaunayScratch scratch;
+    if (const char *pt = getenv("SVB_DELAUNAY_PAR")) scratch.par_threads = atoi(pt);  // tests: subtrees of a large list on threads of their own
     const int m = delaunay_support(support, n, right_image, tri, cap, scratch);
     if (n_tri_out) *n_tri_out = m;
     return SVB_OK;

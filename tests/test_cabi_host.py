@@ -190,3 +190,15 @@ def test_synth_pair_is_deterministic_and_has_known_disparity(svb):
     diff = np.abs(R1[:40, :300].astype(int) - L1[:40, 8:308].astype(int))
     assert diff.max() <= 3
     assert L1.std() > 10
+
+
+@pytest.mark.parametrize("threads", ["2", "4", "16"])
+def test_host_delaunay_subtrees_in_parallel(svb, ref, monkeypatch, threads):
+    """A large list (one 4K frame has 14 700 support points) builds the subtrees of one recursion depth on threads of their own --
+    their record ranges are disjoint and known in advance -- and merges the levels above afterwards: same list as the reference,
+    order included, whatever the thread count."""
+    monkeypatch.setenv("SVB_DELAUNAY_PAR", threads)
+    for seed, n in ((31, 2048), (32, 6000), (33, 15000)):
+        s = lattice_support(np.random.default_rng(seed), n, W=3840, H=2160, dmax=200)
+        for side in (0, 1):
+            assert np.array_equal(svb.delaunay(s, side), ref.delaunay(s, side)), (seed, n, side, threads)
