@@ -63,6 +63,57 @@ __device__ __forceinline__ uint32_t range_mask(int lo, int hi, int base) {
     return (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
 }
 
+// (i) of dense_body: the warp-uniform walk over the union of the lanes' grid candidates; returns the packed minimum.
+// CLIP = false: no lane of the warp has an admissible interval [dlo, dhi] that cuts into [0, disp_max]; a lane's candidates of word w
+// are then its cell's bits minus the band [dmin, dmax], which is a window of at most 15 bits starting in word dmin >> 5
+// (5 instructions per word instead of the two general range masks).
+template <int SIDE, bool CLIP, bool COUNT>
+__device__ __forceinline__ unsigned grid_phase(const DenseArgs &a, const uint32_t *cell, const uint4 &m4_first, bool active, int dmin, int dmax,
+                                               int dlo, int dhi, const uint4 &c, const uint4 *po, unsigned &n_hyp) {
+    unsigned key = 0xFFFFFFFFu;
+    const unsigned width = dmax >= dmin ? (2u << (dmax - dmin)) - 1u : 0u;
+    const unsigned band_lo = width << (dmin & 31), band_hi = __funnelshift_l(width, 0u, dmin & 31);
+    const int wband = dmin >> 5;  // dmin >= 0 wherever the band is not empty
+    // gwords is a multiple of 4 (make_dims): a cell is read as 16-byte vectors, and a group of four words (128
+    // disparities) without any candidate in the whole warp is skipped with one vote
+    for (int w4 = 0; w4 < a.gwords; w4 += 4) {
+        uint4 m4 = w4 == 0 ? m4_first : __ldg(reinterpret_cast<const uint4 *>(cell + w4));
+        if (!active) m4 = make_uint4(0, 0, 0, 0);
+        if (!__any_sync(0xFFFFFFFFu, (m4.x | m4.y | m4.z | m4.w) != 0u)) continue;
+        const int rel = wband - w4;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int w = w4 + j;
+            uint32_t mine = j == 0 ? m4.x : j == 1 ? m4.y : j == 2 ? m4.z : m4.w;
+            if (CLIP) {
+                if (mine) mine &= ~range_mask(dmin, dmax, w << 5) & range_mask(dlo, dhi, w << 5);
+            } else {
+                mine &= ~((rel == j ? band_lo : 0u) | (rel == j - 1 ? band_hi : 0u));
+            }
+            if (COUNT) n_hyp += __popc(mine);
+            uint32_t uni = __reduce_or_sync(0xFFFFFFFFu, mine);
+            while (uni) {
+                // two candidates per trip: both loads are in flight before either SAD chain starts
+                const uint32_t bit0 = uni & (0u - uni);  // lowest candidate of the union
+                uni ^= bit0;
+                const uint32_t bit1 = uni & (0u - uni);  // next one (0 if there is none: it then re-evaluates bit0's d, masked out)
+                uni ^= bit1;
+                const int d0 = (w << 5) + (31 - __clz(bit0));
+                const int d1 = bit1 ? (w << 5) + (31 - __clz(bit1)) : d0;
+                SVB_GUARD_DESC(desc_at(po, SIDE ? d0 : -d0), SIDE ^ 1);
+                SVB_GUARD_DESC(desc_at(po, SIDE ? d1 : -d1), SIDE ^ 1);
+                const uint4 o0 = __ldg(desc_at(po, SIDE ? d0 : -d0));
+                const uint4 o1 = __ldg(desc_at(po, SIDE ? d1 : -d1));
+                const unsigned cand0 = (sad16_acc(c, o0, a.bias) << 13) + (unsigned)d0;
+                const unsigned cand1 = (sad16_acc(c, o1, a.bias) << 13) + (unsigned)d1;
+                key = min(key, (mine & bit0) ? cand0 : 0xFFFFFFFFu);
+                key = min(key, (mine & bit1) ? cand1 : 0xFFFFFFFFu);
+            }
+        }
+    }
+    return key;
+}
+
 // grid: (ceil(W/128), H, nf*2); blockIdx.z = 2*frame + side.  One thread = one pixel, one warp = 32 consecutive
 // pixels of a row.  The candidate loops are WARP-UNIFORM: the warp walks the union of its lanes' grid-cell bit
 // masks (REDUX.OR) in ascending d, so in every step all lanes look at the same disparity -- their loads hit 32
@@ -129,40 +180,12 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     const int dlo = SIDE ? 2 - u : u - (W - 3);
     const int dhi = SIDE ? (W - 3) - u : u - 2;
 
-    unsigned key = 0xFFFFFFFFu;
-    // (i) grid candidates outside the band, ascending (elas.cpp:759-767 / 778-786)
-    // gwords is a multiple of 4 (make_dims): a cell is read as 16-byte vectors, and a group of four words (128
-    // disparities) without any candidate in the whole warp is skipped with one vote
-    for (int w4 = 0; w4 < a.gwords; w4 += 4) {
-        uint4 m4 = w4 == 0 ? m4_first : __ldg(reinterpret_cast<const uint4 *>(cell + w4));
-        if (!active) m4 = make_uint4(0, 0, 0, 0);
-        if (!__any_sync(0xFFFFFFFFu, (m4.x | m4.y | m4.z | m4.w) != 0u)) continue;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int w = w4 + j;
-            uint32_t mine = j == 0 ? m4.x : j == 1 ? m4.y : j == 2 ? m4.z : m4.w;
-            if (mine) mine &= ~range_mask(dmin, dmax, w << 5) & range_mask(dlo, dhi, w << 5);
-            if (COUNT) n_hyp += __popc(mine);
-            uint32_t uni = __reduce_or_sync(0xFFFFFFFFu, mine);
-            while (uni) {
-                // two candidates per trip: both loads are in flight before either SAD chain starts
-                const uint32_t bit0 = uni & (0u - uni);  // lowest candidate of the union
-                uni ^= bit0;
-                const uint32_t bit1 = uni & (0u - uni);  // next one (0 if there is none: it then re-evaluates bit0's d, masked out)
-                uni ^= bit1;
-                const int d0 = (w << 5) + (31 - __clz(bit0));
-                const int d1 = bit1 ? (w << 5) + (31 - __clz(bit1)) : d0;
-                SVB_GUARD_DESC(desc_at(po, SIDE ? d0 : -d0), SIDE ^ 1);
-                SVB_GUARD_DESC(desc_at(po, SIDE ? d1 : -d1), SIDE ^ 1);
-                const uint4 o0 = __ldg(desc_at(po, SIDE ? d0 : -d0));
-                const uint4 o1 = __ldg(desc_at(po, SIDE ? d1 : -d1));
-                const unsigned cand0 = (sad16_acc(c, o0, a.bias) << 13) + (unsigned)d0;
-                const unsigned cand1 = (sad16_acc(c, o1, a.bias) << 13) + (unsigned)d1;
-                key = min(key, (mine & bit0) ? cand0 : 0xFFFFFFFFu);
-                key = min(key, (mine & bit1) ? cand1 : 0xFFFFFFFFu);
-            }
-        }
-    }
+    // (i) grid candidates outside the band, ascending (elas.cpp:759-767 / 778-786).  Only warps next to the image border (some
+    // lane's admissible interval [dlo, dhi] cuts into [0, disp_max], the range of the grid's bits: k_grid_scatter) need the clipping
+    // masks; everywhere else a lane's candidates are its cell's bits minus the band, and the band is one window of at most 15 bits.
+    const bool clip = __any_sync(0xFFFFFFFFu, active && (dlo > 0 || dhi < a.disp_max));
+    unsigned key = clip ? grid_phase<SIDE, true, COUNT>(a, cell, m4_first, active, dmin, dmax, dlo, dhi, c, po, n_hyp)
+                        : grid_phase<SIDE, false, COUNT>(a, cell, m4_first, active, dmin, dmax, dlo, dhi, c, po, n_hyp);
     // (ii) the plane band with the prior (elas.cpp:768-774 / 787-793)
     const int lo2 = max(dmin, dlo), hi2 = min(dmax, dhi);
     const unsigned span = hi2 >= lo2 ? (unsigned)(hi2 - lo2) : 0u;

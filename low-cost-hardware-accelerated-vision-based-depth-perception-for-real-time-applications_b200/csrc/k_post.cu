@@ -43,145 +43,194 @@ __global__ void __launch_bounds__(256) k_lr_check(const float *__restrict__ D1in
     }
 }
 
-// ---- gap interpolation, row pass --------------------------------------------------------------------
-// For an invalid pixel only the nearest valid pixel on each side matters: with p = previous valid column and
-// n = next valid column (values dp, dn, untouched by the pass),
-//   p and n exist, n-p-1 <= gap : fill with (dp+dn)/2 if |dp-dn| < 3 else min(dp,dn)       (elas.cpp:1156-1176)
+// ---- gap interpolation ------------------------------------------------------------------------------------
+// For an invalid pixel only the nearest valid pixel on each side of its line (row, then column) matters: with p = previous valid
+// position and n = next valid position in the state BEFORE the pass (values dp, dn; fills never create a boundary for another gap),
+//   p and n exist, n-p-1 <= gap : fill with (dp+dn)/2 if |dp-dn| < 3 else min(dp,dn)       (elas.cpp:1156-1176, 1220-1293)
 //   only n exists (n = first valid), add_corners, n-u <= gap : fill with dn                 (elas.cpp:1191-1201)
 //   only p exists (p = last valid),  add_corners, u-p <= gap : fill with dp                 (elas.cpp:1204-1214)
-// One warp owns one row: a forward sweep records p per column in shared memory, a backward sweep carries n.
-constexpr int GAP_WARPS = 4;
+// Both passes therefore work on VALIDITY BITS: one word per 32 positions of a line, the last valid position before each word and the
+// first one after it.  The map is read once (row pass, all loads independent); only words with a gap are looked at again, and only
+// the gap's two end values are loaded.  The row pass leaves the validity bits of its RESULT (one word per 32 columns of a row) in a
+// scratch array, from which the column pass builds its column words by 32 x 32 bit transposes instead of reading the map again.
+constexpr int GAP_WARPS = 8;
 
 __device__ __forceinline__ float gap_fill_value(float d1, float d2) {
     if (fabsf(__fsub_rn(d1, d2)) < 3.0f) return __fdiv_rn(__fadd_rn(d1, d2), 2.0f);
     return d2 < d1 ? d2 : d1;  // std::min(d1, d2)
 }
 
-// One line (a row in global memory, or a column of a shared-memory strip) handled by one warp: `line[i * stride]`,
-// i = 0 .. n-1; prev = n ints of scratch.
-__device__ __forceinline__ void gap_line(float *line, int stride, int n, int *prev, int lane, int gap_width, int add_corners) {
-    int carry = -1;
-    const int chunks = (n + 31) / 32;
-    for (int k = 0; k < chunks; k++) {
-        const int u = k * 32 + lane;
-        const bool valid = (u < n) && (line[u * stride] >= 0.f);
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid);
-        const unsigned below = bal & ((1u << lane) - 1u);
-        if (u < n) prev[u] = below ? (k * 32 + 31 - __clz(below)) : carry;
-        if (bal) carry = k * 32 + 31 - __clz(bal);
+// Row pass, one warp per row.  Dynamic smem: GAP_WARPS * 3 * Cpad words (validity words, carry, ncarry per 32-column chunk).
+// grid: (ceil(H / GAP_WARPS), nimg)
+__global__ void __launch_bounds__(GAP_WARPS * 32) k_gap_rows(float *__restrict__ D_all, uint32_t *__restrict__ bits_all, int W, int H, int Cw,
+                                                             int Cpad, int gap_width, int add_corners) {
+    extern __shared__ int s_gap[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int v = blockIdx.x * GAP_WARPS + wid;
+    if (v >= H) return;  // warp-uniform; the kernel has no CTA-wide barrier
+    float *line = D_all + ((size_t)blockIdx.y * H + v) * W;
+    uint32_t *words = reinterpret_cast<uint32_t *>(s_gap) + (size_t)wid * 3 * Cpad;
+    int *carry = s_gap + (size_t)wid * 3 * Cpad + Cpad, *ncarry = carry + Cpad;
+    // 1: validity words (four independent loads in flight per lane)
+    for (int k0 = 0; k0 < Cw; k0 += 4) {
+        float val[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int u = (k0 + i) * 32 + lane;
+            val[i] = u < W ? line[u] : -1.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, val[i] >= 0.f);
+            if (lane == 0 && k0 + i < Cw) words[k0 + i] = bal;
+        }
     }
     __syncwarp();
-    int ncarry = -1;  // next valid position beyond the current chunk
-    for (int k = chunks - 1; k >= 0; k--) {
+    // 2: last valid column before / first valid column after every chunk: lane j scans chunks j*per .. j*per+per-1, the lanes are
+    // chained by a prefix maximum / suffix minimum
+    const int per = (Cw + 31) >> 5;
+    const int k_lo = min(lane * per, Cw), k_hi = min(k_lo + per, Cw);
+    int last = -1, first = 0x7FFFFFFF;
+    for (int k = k_lo; k < k_hi; k++) {
+        const uint32_t w = words[k];
+        if (w) {
+            last = k * 32 + 31 - __clz(w);
+            if (first == 0x7FFFFFFF) first = k * 32 + __ffs(w) - 1;
+        }
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int a = __shfl_up_sync(0xFFFFFFFFu, last, off), b = __shfl_down_sync(0xFFFFFFFFu, first, off);
+        if (lane >= off) last = max(last, a);
+        if (lane + off < 32) first = min(first, b);
+    }
+    int run = __shfl_up_sync(0xFFFFFFFFu, last, 1), nrun = __shfl_down_sync(0xFFFFFFFFu, first, 1);
+    if (lane == 0) run = -1;
+    if (lane == 31) nrun = 0x7FFFFFFF;
+    for (int k = k_lo; k < k_hi; k++) {
+        carry[k] = run;
+        const uint32_t w = words[k];
+        if (w) run = k * 32 + 31 - __clz(w);
+    }
+    for (int k = k_hi - 1; k >= k_lo; k--) {
+        ncarry[k] = nrun == 0x7FFFFFFF ? -1 : nrun;
+        const uint32_t w = words[k];
+        if (w) nrun = k * 32 + __ffs(w) - 1;
+    }
+    __syncwarp();
+    // 3: chunks with a gap
+    for (int k = 0; k < Cw; k++) {
+        const uint32_t w = words[k];
         const int u = k * 32 + lane;
-        const float val = (u < n) ? line[u * stride] : -1.f;
-        const bool valid = (u < n) && (val >= 0.f);
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid);
-        const unsigned above = (lane == 31) ? 0u : (bal & ~((2u << lane) - 1u));
-        const int nx = above ? (k * 32 + __ffs(above) - 1) : ncarry;
-        if (u < n && !valid) {
-            const int p = prev[u];
-            SVB_GUARD_ASSERT(p >= -1 && p < u && nx < n && (nx < 0 || nx > u));
+        const uint32_t in_row = (k * 32 + 32 <= W) ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (k * 32 + 32 - W));
+        if (w == in_row) continue;  // warp-uniform
+        bool do_fill = false;
+        if (!((w >> lane) & 1u) && u < W) {
+            const uint32_t below = w & ((1u << lane) - 1u), above = lane == 31 ? 0u : (w & ~((2u << lane) - 1u));
+            const int p = below ? (k * 32 + 31 - __clz(below)) : carry[k];
+            const int nx = above ? (k * 32 + __ffs(above) - 1) : ncarry[k];
+            SVB_GUARD_ASSERT(p >= -1 && p < u && nx < W && (nx < 0 || nx > u));
             float fill = 0.f;
-            bool do_fill = false;
+            // the values at p and nx are valid pixels, which this pass never modifies: reading them while other lanes write
+            // invalid positions is race free
             if (p >= 0 && nx >= 0) {
                 if (nx - p - 1 <= gap_width) {
-                    SVB_GUARD_ASSERT(p >= 0 && p < n && nx >= 0 && nx < n);
-                    fill = gap_fill_value(line[p * stride], line[nx * stride]);
+                    fill = gap_fill_value(line[p], line[nx]);
                     do_fill = true;
                 }
             } else if (add_corners && p < 0 && nx >= 0) {
                 if (nx - u <= gap_width) {
-                    fill = line[nx * stride];
+                    fill = line[nx];
                     do_fill = true;
                 }
             } else if (add_corners && p >= 0 && nx < 0) {
                 if (u - p <= gap_width) {
-                    fill = line[p * stride];
+                    fill = line[p];
                     do_fill = true;
                 }
             }
-            // values at p and nx are valid pixels, which this pass never modifies: reading them while other
-            // lanes write invalid positions is race free
-            if (do_fill) line[u * stride] = fill;
+            if (do_fill) line[u] = fill;
         }
-        if (bal) ncarry = k * 32 + __ffs(bal) - 1;
+        // every fill value is >= 0 (a valid disparity, a mean or a minimum of two): the filled pixels are valid for the column pass
+        const unsigned filled = __ballot_sync(0xFFFFFFFFu, do_fill);
+        if (lane == 0) words[k] = w | filled;
     }
+    __syncwarp();
+    uint32_t *out = bits_all + ((size_t)blockIdx.y * H + v) * Cw;
+    for (int k = lane; k < Cw; k += 32) out[k] = words[k];
 }
 
-// grid: (ceil(H/warps), nimg); dynamic smem: warps * Wpad int32
-__global__ void __launch_bounds__(GAP_WARPS * 32) k_gap_rows(float *__restrict__ D_all, int W, int H, int gap_width, int add_corners, int Wpad) {
-    extern __shared__ int s_prev[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    const int v = blockIdx.x * warps + wid;
-    if (v >= H) return;
-    gap_line(D_all + ((size_t)blockIdx.y * H + v) * W, 1, W, s_prev + wid * Wpad, lane, gap_width, add_corners);
-}
-
-// Column pass with the same warp-parallel line algorithm: a CTA stages a strip of GC_COLS columns in shared memory
-// (row stride GC_COLS + 1, so that a warp reading 32 consecutive ROWS of one column hits 32 different banks), each of
-// its warps handles GC_COLS / GC_WARPS columns, and the strip is written back.  Every invalid pixel only depends on
-// the nearest valid pixels above and below in the state BEFORE the pass (fills never create a boundary for another
-// gap, elas.cpp:1220-1293), so the sequential walk and this formulation agree exactly.
-constexpr int GC_WARPS = 8;
-
-// GC_COLS columns per CTA: 16, or 8 for very tall frames so that the strip still fits in shared memory
-template <int GC_COLS>
-__global__ void __launch_bounds__(GC_WARPS * 32) k_gap_cols_strip(float *__restrict__ D_all, int W, int H, int gap_width, int add_corners,
-                                                                  int Hpad) {
-    extern __shared__ float s_gc[];  // [H][GC_COLS + 1] floats, then GC_WARPS * Hpad ints
-    float *strip = s_gc;
-    int *prev_all = reinterpret_cast<int *>(s_gc + (size_t)H * (GC_COLS + 1));
+// Column pass: a CTA owns 32 neighbouring columns (lane = column) over all rows.  Dynamic smem: 3 * HW * 32 words (column validity
+// words [k][lane], carry, ncarry), HW = ceil(H / 32).
+// grid: (Cw, nimg)
+__global__ void __launch_bounds__(GAP_WARPS * 32) k_gap_cols(float *__restrict__ D_all, const uint32_t *__restrict__ bits_all, int W, int H, int Cw,
+                                                             int HW, int gap_width, int add_corners) {
+    extern __shared__ int s_gap[];
+    uint32_t *colw = reinterpret_cast<uint32_t *>(s_gap);
+    int *carry = s_gap + (size_t)HW * 32, *ncarry = carry + (size_t)HW * 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int u0 = blockIdx.x * GC_COLS;
-    float *Dimg = D_all + (size_t)blockIdx.y * W * H;
-    for (int i = threadIdx.x; i < H * GC_COLS; i += GC_WARPS * 32) {
-        const int v = i / GC_COLS, c = i - v * GC_COLS;
-        strip[v * (GC_COLS + 1) + c] = (u0 + c < W) ? Dimg[(size_t)v * W + u0 + c] : -10.f;
+    const int u = blockIdx.x * 32 + lane;
+    const uint32_t *bits = bits_all + (size_t)blockIdx.y * H * Cw + blockIdx.x;
+    // 1: lane r reads the row word of row 32 k + r; 32 ballots transpose the 32 x 32 bit block into one word per column
+    for (int k = wid; k < HW; k += GAP_WARPS) {
+        const int v = k * 32 + lane;
+        const uint32_t rw = v < H ? bits[(size_t)v * Cw] : 0u;
+        uint32_t word = 0u;
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            const unsigned b = __ballot_sync(0xFFFFFFFFu, (rw >> c) & 1u);
+            if (lane == c) word = b;
+        }
+        colw[k * 32 + lane] = word;
     }
     __syncthreads();
-    for (int c = wid; c < GC_COLS; c += GC_WARPS)
-        if (u0 + c < W) gap_line(strip + c, GC_COLS + 1, H, prev_all + wid * Hpad, lane, gap_width, add_corners);
-    __syncthreads();
-    for (int i = threadIdx.x; i < H * GC_COLS; i += GC_WARPS * 32) {
-        const int v = i / GC_COLS, c = i - v * GC_COLS;
-        if (u0 + c < W) Dimg[(size_t)v * W + u0 + c] = strip[v * (GC_COLS + 1) + c];
-    }
-}
-
-// ---- gap interpolation, column pass -------------------------------------------------------------------
-// One thread walks one column top to bottom exactly like elas.cpp:1220-1293; neighbouring threads own
-// neighbouring columns, so every step of the walk is a coalesced row access.
-__global__ void __launch_bounds__(128) k_gap_cols(float *__restrict__ D_all, int W, int H, int gap_width, int add_corners) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= W) return;
-    float *D = D_all + (size_t)blockIdx.y * W * H + u;
-    int count = 0;
-    int first_valid = -1, last_valid = -1;
-    for (int v = 0; v < H; v++) {
-        const float val = D[(size_t)v * W];
-        if (val >= 0.f) {
-            if (count >= 1 && count <= gap_width) {
-                const int v_first = v - count, v_last = v - 1;
-                if (v_first > 0 && v_last < H - 1) {
-                    const float d1 = D[(size_t)(v_first - 1) * W];
-                    const float fill = gap_fill_value(d1, val);
-                    for (int vc = v_first; vc <= v_last; vc++) D[(size_t)vc * W] = fill;
-                }
-            }
-            count = 0;
-            if (first_valid < 0) first_valid = v;
-            last_valid = v;
-        } else {
-            count++;
+    // 2: per column, the last valid row before / the first valid row after every word (warp 0 downwards, warp 1 upwards)
+    if (wid == 0) {
+        int run = -1;
+        for (int k = 0; k < HW; k++) {
+            carry[k * 32 + lane] = run;
+            const uint32_t w = colw[k * 32 + lane];
+            if (w) run = k * 32 + 31 - __clz(w);
+        }
+    } else if (wid == 1) {
+        int nrun = -1;
+        for (int k = HW - 1; k >= 0; k--) {
+            ncarry[k * 32 + lane] = nrun;
+            const uint32_t w = colw[k * 32 + lane];
+            if (w) nrun = k * 32 + __ffs(w) - 1;
         }
     }
-    if (add_corners && first_valid >= 0) {
-        // the first / last valid pixel of the column is the same before and after the interior fill
-        const float top = D[(size_t)first_valid * W];
-        for (int v2 = max(first_valid - gap_width, 0); v2 < first_valid; v2++) D[(size_t)v2 * W] = top;
-        const float bot = D[(size_t)last_valid * W];
-        for (int v2 = last_valid + 1; v2 <= min(last_valid + gap_width, H - 1); v2++) D[(size_t)v2 * W] = bot;
+    __syncthreads();
+    if (u >= W) return;
+    // 3: every lane walks the gaps of its column word by word; a maximal run of invalid rows inside a word has its end points either
+    // in the word (the neighbouring bits) or in carry / ncarry
+    float *D = D_all + (size_t)blockIdx.y * W * H + u;
+    for (int k = wid; k < HW; k += GAP_WARPS) {
+        const uint32_t inv = ~colw[k * 32 + lane];  // rows >= H are invalid: a run that reaches them has no next valid row in the word
+        const int rows = min(32, H - k * 32);
+        uint32_t todo = rows == 32 ? inv : (inv & ((1u << rows) - 1u));
+        while (todo) {
+            const int r0 = __ffs(todo) - 1;
+            const uint32_t t = ~(inv >> r0);  // first zero of the shifted word = end of the run
+            const int len = t ? __ffs(t) - 1 : 32 - r0;
+            const int r1 = min(r0 + len, rows);  // rows r0 .. r1-1 are this word's part of the gap
+            todo = r0 + len >= 32 ? 0u : (todo & (0xFFFFFFFFu << (r0 + len)));
+            const int p = r0 > 0 ? k * 32 + r0 - 1 : carry[k * 32 + lane];
+            const int nx = r0 + len < 32 ? k * 32 + r0 + len : ncarry[k * 32 + lane];
+            SVB_GUARD_ASSERT(p >= -1 && p < k * 32 + r0 && nx < H && (nx < 0 || nx >= k * 32 + r1));
+            if (p >= 0 && nx >= 0) {
+                if (nx - p - 1 <= gap_width) {
+                    const float fill = gap_fill_value(D[(size_t)p * W], D[(size_t)nx * W]);
+                    for (int r = r0; r < r1; r++) D[(size_t)(k * 32 + r) * W] = fill;
+                }
+            } else if (add_corners && p < 0 && nx >= 0) {
+                const float fill = D[(size_t)nx * W];
+                for (int r = max(r0, nx - gap_width - k * 32); r < r1; r++) D[(size_t)(k * 32 + r) * W] = fill;
+            } else if (add_corners && p >= 0 && nx < 0) {
+                const float fill = D[(size_t)p * W];
+                for (int r = r0; r < min(r1, p + gap_width + 1 - k * 32); r++) D[(size_t)(k * 32 + r) * W] = fill;
+            }
+        }
     }
 }
 
@@ -399,72 +448,48 @@ namespace {
 
 int gap_width_of(const Dims &d, const svb_params &p) { return d.sub ? p.ipol_gap_width / 2 + 1 : p.ipol_gap_width; }  // elas.cpp:1131-1135
 
-int launch_gap_rows(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s) {
-    const int W = d.Dw, H = d.Dh;
-    const int Wpad = (W + 31) & ~31;
-    const int warps = GAP_WARPS;  // 4 warps x 8192 px x 4 B = 128 KB at the largest supported width
-    const size_t smem = (size_t)warps * Wpad * sizeof(int);
-    static size_t configured[64] = {};
+// opt-in for more than 48 KB of dynamic shared memory, once per device and kernel
+template <typename K>
+int gap_smem_optin(K kernel, size_t smem, size_t (&configured)[64]) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > 48 * 1024 && dev >= 0 && dev < 64 && configured[dev] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_gap_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(k_gap_rows, %zu): %s", smem, cudaGetErrorString(e));
+            set_error("cudaFuncSetAttribute(gap kernel, %zu): %s", smem, cudaGetErrorString(e));
             return SVB_ERR_CUDA;
         }
         configured[dev] = smem;
     }
-    dim3 grid((H + warps - 1) / warps, nimg);
-    k_gap_rows<<<grid, warps * 32, smem, s>>>(D, W, H, gap_width_of(d, p), p.add_corners, Wpad);
-    SVB_LAUNCH_CHECK();
-    return SVB_OK;
-}
-
-int launch_gap_cols(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s) {
-    const int W = d.Dw, H = d.Dh;
-    const int gap_width = gap_width_of(d, p);
-    const int Hpad = (H + 31) & ~31;
-    int GC_COLS = 16;
-    size_t smem = (size_t)H * (GC_COLS + 1) * sizeof(float) + (size_t)GC_WARPS * Hpad * sizeof(int);
-    if (smem > 200 * 1024) {
-        GC_COLS = 8;
-        smem = (size_t)H * (GC_COLS + 1) * sizeof(float) + (size_t)GC_WARPS * Hpad * sizeof(int);
-    }
-    if (smem <= 200 * 1024) {
-        static size_t configured[64][2] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        const int which = GC_COLS == 16 ? 0 : 1;
-        if (smem > 48 * 1024 && dev >= 0 && dev < 64 && configured[dev][which] < smem) {
-            cudaError_t e = GC_COLS == 16 ? cudaFuncSetAttribute(k_gap_cols_strip<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                          : cudaFuncSetAttribute(k_gap_cols_strip<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) {
-                set_error("cudaFuncSetAttribute(k_gap_cols_strip): %s", cudaGetErrorString(e));
-                return SVB_ERR_CUDA;
-            }
-            configured[dev][which] = smem;
-        }
-        dim3 grid((W + GC_COLS - 1) / GC_COLS, nimg);
-        if (GC_COLS == 16)
-            k_gap_cols_strip<16><<<grid, GC_WARPS * 32, smem, s>>>(D, W, H, gap_width, p.add_corners, Hpad);
-        else
-            k_gap_cols_strip<8><<<grid, GC_WARPS * 32, smem, s>>>(D, W, H, gap_width, p.add_corners, Hpad);
-        SVB_LAUNCH_CHECK();
-        return SVB_OK;
-    }
-    dim3 grid((W + 127) / 128, nimg);
-    k_gap_cols<<<grid, 128, 0, s>>>(D, W, H, gap_width, p.add_corners);
-    SVB_LAUNCH_CHECK();
     return SVB_OK;
 }
 
 }  // namespace
 
-int launch_gap(const Dims &d, const svb_params &p, float *D, int nimg, cudaStream_t s) {
+size_t gap_scratch_words(const Dims &d, int nimg) { return (size_t)nimg * d.Dh * ((d.Dw + 31) / 32); }
+
+// scratch: gap_scratch_words(d, nimg) words (the validity bits the row pass hands to the column pass)
+int launch_gap(const Dims &d, const svb_params &p, float *D, uint32_t *scratch, int nimg, cudaStream_t s) {
     if (nimg <= 0) return SVB_OK;
-    SVB_TRY(launch_gap_rows(d, p, D, nimg, s));
-    return launch_gap_cols(d, p, D, nimg, s);
+    const int W = d.Dw, H = d.Dh, Cw = (W + 31) / 32, HW = (H + 31) / 32;
+    const int Cpad = (Cw + 3) & ~3;
+    {
+        const size_t smem = (size_t)GAP_WARPS * 3 * Cpad * sizeof(int);  // 24 KB at the largest supported width
+        static size_t configured[64] = {};
+        SVB_TRY(gap_smem_optin(k_gap_rows, smem, configured));
+        dim3 grid((H + GAP_WARPS - 1) / GAP_WARPS, nimg);
+        k_gap_rows<<<grid, GAP_WARPS * 32, smem, s>>>(D, scratch, W, H, Cw, Cpad, gap_width_of(d, p), p.add_corners);
+        SVB_LAUNCH_CHECK();
+    }
+    {
+        const size_t smem = (size_t)3 * HW * 32 * sizeof(int);  // 96 KB at the largest supported height
+        static size_t configured[64] = {};
+        SVB_TRY(gap_smem_optin(k_gap_cols, smem, configured));
+        dim3 grid(Cw, nimg);
+        k_gap_cols<<<grid, GAP_WARPS * 32, smem, s>>>(D, scratch, W, H, Cw, HW, gap_width_of(d, p), p.add_corners);
+        SVB_LAUNCH_CHECK();
+    }
+    return SVB_OK;
 }
 
 int launch_adaptive_mean(const Dims &d, int mean_mode, float *D, float *tmp, int nimg, cudaStream_t s) {

@@ -395,7 +395,8 @@ int svb::stage_host(svb_context *c, Lane &L, int nf, bool unpacked) {
         }
     }
     // fewer lists than threads (one 4K frame): a large list may spread its subtrees over the threads that would idle otherwise
-    const int par_threads = jobs.empty() ? 1 : std::max(1, c->pool->size() / (int)jobs.size());
+    // (these are threads of the triangulation's own, not the pool's: a one-frame context has a pool of two)
+    const int par_threads = jobs.empty() ? 1 : std::max(1, c->host_threads / (int)jobs.size());
     if (!jobs.empty())
         c->pool->parallel_for((int)jobs.size(), [&](int j, int worker) {
             const auto w0 = std::chrono::steady_clock::now();
@@ -494,7 +495,7 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, 
         if (both) SVB_TRY(tap_store(c, "D2seg", D2, DN * 4, L.stream));
     }
     SVB_TRY(T.mark(ST_GAP));
-    for (int s = 0; s < passes; s++) SVB_TRY(launch_gap(d, p, s ? D2 : D1, nf, L.stream));
+    for (int s = 0; s < passes; s++) SVB_TRY(launch_gap(d, p, s ? D2 : D1, reinterpret_cast<uint32_t *>(L.sizes), nf, L.stream));  // the component sizes are dead by now
     if (c->tap_mode && nf == 1) {
         SVB_TRY(tap_store(c, "D1gap", D1, DN * 4, L.stream));
         if (both) SVB_TRY(tap_store(c, "D2gap", D2, DN * 4, L.stream));
@@ -696,6 +697,7 @@ svb_context *svb_create(const svb_params *params, int width, int height, int chu
     int nthreads = hw ? (int)hw : 4;
     if (nthreads > 2 * c->chunk) nthreads = 2 * c->chunk;
     if (nthreads > 64) nthreads = 64;
+    c->host_threads = hw ? (int)hw : 4;
     c->pool.reset(new ThreadPool(nthreads));
     c->scratch.resize(c->pool->size());
     memset(&c->stats, 0, sizeof(c->stats));
@@ -1112,7 +1114,7 @@ static int stage_inplace(svb_context *c, float *D, int which) {
     if (!D) return SVB_ERR_ARG;
     SVB_CUDA(cudaMemcpyAsync(L.Dlr, D, (size_t)d.DN * 4, cudaMemcpyHostToDevice, L.stream));
     if (which == 0) SVB_TRY(launch_remove_small_segments(d, c->p, L.Dlr, L.labels, L.sizes, L.ccl_roots, L.ccl_counts, 1, L.stream));
-    if (which == 1) SVB_TRY(launch_gap(d, c->p, L.Dlr, 1, L.stream));
+    if (which == 1) SVB_TRY(launch_gap(d, c->p, L.Dlr, reinterpret_cast<uint32_t *>(L.sizes), 1, L.stream));
     if (which == 2) SVB_TRY(launch_adaptive_mean(d, c->mean_mode, L.Dlr, L.Dtmp, 1, L.stream));
     if (which == 3) SVB_TRY(launch_median(d, L.Dlr, L.Dtmp, 1, L.stream));
     SVB_CUDA(cudaMemcpyAsync(D, L.Dlr, (size_t)d.DN * 4, cudaMemcpyDeviceToHost, L.stream));

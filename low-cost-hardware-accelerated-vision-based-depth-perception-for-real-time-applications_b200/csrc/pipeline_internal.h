@@ -109,6 +109,7 @@ struct svb_context {
     bool delaunay_device = true;    // SVB_DELAUNAY_DEVICE=0: the divide-and-conquer runs on the host for every list (k_delaunay.cu otherwise)
     int dups_policy = 0;            // lists with duplicate coordinates: 0 = by host thread count, 1 = device, 2 = host (SVB_DELAUNAY_DUPS)
     int dd_cap = 2048;              // vertex capacity the device divide-and-conquer is launched with (shared memory); follows the lists seen
+    int host_threads = 1;           // hardware threads of the host (a large list spreads its subtrees over those the list-level pool leaves idle)
     bool gpu_order = true;  // SVB_GPU_ORDER=0: the host stage sorts and partitions the vertices itself
     std::vector<svb::StageEvents> stage_ev;  // one set per chunk of the call in flight
     std::mutex mu;

@@ -585,3 +585,35 @@ def test_multi_cta_lattice_filters(svb, ref, kitti_gray, monkeypatch, sweeps):
             os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kitti_gray.npz"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("W,H", [(1242, 375), (97, 66), (33, 31), (64, 32), (640, 1217)])
+def test_gap_interpolation_on_random_validity_maps(svb, ref, W, H):
+    """gapInterpolation alone (elas.cpp:1126-1295) on maps whose holes are drawn at random: isolated pixels, long runs, whole invalid
+    rows and columns, holes touching every border, widths and heights that are and are not multiples of the 32-position words the
+    kernels work on; gap widths below, around and above the word size, corners on and off."""
+    rng = np.random.default_rng(W * 1000 + H)
+    for case, (gap, corners, density) in enumerate([(3, 0, 0.3), (3, 1, 0.7), (7, 1, 0.5), (31, 1, 0.9), (40, 0, 0.95), (5000, 1, 0.97),
+                                                   (5000, 0, 0.5), (5000, 1, 0.999)]):
+        D = rng.integers(0, 64, (H, W)).astype(np.float32) + rng.integers(0, 4, (H, W)).astype(np.float32) / 4
+        holes = rng.random((H, W)) < density
+        for _ in range(6):  # whole lines, and lines that are invalid up to / from a random position
+            holes[rng.integers(0, H), :] = True
+            holes[:, rng.integers(0, W)] = True
+            holes[rng.integers(0, H), : rng.integers(1, W)] = True
+            holes[rng.integers(0, H), rng.integers(0, W - 1):] = True
+            holes[: rng.integers(1, H), rng.integers(0, W)] = True
+            holes[rng.integers(0, H - 1):, rng.integers(0, W)] = True
+        D[holes] = np.where(rng.random(int(holes.sum())) < 0.5, -1.0, -10.0).astype(np.float32)
+        if case == 7:
+            D[:] = -10.0
+            D[H // 2, W // 3] = 5.0  # one valid pixel in the whole map
+        q = svb.default_params(svb.ROBOTICS, ipol_gap_width=gap, add_corners=corners)
+        q_ref = ref.params(0, ipol_gap_width=gap, add_corners=corners)
+        c = svb.Context(q, W, H)
+        try:
+            got = c.gap_interpolation(D)
+        finally:
+            c.close()
+        want = ref.gap_interpolation(q_ref, D)
+        assert np.array_equal(got, want), (W, H, gap, corners, density, int((got != want).sum()))
