@@ -56,13 +56,14 @@ __device__ void unite(int32_t *labels, int a, int b) {
 // Every per-pixel kernel below lets a thread walk RPB consecutive rows of its column: 8x fewer, 8x longer CTAs than
 // one pixel per thread (the one-pixel form was bound by CTA launch rate and exposed load latency).
 constexpr int RPB = 8;
+constexpr int CCL_KEPT = 0x40000000;  // flag in a non-root pixel's label (pixel indices are < 2^26)
 constexpr int TW = 128, TH = 2 * RPB;  // tile: 128 columns x 16 rows, 256 threads (thread = one column, 8 rows)
 
 // grid: (ceil(W/TW), ceil(H/TH), nimg).  labels: -1 for invalid pixels, else the global index (v*W + u) of the pixel's
 // tile-local root; sizes = size of the tile-local component at its local root, 0 everywhere else.
 __global__ void __launch_bounds__(2 * TW) k_ccl_tile(const float *__restrict__ D_all, int32_t *__restrict__ labels_all,
                                                     int32_t *__restrict__ sizes_all, int32_t *__restrict__ roots_all, int32_t *__restrict__ counts_all,
-                                                    int W, int H, float thr) {
+                                                    int W, int H, float thr, int min_size) {
     __shared__ float sD[TH * TW];
     __shared__ int sL[TH * TW];
     __shared__ int sS[TH * TW];
@@ -110,17 +111,23 @@ __global__ void __launch_bounds__(2 * TW) k_ccl_tile(const float *__restrict__ D
         unite(sL, idx, idx - TW);
     }
     __syncthreads();
-    // flatten, count the tile-local sizes (equal roots combined inside each warp first)
+    // flatten; the tile-local sizes are counted per run segment (the part of a horizontal run inside one warp's 32 columns): its first
+    // lane adds the segment's length to the root
     int root[RPB];
 #pragma unroll
     for (int k = 0; k < RPB; k++) {
         const int idx = (r0 + k) * TW + c;
         const int l = sL[idx];
         root[k] = l >= 0 ? find_root(sL, l) : -1;
-        const unsigned act = __ballot_sync(0xFFFFFFFFu, root[k] >= 0);
-        if (root[k] >= 0) {
-            const unsigned same = __match_any_sync(act, root[k]);
-            if (lane == __ffs(same) - 1) atomicAdd(&sS[root[k]], __popc(same));
+        // segment starts: valid lanes whose label is not shared with the lane to the left
+        const int left = __shfl_up_sync(0xFFFFFFFFu, l, 1);
+        const bool start = l >= 0 && (lane == 0 || left != l);
+        const unsigned valid = __ballot_sync(0xFFFFFFFFu, l >= 0), starts = __ballot_sync(0xFFFFFFFFu, start);
+        if (start) {
+            // the segment ends before the next start or the next invalid lane
+            const unsigned stop = (starts | ~valid) & (lane == 31 ? 0u : (0xFFFFFFFFu << (lane + 1)));
+            const int end = stop ? __ffs(stop) - 1 : 32;
+            atomicAdd(&sS[root[k]], end - lane);
         }
     }
     __syncthreads();
@@ -138,6 +145,9 @@ __global__ void __launch_bounds__(2 * TW) k_ccl_tile(const float *__restrict__ D
         if (root[k] >= 0) {
             const int rr = root[k] >> 7, rc = root[k] & (TW - 1);
             label = (y0 + rr) * W + x0 + rc;
+            // a component that is large enough inside this tile alone is kept whatever it joins across the borders: its pixels say so
+            // themselves, and the pruning pass skips them without a look-up (root entries are parent pointers and stay plain)
+            if (root[k] != idx && sS[root[k]] >= min_size) label |= CCL_KEPT;
         }
         labels[g] = label;
         if (root[k] == idx) {  // a tile-local root: its size is only ever read at this index
@@ -178,8 +188,8 @@ __global__ void __launch_bounds__(256) k_ccl_borders(const float *__restrict__ D
     } else {
         return;
     }
-    SVB_GUARD_ASSERT(p >= 0 && p < W * H && q >= 0 && q < W * H && labels[p] >= 0 && labels[q] >= 0);
-    unite(labels, labels[p], labels[q]);  // both pixels are valid: their labels are local roots
+    SVB_GUARD_ASSERT(p >= 0 && p < W * H && q >= 0 && q < W * H && labels[p] >= 0 && labels[q] >= 0 && (labels[p] & ~CCL_KEPT) < W * H);
+    unite(labels, labels[p] & ~CCL_KEPT, labels[q] & ~CCL_KEPT);  // both pixels are valid: their labels are local roots
 }
 
 // Every tile-local root adds its size to the root of its component: one warp per tile walks the tile's root list.
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(128) k_ccl_prune(float *__restrict__ D_all, co
         const int r = labels[idx];
         if (r < 0) {
             if (1 < min_size) D_all[img + (unsigned)idx] = -10.f;
-        } else if (sizes_all[img + (unsigned)labels[r]] < min_size) {  // r is a tile-local root; k_ccl_totals compressed its path
+        } else if (!(r & CCL_KEPT) && sizes_all[img + (unsigned)labels[r]] < min_size) {  // r is a tile-local root; k_ccl_totals compressed its path
             D_all[img + (unsigned)idx] = -10.f;
         }
     }
@@ -239,7 +249,7 @@ int launch_ccl_label(const Dims &d, const svb_params &p, const float *D, int32_t
     if (nimg <= 0) return SVB_OK;
     const int W = d.Dw, H = d.Dh;
     dim3 tiles((W + TW - 1) / TW, (H + TH - 1) / TH, nimg);
-    k_ccl_tile<<<tiles, 2 * TW, 0, s>>>(D, labels, sizes, roots, counts, W, H, p.speckle_sim_threshold);
+    k_ccl_tile<<<tiles, 2 * TW, 0, s>>>(D, labels, sizes, roots, counts, W, H, p.speckle_sim_threshold, ccl_min_size(d, p));
     SVB_LAUNCH_CHECK();
     const int border_edges = ((H - 1) / TH) * W + ((W - 1) / TW) * H;
     if (border_edges > 0) {
