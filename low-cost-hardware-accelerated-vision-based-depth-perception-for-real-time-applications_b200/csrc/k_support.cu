@@ -168,6 +168,178 @@ __global__ void __launch_bounds__(SM_WARPS * 32) k_support_match(const uint8_t *
     if (has) dcan_raw[(size_t)f * cw * ch + (size_t)vc * cw + uc] = (int16_t)result;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Matching, one CTA per lattice row (the form every frame up to 3845 pixels wide uses; the patch kernel above remains for wider ones).
+//
+// The two "other image" rows a lattice row reads (v - 2 and v + 2) are staged in shared memory once, and every lane walks ITS OWN
+// matched columns: in step k all lanes of the warp evaluate the SAME disparity d_k (so the disparity is a scalar of the key, and
+// a lane's range is the warp's range wherever no border cuts it short) on columns x = u -+ d_k that differ per lane.  Reading
+// different columns per lane costs nothing in shared memory -- the 8 lanes of a quarter warp sit 5 columns = 80 bytes apart, which
+// spreads a 16-byte access over all 32 banks -- whereas the broadcast form above has to walk the UNION of the lanes' column ranges
+// (88 % of its hypotheses are in range) and to test every hypothesis against its lane's range.  Loop body: 2 LDS.128, 16 chained
+// VABSDIFF4.ACC, 3 min/max, 2 IMAD (FMA pipe).  Forward and backward pass are two launches of the same kernel with the images'
+// roles exchanged; the forward result waits in dcan_raw.
+constexpr int MR_MAX_THREADS = 768;  // candidates per lattice row (one CTA); 80 registers x 768 threads fit the register file
+
+__device__ __forceinline__ unsigned imad_fma_pipe(unsigned a, unsigned b, unsigned c) {
+    unsigned r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// RIGHT = false: candidates (uc * step, v) of image `own` = left, matched columns x = u - d in the right image, result -> dcan_raw
+// RIGHT = true : candidates (u - d_forward, v) of image `own` = right, matched columns x = u' + d in the left image; dcan_raw keeps
+//                d_forward where the backward match agrees within lr_threshold, else -1 (elas.cpp:394-411)
+// grid: (vc1 - vc0, nf); dynamic smem: 2 * row_cols uint4
+template <bool RIGHT, bool COUNT>
+__global__ void __launch_bounds__(MR_MAX_THREADS) k_support_match_row(const uint8_t *__restrict__ desc_own, const uint8_t *__restrict__ desc_oth,
+                                                                       int16_t *__restrict__ dcan_raw, int W, int H, int cw, int ch, int step,
+                                                                       int disp_min, int disp_max, int support_texture, float support_threshold,
+                                                                       int lr_threshold, int vc0, int padl, int row_cols, unsigned long long *evals) {
+    // [2][row_cols]: rows v - 2 and v + 2 of the other image, column x at index padl + x.  padl = 32 * step + 8 columns left of column 0:
+    // the lanes beside the one with the largest range start up to 31 * step + 2 columns before column 5 (their hypotheses there are discarded)
+    extern __shared__ __align__(128) uint4 s_match_rows[];
+    const int lane = threadIdx.x & 31;
+    const int vc = vc0 + blockIdx.x, f = blockIdx.y;
+    const int v = vc * step;
+    int uc = 1 + threadIdx.x;
+    bool has = uc < cw;
+    const size_t row_cell = (size_t)f * cw * ch + (size_t)vc * cw;
+    if (v < 5 || v > H - 6) {  // no candidate of this row is inside the frame (elas.cpp:279)
+        if (!RIGHT && has) dcan_raw[row_cell + uc] = -1;
+        return;
+    }
+    // Backward pass: only the candidates the forward pass matched take part (5 of 6, fewer on real frames).  They are packed into the
+    // first lanes of the CTA -- neither the shared-memory walk nor its bank alignment cares which candidate a lane holds -- and the
+    // warps left without one retire.
+    __shared__ int s_count[MR_MAX_THREADS / 32];
+    __shared__ int s_packed[MR_MAX_THREADS];  // (uc << 16) | d_forward
+    int d_fwd = -1;
+    if (RIGHT) {
+        d_fwd = has ? dcan_raw[row_cell + uc] : -1;
+        const unsigned matched = __ballot_sync(0xFFFFFFFFu, d_fwd >= 0);
+        if (lane == 0) s_count[threadIdx.x >> 5] = __popc(matched);
+        __syncthreads();
+        int before = __popc(matched & ((1u << lane) - 1u));
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before += s_count[w];
+        if (d_fwd >= 0) s_packed[before] = (uc << 16) | d_fwd;
+    }
+    const size_t fo = (size_t)f * W * H;
+    const uint4 *own = reinterpret_cast<const uint4 *>(desc_own) + fo;
+    const uint4 *oth = reinterpret_cast<const uint4 *>(desc_oth) + fo;
+    for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) {
+        const int r = i >= W ? 1 : 0, x = i - r * W;
+        s_match_rows[r * row_cols + padl + x] = __ldg(oth + (size_t)(v + (r ? 2 : -2)) * W + x);
+    }
+    __syncthreads();
+
+    // the candidate's column in its own image
+    int u;
+    bool ok;
+    if (RIGHT) {
+        int total = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) total += s_count[w];
+        if ((int)(threadIdx.x & ~31u) >= total) return;  // whole warps; no barrier follows
+        has = (int)threadIdx.x < total;
+        const int e = has ? s_packed[threadIdx.x] : 0;
+        uc = has ? e >> 16 : 1;
+        d_fwd = has ? (e & 0xFFFF) : -1;
+        u = uc * step - max(d_fwd, 0);
+        ok = has;
+    } else {
+        u = min(uc, cw - 1) * step;
+        ok = has;
+    }
+    const size_t cell = row_cell + uc;
+    // candidate validity and disparity range (elas.cpp:279,296-300,318-327)
+    ok = ok && u >= 5 && u <= W - 6;
+    if (ok) ok = (int)texture16(__ldg(own + (size_t)v * W + u)) >= support_texture;
+    const int dmin = max(disp_min, 0);
+    const int dmax = RIGHT ? min(disp_max, W - u - 5) : min(disp_max, u - 5);
+    ok = ok && (dmax - dmin >= 10);
+    unsigned n_hyp = ok ? (unsigned)(dmax - dmin + 1) : 0u;  // elas.cpp:330: every d of the range is evaluated
+    int result = -1;
+    const int d_hi = __reduce_max_sync(0xFFFFFFFFu, ok ? dmax : -1);  // the warp walks d = dmin .. d_hi
+    if (d_hi >= 0) {
+        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
+        if (ok) {
+            a0 = __ldg(own + (size_t)(v - 2) * W + u - 2);
+            a1 = __ldg(own + (size_t)(v - 2) * W + u + 2);
+            a2 = __ldg(own + (size_t)(v + 2) * W + u - 2);
+            a3 = __ldg(own + (size_t)(v + 2) * W + u + 2);
+        }
+        // Columns ascend in both passes.  The left candidates of a warp sit `step` columns apart and walk d = d_hi down to dmin in
+        // lock step: with step = 5 the 8 lanes of a quarter warp read 16-byte columns 80 bytes apart -- all 32 banks, no conflict.
+        // The right candidates u - d_forward sit anywhere; lane j of a quarter warp therefore starts up to 7 columns early, on a column
+        // whose index is j modulo 8 (again one bank group per lane), and carries its own disparity counter.
+        const int shift = RIGHT ? ((padl + u + dmin - lane) & 7) : 0;
+        const int x0 = RIGHT ? u + dmin - shift : u - d_hi;
+        const int n = RIGHT ? __reduce_max_sync(0xFFFFFFFFu, ok ? dmax - dmin + 1 + shift : 0) : d_hi - dmin + 1;
+        const uint4 *pt = s_match_rows + padl + x0, *pb = pt + row_cols;
+        SVB_GUARD_ASSERT(padl + x0 - 2 >= 0 && padl + x0 + n + 2 <= row_cols);
+        unsigned drel = (unsigned)(RIGHT ? -shift : d_hi - dmin);  // d - dmin of the step; a hypothesis counts iff drel <= span
+        const unsigned span = (unsigned)(dmax - dmin);
+        // constants the compiler cannot see through (blockDim.z is 1): key = e * 65536 + drel stays an IMAD on the FMA pipe, which is
+        // idle here, instead of becoming a shift-add on the ALU pipe, which is the limiter
+        const unsigned one = blockDim.z, shift16 = 65536u * blockDim.z;
+        const unsigned dstep = RIGHT ? 1u : 0xFFFFFFFFu;
+        unsigned best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;  // (E << 16) | (d - dmin)
+        // ring of four descriptors per row: the descriptor of column x + 2 is needed again four steps later as column (x + 4) - 2
+        uint4 t0 = pt[-2], t1 = pt[-1], t2 = pt[0], t3 = pt[1];
+        uint4 b0 = pb[-2], b1 = pb[-1], b2 = pb[0], b3 = pb[1];
+#define SVB_ROW_STEP(TK, BK, OFF, PRED)                                \
+    {                                                                  \
+        const uint4 tn = pt[2 + OFF], bn = pb[2 + OFF];                \
+        unsigned e = sad16_acc(a0, TK, 0u);                            \
+        e = sad16_acc(a1, tn, e);                                      \
+        e = sad16_acc(a2, BK, e);                                      \
+        e = sad16_acc(a3, bn, e);                                      \
+        const unsigned key = imad_fma_pipe(e, shift16, drel);          \
+        if (!(PRED) || drel <= span) {                                 \
+            second = min(second, max(best, key));                      \
+            best = min(best, key);                                     \
+        }                                                              \
+        drel = imad_fma_pipe(dstep, one, drel);                        \
+        TK = tn;                                                       \
+        BK = bn;                                                       \
+    }
+#define SVB_ROW_WALK(PRED)                                 \
+    {                                                      \
+        _Pragma("unroll 2") for (int g = n >> 2; g > 0; g--) { \
+            SVB_ROW_STEP(t0, b0, 0, PRED)                  \
+            SVB_ROW_STEP(t1, b1, 1, PRED)                  \
+            SVB_ROW_STEP(t2, b2, 2, PRED)                  \
+            SVB_ROW_STEP(t3, b3, 3, PRED)                  \
+            pt += 4;                                       \
+            pb += 4;                                       \
+        }                                                  \
+        const int rem = n & 3;                             \
+        if (rem > 0) SVB_ROW_STEP(t0, b0, 0, PRED)         \
+        if (rem > 1) SVB_ROW_STEP(t1, b1, 1, PRED)         \
+        if (rem > 2) SVB_ROW_STEP(t2, b2, 2, PRED)         \
+    }
+        // lanes without a candidate compute garbage that is discarded; where every candidate of the warp has the warp's range
+        // (no border cuts a lane short) the hypotheses need no test at all
+        if (!RIGHT && __all_sync(0xFFFFFFFFu, !ok || dmax == d_hi))
+            SVB_ROW_WALK(false)
+        else
+            SVB_ROW_WALK(true)
+#undef SVB_ROW_WALK
+#undef SVB_ROW_STEP
+        if (ok) {
+            // at least 11 hypotheses were evaluated, so both minima exist (min_1_d >= 0 && min_2_d >= 0)
+            const int min1_e = (int)(best >> 16), min1_d = (int)(best & 0xFFFFu) + dmin, min2_e = (int)(second >> 16);
+            if ((float)min1_e < __fmul_rn(support_threshold, (float)min2_e)) result = min1_d;  // elas.cpp:364
+        }
+    }
+    if (COUNT) {
+        const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, n_hyp);
+        if (lane == 0 && tot) atomicAdd(evals, (unsigned long long)tot);
+    }
+    if (RIGHT) result = (d_fwd >= 0 && result >= 0 && abs(d_fwd - result) <= lr_threshold) ? d_fwd : -1;  // elas.cpp:404-409
+    if (has) dcan_raw[cell] = (int16_t)result;
+}
+
 // Row 0 / column 0 of D_can keep the calloc zero (elas.cpp:387): a valid disparity-0 neighbour for the filters.
 __global__ void k_dcan_border(int16_t *__restrict__ dcan_raw, int cw, int ch) {
     int16_t *d = dcan_raw + (size_t)blockIdx.y * cw * ch;
@@ -575,6 +747,49 @@ int launch_dcan_border(const Dims &d, int16_t *dcan_raw, int nf, cudaStream_t s)
 int launch_support_match_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int nf, int vc0,
                               int vc1, cudaStream_t s) {
     if (nf <= 0 || d.cw < 2 || vc1 <= vc0) return SVB_OK;
+    // one CTA per lattice row wherever a row's candidates fit one CTA and its two descriptor rows fit shared memory (SVB_MATCH_ROWS=0:
+    // the patch kernel everywhere)
+    static const bool rows_off = getenv("SVB_MATCH_ROWS") && atoi(getenv("SVB_MATCH_ROWS")) == 0;
+    const int padl = 32 * d.step + 8;
+    const int row_cols = (padl + d.W + max(p.disp_max, 0) + 24 + 7) & ~7;  // a multiple of 8 columns: both rows start on the same bank
+    const size_t smem = (size_t)2 * row_cols * sizeof(uint4);
+    const int threads = ((d.cw - 1 + 31) / 32) * 32;
+    if (!rows_off && threads <= MR_MAX_THREADS && smem <= 200 * 1024) {
+        static size_t configured[64][4] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const dim3 grid(vc1 - vc0, nf);
+        for (int pass = 0; pass < 2; pass++) {
+            const int which = pass * 2 + (d.evals ? 1 : 0);
+            const void *fn = which == 0   ? (const void *)k_support_match_row<false, false>
+                             : which == 1 ? (const void *)k_support_match_row<false, true>
+                             : which == 2 ? (const void *)k_support_match_row<true, false>
+                                          : (const void *)k_support_match_row<true, true>;
+            if (smem > 48 * 1024 && dev >= 0 && dev < 64 && configured[dev][which] < smem) {
+                cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) {
+                    set_error("cudaFuncSetAttribute(k_support_match_row, %zu): %s", smem, cudaGetErrorString(e));
+                    return SVB_ERR_CUDA;
+                }
+                configured[dev][which] = smem;
+            }
+            const uint8_t *own = pass ? desc2 : desc1, *oth = pass ? desc1 : desc2;
+            if (which == 0)
+                k_support_match_row<false, false><<<grid, threads, smem, s>>>(own, oth, dcan_raw, d.W, d.H, d.cw, d.ch, d.step, p.disp_min, p.disp_max,
+                                                                              p.support_texture, p.support_threshold, p.lr_threshold, vc0, padl, row_cols, nullptr);
+            else if (which == 1)
+                k_support_match_row<false, true><<<grid, threads, smem, s>>>(own, oth, dcan_raw, d.W, d.H, d.cw, d.ch, d.step, p.disp_min, p.disp_max,
+                                                                             p.support_texture, p.support_threshold, p.lr_threshold, vc0, padl, row_cols, d.evals);
+            else if (which == 2)
+                k_support_match_row<true, false><<<grid, threads, smem, s>>>(own, oth, dcan_raw, d.W, d.H, d.cw, d.ch, d.step, p.disp_min, p.disp_max,
+                                                                             p.support_texture, p.support_threshold, p.lr_threshold, vc0, padl, row_cols, nullptr);
+            else
+                k_support_match_row<true, true><<<grid, threads, smem, s>>>(own, oth, dcan_raw, d.W, d.H, d.cw, d.ch, d.step, p.disp_min, p.disp_max,
+                                                                            p.support_texture, p.support_threshold, p.lr_threshold, vc0, padl, row_cols, d.evals);
+            SVB_LAUNCH_CHECK();
+        }
+        return SVB_OK;
+    }
     const int patches = ((d.cw - 1 + PATCH_U - 1) / PATCH_U) * ((vc1 - vc0 + PATCH_V - 1) / PATCH_V);
     dim3 grid((patches + SM_WARPS - 1) / SM_WARPS, nf);
     if (d.evals)
