@@ -4,6 +4,8 @@
 // Replaces Elas::findMatch + updatePosteriorMinimum (src/serial_includes/elas/elas.cpp:655-802) as driven by
 // Elas::computeDisparity (elas.cpp:804-944); the triangle -> pixel assignment comes from the owner map
 // (k_prior.cu).  Evaluation order and the strict "<" (first evaluated wins ties) are the reference's.
+#include <stdlib.h>
+
 #include "svb_internal.h"
 
 namespace svb {
@@ -242,6 +244,162 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Row form (full-resolution maps, plane radius 2 or 3, disp_max <= 1023): one CTA owns one image row of one side.  The row of the
+// other image's descriptors every hypothesis of the row reads, and the bit masks of the one grid row its pixels fall into, are staged
+// in shared memory once; a thread then walks pixels x, x + 256, ... of the row.  Against one pixel per thread this
+//  * replaces the per-pixel 64-bit address arithmetic over six arrays by row bases computed once per CTA,
+//  * lets every lane walk ITS OWN candidates (shared memory does not need the warp to agree on the disparity): a trip of the candidate
+//    loop serves the lane's next two bits, so the trip count is the largest candidate count of a lane, not the size of the union,
+//  * visits only the mask words that have a bit in some lane's cell (a per-cell summary of non-zero words, one REDUX per pixel).
+// Arithmetic, evaluation-order semantics and the packed key are those of dense_body.
+constexpr int DR_THREADS = 256;
+
+template <int SIDE, int RADIUS, bool COUNT>
+__device__ __forceinline__ void dense_row_body(const DenseArgs &a, uint4 *s_oth, uint32_t *s_cell, uint32_t *s_nz) {
+    const int W = a.W, H = a.H;
+    const int v = a.row0 + blockIdx.x;
+    const unsigned uf = blockIdx.y >> 1;
+    const int row = max(min(v, H - 3), 2);  // elas.cpp:718
+    const size_t row_desc = (size_t)uf * (unsigned)(W * H) + (size_t)(row * W);
+    const uint4 *own = reinterpret_cast<const uint4 *>(a.desc[SIDE]) + row_desc;
+    const uint4 *oth = reinterpret_cast<const uint4 *>(a.desc[SIDE ^ 1]) + row_desc;
+    const int pad = a.disp_max + 16;  // columns either side of the row: a hypothesis (or a clamped band address) may leave the row, its result is discarded
+    for (int x = threadIdx.x; x < W; x += DR_THREADS) {
+        SVB_GUARD_DESC(oth + x, SIDE ^ 1);
+        s_oth[pad + x] = __ldg(oth + x);
+    }
+    const int gy = a.grid_size == 1 ? v : (int)__umulhi((unsigned)v, a.grid_magic);  // v >= 0: equals the float floor (elas.cpp:744-745)
+    const int gwords = a.gwords;
+    const uint32_t *cells = a.grid[SIDE] + (size_t)uf * (unsigned)(a.gw * a.gh * gwords) + (size_t)(gy * a.gw * gwords);
+    for (int i = threadIdx.x; i < a.gw * gwords; i += DR_THREADS) s_cell[i] = __ldg(cells + i);
+    __syncthreads();
+    for (int g = threadIdx.x; g < a.gw; g += DR_THREADS) {
+        unsigned nz = 0u;
+        for (int w = 0; w < gwords; w++) nz |= s_cell[g * gwords + w] ? (1u << w) : 0u;
+        s_nz[g] = nz;
+    }
+    __syncthreads();
+    const size_t row_map = (size_t)uf * (unsigned)a.DN + (size_t)(v * W);
+    const int32_t *owner = a.owner[SIDE] + row_map;
+    float *D = a.D[SIDE] + row_map;
+    const PlaneRec *rec = a.rec[SIDE] + (size_t)uf * (unsigned)a.maxT;
+    const uint4 k128 = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+    const float fv = (float)v;
+    unsigned n_hyp = 0u;
+    const int lane = threadIdx.x & 31;
+    for (int u = threadIdx.x; u - lane < W; u += DR_THREADS) {  // whole warps: the loops below vote
+        const bool in = u < W;
+        const int uc = in ? u : W - 1;
+        const int gx = a.grid_size == 1 ? uc : (int)__umulhi((unsigned)uc, a.grid_magic);
+        const int o = in ? __ldg(owner + u) : -1;
+        const uint4 c = __ldg(own + uc);
+        // elas.cpp:714 (column range) and :731-736 (texture)
+        const bool active = in && o >= 0 && u >= 2 && u < W - 2 && (int)sad16(c, k128) >= a.match_texture;
+        int d_plane = 0, dmin = 1, dmax = 0;  // empty band for inactive lanes
+        unsigned prior_on = 0u;
+        if (active) {
+            const PlaneRec pr = rec[(unsigned)o];
+            // elas.cpp:739: (a*u + b*v) + c in f32, separate roundings, truncation like cvttss2si
+            const float fp = __fadd_rn(__fadd_rn(__fmul_rn(pr.a, (float)u), __fmul_rn(pr.b, fv)), pr.c);
+            d_plane = f2i_trunc_x86(fp);
+            dmin = max((int)((unsigned)d_plane - (unsigned)a.plane_radius), 0);
+            dmax = min((int)((unsigned)d_plane + (unsigned)a.plane_radius), a.disp_max);
+            prior_on = pr.valid ? 0xFFFFFFFFu : 0u;
+        }
+        // warped column u -+ d must lie in [2, W-2): an interval of admissible d
+        const int dlo = SIDE ? 2 - u : u - (W - 3);
+        const int dhi = SIDE ? (W - 3) - u : u - 2;
+        const uint4 *po = s_oth + pad + uc;  // hypothesis d reads po[-d] (left) / po[+d] (right)
+
+        // (i) grid candidates outside the band (elas.cpp:759-767 / 778-786); see grid_phase for the two mask forms
+        unsigned key = 0xFFFFFFFFu;
+        const bool clip = __any_sync(0xFFFFFFFFu, active && (dlo > 0 || dhi < a.disp_max));
+        const unsigned width = dmax >= dmin ? (2u << (dmax - dmin)) - 1u : 0u;
+        const unsigned band_lo = width << (dmin & 31), band_hi = __funnelshift_l(width, 0u, dmin & 31);
+        const int wband = dmin >> 5;
+        const uint32_t *cw = s_cell + gx * gwords;
+        unsigned words = __reduce_or_sync(0xFFFFFFFFu, active ? s_nz[gx] : 0u);
+        while (words) {
+            const int w = __ffs(words) - 1;
+            words &= words - 1u;
+            uint32_t mine = active ? cw[w] : 0u;
+            if (clip) {
+                if (mine) mine &= ~range_mask(dmin, dmax, w << 5) & range_mask(dlo, dhi, w << 5);
+            } else {
+                mine &= ~((w == wband ? band_lo : 0u) | (w == wband + 1 ? band_hi : 0u));
+            }
+            if (COUNT) n_hyp += __popc(mine);
+            while (__any_sync(0xFFFFFFFFu, mine != 0u)) {
+                // the lane's next two candidates: both loads are in flight before either SAD chain starts (a lane that has none left
+                // re-reads the word's first column and discards the result)
+                const uint32_t bit0 = mine & (0u - mine);
+                mine ^= bit0;
+                const uint32_t bit1 = mine & (0u - mine);
+                mine ^= bit1;
+                const int d0 = (w << 5) + (bit0 ? 31 - __clz(bit0) : 0);
+                const int d1 = (w << 5) + (bit1 ? 31 - __clz(bit1) : 0);
+                SVB_GUARD_ASSERT(d0 >= 0 && d0 <= pad && d1 >= 0 && d1 <= pad);
+                const uint4 o0 = po[SIDE ? d0 : -d0];
+                const uint4 o1 = po[SIDE ? d1 : -d1];
+                const unsigned cand0 = (sad16_acc(c, o0, a.bias) << 13) + (unsigned)d0;
+                const unsigned cand1 = (sad16_acc(c, o1, a.bias) << 13) + (unsigned)d1;
+                key = min(key, bit0 ? cand0 : 0xFFFFFFFFu);
+                key = min(key, bit1 ? cand1 : 0xFFFFFFFFu);
+            }
+        }
+        // (ii) the plane band with the prior (elas.cpp:768-774 / 787-793)
+        const int lo2 = max(dmin, dlo), hi2 = min(dmax, dhi);
+        const unsigned span = hi2 >= lo2 ? (unsigned)(hi2 - lo2) : 0u;
+        const int lo3 = hi2 >= lo2 ? lo2 : 0x40000000;  // empty interval: nothing passes the unsigned range test
+        {
+            // for the ADDRESS the plane disparity is clamped to [-8, disp_max + 8] (see dense_body): inside the staged row's margins
+            const int d_addr = min(max(d_plane, -8), a.disp_max + 8);
+            const uint4 *pb = po + (SIDE ? d_addr : -d_addr);
+            uint4 ob[2 * RADIUS + 1];
+            bool okb[2 * RADIUS + 1];
+#pragma unroll
+            for (int k = -RADIUS; k <= RADIUS; k++) {
+                const int d = (int)((unsigned)d_plane + (unsigned)k);
+                okb[k + RADIUS] = (unsigned)(d - lo3) <= span;
+                ob[k + RADIUS] = pb[SIDE ? k : -k];
+                if (COUNT) n_hyp += okb[k + RADIUS] ? 1u : 0u;
+            }
+            unsigned seed[RADIUS + 1];  // bias + prior of |k| (the prior only where both planes are valid, elas.cpp:910)
+#pragma unroll
+            for (int k = 0; k <= RADIUS; k++) seed[k] = a.bias + ((unsigned)a.P[k] & prior_on);
+#pragma unroll
+            for (int k = -RADIUS; k <= RADIUS; k++) {
+                const unsigned dk = (unsigned)d_plane + (unsigned)(0x1000 + k);  // phase bit + d
+                const unsigned cand = (sad16_acc(c, ob[k + RADIUS], seed[k < 0 ? -k : k]) << 13) + dk;
+                key = min(key, okb[k + RADIUS] ? cand : 0xFFFFFFFFu);
+            }
+        }
+        if (in) {
+            float out = -10.f;                                                    // elas.cpp:820-826: pixels nobody writes keep -10
+            if (active) out = key != 0xFFFFFFFFu ? (float)(key & 0xFFFu) : -1.f;  // elas.cpp:797-800
+            D[u] = out;
+        }
+    }
+    if (COUNT) {
+        const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, n_hyp);
+        if (lane == 0 && tot) atomicAdd(a.evals + 1, (unsigned long long)tot);
+    }
+}
+
+// grid: (rows, nf * 2); dynamic smem: (W + 2 (disp_max + 16)) uint4, then gw * gwords + gw words
+template <int RADIUS, bool COUNT>
+__global__ void __launch_bounds__(DR_THREADS) k_dense_row(const DenseArgs a) {
+    extern __shared__ __align__(16) uint4 s_dense_row[];
+    uint4 *s_oth = s_dense_row;
+    uint32_t *s_cell = reinterpret_cast<uint32_t *>(s_dense_row + a.W + 2 * (a.disp_max + 16));
+    uint32_t *s_nz = s_cell + a.gw * a.gwords;
+    if (blockIdx.y & 1)
+        dense_row_body<1, RADIUS, COUNT>(a, s_oth, s_cell, s_nz);
+    else
+        dense_row_body<0, RADIUS, COUNT>(a, s_oth, s_cell, s_nz);
+}
+
 template <int RADIUS, bool COUNT>
 __global__ void __launch_bounds__(128, 12) k_dense(const DenseArgs a) {
     if (blockIdx.z & 1)
@@ -299,8 +457,40 @@ int launch_dense_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, 
         return SVB_ERR_UNSUPPORTED;
     }
     const int rows = d.sub ? d.Dh : row1 - row0;
-    dim3 grid((d.Dw + 127) / 128, rows, nf * 2);
     a.evals = d.evals;
+    // the row form wherever it applies (SVB_DENSE_ROWS=0: one pixel per thread everywhere)
+    static const bool rows_off = getenv("SVB_DENSE_ROWS") && atoi(getenv("SVB_DENSE_ROWS")) == 0;
+    const size_t row_smem = ((size_t)d.W + 2 * (p.disp_max + 16)) * sizeof(uint4) + ((size_t)d.gw * d.gwords + d.gw) * sizeof(uint32_t);
+    if (!rows_off && !d.sub && (d.plane_radius == 2 || d.plane_radius == 3) && d.gwords <= 32 && row_smem <= 55 * 1024) {  // at least four CTAs per SM: wider rows (4K) are faster one pixel per thread
+        const int which = (d.plane_radius == 3 ? 2 : 0) + (d.evals ? 1 : 0);
+        const void *fn = which == 0   ? (const void *)k_dense_row<2, false>
+                         : which == 1 ? (const void *)k_dense_row<2, true>
+                         : which == 2 ? (const void *)k_dense_row<3, false>
+                                      : (const void *)k_dense_row<3, true>;
+        static size_t configured[64][4] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (row_smem > 48 * 1024 && dev >= 0 && dev < 64 && configured[dev][which] < row_smem) {
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem);
+            if (e != cudaSuccess) {
+                set_error("cudaFuncSetAttribute(k_dense_row, %zu): %s", row_smem, cudaGetErrorString(e));
+                return SVB_ERR_CUDA;
+            }
+            configured[dev][which] = row_smem;
+        }
+        const dim3 rgrid(rows, nf * 2);
+        if (which == 0)
+            k_dense_row<2, false><<<rgrid, DR_THREADS, row_smem, s>>>(a);
+        else if (which == 1)
+            k_dense_row<2, true><<<rgrid, DR_THREADS, row_smem, s>>>(a);
+        else if (which == 2)
+            k_dense_row<3, false><<<rgrid, DR_THREADS, row_smem, s>>>(a);
+        else
+            k_dense_row<3, true><<<rgrid, DR_THREADS, row_smem, s>>>(a);
+        SVB_LAUNCH_CHECK();
+        return SVB_OK;
+    }
+    dim3 grid((d.Dw + 127) / 128, rows, nf * 2);
     if (d.evals) {
         if (d.plane_radius == 2)
             k_dense<2, true><<<grid, 128, 0, s>>>(a);

@@ -617,3 +617,40 @@ def test_gap_interpolation_on_random_validity_maps(svb, ref, W, H):
             c.close()
         want = ref.gap_interpolation(q_ref, D)
         assert np.array_equal(got, want), (W, H, gap, corners, density, int((got != want).sum()))
+
+
+def test_patch_form_of_support_matching(svb, ref, kitti_gray, monkeypatch):
+    """Frames wider than 3845 pixels (more lattice candidates per row than one CTA holds) use the patch form of support matching
+    (k_support_match); SVB_MATCH_ROWS=0 forces it onto KITTI-size, ragged and subsampled frames: candidate lattice and everything
+    downstream against the oracle."""
+    monkeypatch.setenv("SVB_MATCH_ROWS", "0")
+    import subprocess
+    import sys
+    import textwrap
+
+    # the switch is read once per process: run the check in a fresh interpreter
+    code = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import numpy as np
+        from conftest import load_binding
+        import parity
+        from oracle.ref import RefElas
+        svb = load_binding().binding
+        ref = RefElas()
+        z = np.load(%r)
+        cases = [(z["L5"], z["R5"], svb.default_params(svb.PIPELINE), ref.pipeline_params()),
+                 (z["L5"], z["R5"], svb.default_params(svb.PIPELINE, subsampling=1), ref.pipeline_params(subsampling=1))]
+        Ls, Rs = svb.synth_pair(32, 517, 203, 1)
+        cases.append((Ls, Rs, svb.default_params(svb.ROBOTICS), ref.params(0)))
+        for L, R, p, p_ref in cases:
+            ctx = svb.Context(p, L.shape[1], L.shape[0])
+            res, t, _ = parity.staged_parity(ctx, ref, p_ref, L, R, inject=False)
+            bad = {k: v for k, v in res.items() if isinstance(v, dict) and not v["equal"]}
+            assert not bad, bad
+            ctx.close()
+        print("patch form: OK")
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
+            os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kitti_gray.npz"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
