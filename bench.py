@@ -87,11 +87,11 @@ def stage_bytes(p, d):
 # What actually bounds each stage's kernels (ncu --set full captures under profiles/): only the stages labelled "hbm"
 # are meant to be read against the HBM peak; the others carry their HBM figure for completeness.
 STAGE_BOUND = {
-    "descriptor": "hbm + alu (tile staging)", "support_match": "int_alu (VABSDIFF4, half-rate pipe)", "support_filter": "latency (one CTA per frame)",
+    "descriptor": "hbm + alu (tile staging)", "support_match": "int_alu (VABSDIFF4, half-rate pipe; 16 of 19 ALU instructions per hypothesis are the SAD)", "support_filter": "latency (one CTA per frame)",
     "delaunay_device": "latency (one CTA per triangulation, sequential merges near the root)", "planes": "latency", "grid": "latency",
     "raster": "l2 atomics", "dense_match": "issue + int_alu", "lr_check": "hbm", "remove_small_segments": "issue (shared-memory union-find)",
-    "gap_interpolation": "latency (ballot scans)", "adaptive_mean": "fp32 issue", "median": "fp32 issue", "reproject": "hbm + fp64",
-    "post_fused": "fp32 / fp64 issue (480 instructions per pixel)", "h2d_triangles": "pcie", "d2h_support": "pcie",
+    "gap_interpolation": "issue (validity bit words; the map is read once)", "adaptive_mean": "fp32 issue", "median": "fp32 issue", "reproject": "hbm + fp64",
+    "post_fused": "fp32 / fp64 issue (about 350 instructions per pixel)", "h2d_triangles": "pcie", "d2h_support": "pcie",
 }
 
 

@@ -459,7 +459,8 @@ int launch_dense_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, 
     const int rows = d.sub ? d.Dh : row1 - row0;
     a.evals = d.evals;
     // the row form wherever it applies (SVB_DENSE_ROWS=0: one pixel per thread everywhere)
-    static const bool rows_off = getenv("SVB_DENSE_ROWS") && atoi(getenv("SVB_DENSE_ROWS")) == 0;
+    const char *rows_env = getenv("SVB_DENSE_ROWS");  // read per launch: the determinism stress test switches it between contexts
+    const bool rows_off = rows_env && atoi(rows_env) == 0;
     const size_t row_smem = ((size_t)d.W + 2 * (p.disp_max + 16)) * sizeof(uint4) + ((size_t)d.gw * d.gwords + d.gw) * sizeof(uint32_t);
     if (!rows_off && !d.sub && (d.plane_radius == 2 || d.plane_radius == 3) && d.gwords <= 32 && row_smem <= 55 * 1024) {  // at least four CTAs per SM: wider rows (4K) are faster one pixel per thread
         const int which = (d.plane_radius == 3 ? 2 : 0) + (d.evals ? 1 : 0);

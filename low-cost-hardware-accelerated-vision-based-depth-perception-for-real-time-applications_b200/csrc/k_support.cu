@@ -749,7 +749,8 @@ int launch_support_match_rows(const Dims &d, const svb_params &p, const uint8_t 
     if (nf <= 0 || d.cw < 2 || vc1 <= vc0) return SVB_OK;
     // one CTA per lattice row wherever a row's candidates fit one CTA and its two descriptor rows fit shared memory (SVB_MATCH_ROWS=0:
     // the patch kernel everywhere)
-    static const bool rows_off = getenv("SVB_MATCH_ROWS") && atoi(getenv("SVB_MATCH_ROWS")) == 0;
+    const char *rows_env = getenv("SVB_MATCH_ROWS");  // read per launch: the determinism stress test switches it between contexts
+    const bool rows_off = rows_env && atoi(rows_env) == 0;
     const int padl = 32 * d.step + 8;
     const int row_cols = (padl + d.W + max(p.disp_max, 0) + 24 + 7) & ~7;  // a multiple of 8 columns: both rows start on the same bank
     const size_t smem = (size_t)2 * row_cols * sizeof(uint4);

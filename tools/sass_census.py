@@ -14,7 +14,7 @@ EXCLUDE = {"LDG": "LDG.E.128", "STG": "STG.E.128", "RED": "REDUX"}
 
 print("# SASS census of the sm_100a kernels (cuobjdump -sass of the built objects): static instruction counts per kernel;")
 print("# the SAD kernels are VABSDIFF4.U8.ACC chains, vector loads are 128-bit, warp collectives are REDUX / MATCH / VOTE / SHFL;")
-print("# no tensor-core or TMA instruction appears anywhere (none of the stages is a dense contraction, DESIGN.md 5).")
+print("# no tensor-core instruction appears anywhere (none of the stages is a dense contraction, DESIGN.md 5); the descriptor kernel stages its tile with one TMA load (UTMALDG).")
 for obj in sorted(glob.glob(os.path.join(ROOT, "low-cost*", "lib", "obj", "k_*.o"))):
     out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
     fn, cnt = None, collections.OrderedDict()

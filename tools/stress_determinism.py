@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Large-batch determinism check: the same 512 frames through the multi-lane pipeline twice, through the single-stream pipeline,
-with the device vertex order off, with the whole Delaunay stage on the host, with the stage-by-stage tail kernels, and -- on the
+with the device vertex order off, with the whole Delaunay stage on the host, with the stage-by-stage tail kernels, with the patch /
+one-pixel-per-thread forms of the two matching kernels instead of their row forms, and -- on the
 reference's own frames, where two thirds of the right-image lists hold duplicate coordinates -- with the vertex-sort replay on the
 device and on the host; every disparity map and point cloud must agree bit for bit."""
 import hashlib
@@ -21,12 +22,16 @@ Rs = np.stack([p[1] for p in pairs])
 Q = np.array([[1, 0, 0, -609.5593], [0, 1, 0, -172.854], [0, 0, 0, 721.5377], [0, 0, 1.8616, 0]])
 
 
+LAUNCH_TIME = ("SVB_MATCH_ROWS", "SVB_DENSE_ROWS")  # read at every launch, the others when the context is created
+
+
 def run(single_stream, env=None):
     for k, v in (env or {}).items():
         os.environ[k] = v
     ctx = svb.Context(svb.default_params(svb.PIPELINE), W, H, chunk=32)
     for k in (env or {}):
-        del os.environ[k]
+        if k not in LAUNCH_TIME:
+            del os.environ[k]
     ctx.set_calibration(Q)
     ctx.set_single_stream(single_stream)
     ctx.batch_upload(Ls, Rs)
@@ -37,6 +42,8 @@ def run(single_stream, env=None):
         if i % 16 == 0:
             h.update(ctx.batch_points(i).tobytes())
     ctx.close()
+    for k in (env or {}):
+        os.environ.pop(k, None)
     return h.hexdigest()
 
 
@@ -47,8 +54,10 @@ d = run(False, {"SVB_GPU_ORDER": "0"})
 e = run(False, {"SVB_LANES": "6"})
 f = run(False, {"SVB_DELAUNAY_DEVICE": "0"})
 g = run(False, {"SVB_FUSED_POST": "0"})
-print("multi-lane", a[:16], b[:16], "single-stream", c[:16], "host vertex order", d[:16], "6 lanes", e[:16], "host Delaunay", f[:16], "unfused tail", g[:16])
-assert a == b == c == d == e == f == g, "outputs differ between runs"
+h2 = run(False, {"SVB_MATCH_ROWS": "0", "SVB_DENSE_ROWS": "0"})
+print("multi-lane", a[:16], b[:16], "single-stream", c[:16], "host vertex order", d[:16], "6 lanes", e[:16], "host Delaunay", f[:16], "unfused tail", g[:16],
+      "patch / pixel matching kernels", h2[:16])
+assert a == b == c == d == e == f == g == h2, "outputs differ between runs"
 # the reference's own frames (duplicate coordinates in the right image)
 z = np.load(os.path.join(ROOT, "tests", "golden", "kitti_gray.npz"))
 npairs = len([k for k in z.files if k.startswith("L")])
