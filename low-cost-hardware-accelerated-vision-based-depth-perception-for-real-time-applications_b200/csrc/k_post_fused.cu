@@ -154,12 +154,14 @@ __global__ void __launch_bounds__(PF_THREADS, TH == 32 ? 4 : 2) k_post_fused(con
                 const float4 lo = *reinterpret_cast<const float4 *>(row - 4), mid = *reinterpret_cast<const float4 *>(row),
                              hi = *reinterpret_cast<const float4 *>(row + 4);
                 const float x[10] = {lo.y, lo.z, lo.w, mid.x, mid.y, mid.z, mid.w, hi.x, hi.y, hi.z};  // columns c0-3 .. c0+6
+                float m[4];
+                median7x4(x, m);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int u = c0 + j;
                     if (u >= 3 && u < W - 3) {
                         const float own = x[j + 3];
-                        out[j] = own >= 0.f ? median7(x[j], x[j + 1], x[j + 2], x[j + 3], x[j + 4], x[j + 5], x[j + 6]) : own;
+                        out[j] = own >= 0.f ? m[j] : own;
                     }
                 }
             }
@@ -191,10 +193,12 @@ __global__ void __launch_bounds__(PF_THREADS, TH == 32 ? 4 : 2) k_post_fused(con
             SVB_GUARD_ASSERT(r0 - 3 >= 4 && r0 + 6 < RH - 4);
 #pragma unroll
             for (int k = 0; k < 10; k++) x[k] = B[(r0 - 3 + k) * PF_SW + j];
+            float m[4];
+            median7x4(x, m);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int v = v0 + k;
-                if (v >= 3 && v < H - 3 && res[k] >= 0.f) res[k] = median7(x[k], x[k + 1], x[k + 2], x[k + 3], x[k + 4], x[k + 5], x[k + 6]);
+                if (v >= 3 && v < H - 3 && res[k] >= 0.f) res[k] = m[k];
             }
         }
 #pragma unroll
