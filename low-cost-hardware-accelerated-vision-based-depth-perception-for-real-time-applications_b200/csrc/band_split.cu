@@ -267,7 +267,7 @@ int svb_band_process(svb_band_group *g, const uint8_t *I1, const uint8_t *I2, in
     for (int s = 0; s < passes; s++) {
         float *D = L0.Dlr + (size_t)s * N;
         SVB_TRY(launch_remove_small_segments(d, p, D, L0.labels, L0.sizes, L0.ccl_roots, L0.ccl_counts, 1, L0.stream));
-        SVB_TRY(launch_gap(d, p, D, reinterpret_cast<uint32_t *>(L0.sizes), 1, L0.stream));
+        SVB_TRY(launch_gap(d, p, D, reinterpret_cast<uint32_t *>(L0.Dtmp), nullptr, nullptr, 1, L0.stream));
         if (p.filter_adaptive_mean) SVB_TRY(launch_adaptive_mean(d, c0->mean_mode, D, L0.Dtmp, 1, L0.stream));
         if (p.filter_median) SVB_TRY(launch_median(d, D, L0.Dtmp, 1, L0.stream));
     }

@@ -15,8 +15,9 @@
 //   3. totals  : every local root adds its size to its global root.  The tile kernel leaves a compact list of its local roots (a few
 //                per tile) and writes sizes only AT roots, so this step touches a few thousand entries instead of scanning two W*H maps;
 //   4. prune   : pixels whose global root counts < speckle_size become -10 (step 3 leaves every tile-local root pointing straight at
-//                its root, so a pixel gets there in one hop).  Fusing this step into the row pass of the gap interpolation was tried
-//                and measured slower (one warp per row cannot hide the lookup latency the way one thread per pixel does).
+//                its root, so a pixel gets there in one hop; pixels of a component that is large enough inside its tile carry CCL_KEPT
+//                and need no look-up at all).  In the batch pipeline this step rides on the row pass of the gap interpolation
+//                (k_gap_rows, k_post.cu); k_ccl_prune serves the staged calls, tap mode and two-map post-processing.
 #include "svb_internal.h"
 
 namespace svb {
@@ -56,7 +57,6 @@ __device__ void unite(int32_t *labels, int a, int b) {
 // Every per-pixel kernel below lets a thread walk RPB consecutive rows of its column: 8x fewer, 8x longer CTAs than
 // one pixel per thread (the one-pixel form was bound by CTA launch rate and exposed load latency).
 constexpr int RPB = 8;
-constexpr int CCL_KEPT = 0x40000000;  // flag in a non-root pixel's label (pixel indices are < 2^26)
 constexpr int TW = 128, TH = 2 * RPB;  // tile: 128 columns x 16 rows, 256 threads (thread = one column, 8 rows)
 
 // grid: (ceil(W/TW), ceil(H/TH), nimg).  labels: -1 for invalid pixels, else the global index (v*W + u) of the pixel's

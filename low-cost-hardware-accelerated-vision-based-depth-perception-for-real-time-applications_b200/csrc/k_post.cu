@@ -62,22 +62,39 @@ __device__ __forceinline__ float gap_fill_value(float d1, float d2) {
 
 // Row pass, one warp per row.  Dynamic smem: GAP_WARPS * 3 * Cpad words (validity words, carry, ncarry per 32-column chunk).
 // grid: (ceil(H / GAP_WARPS), nimg)
+// labels_all != nullptr: the pruning step of the speckle removal happens here, on the fly (k_ccl_prune's rule: a valid pixel whose
+// component has fewer than min_size pixels becomes -10; most pixels carry CCL_KEPT and need no look-up).
 __global__ void __launch_bounds__(GAP_WARPS * 32) k_gap_rows(float *__restrict__ D_all, uint32_t *__restrict__ bits_all, int W, int H, int Cw,
-                                                             int Cpad, int gap_width, int add_corners) {
+                                                             int Cpad, int gap_width, int add_corners, const int32_t *__restrict__ labels_all,
+                                                             const int32_t *__restrict__ sizes_all, int min_size) {
     extern __shared__ int s_gap[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int v = blockIdx.x * GAP_WARPS + wid;
     if (v >= H) return;  // warp-uniform; the kernel has no CTA-wide barrier
     float *line = D_all + ((size_t)blockIdx.y * H + v) * W;
+    const int32_t *labels = labels_all ? labels_all + (size_t)blockIdx.y * H * W : nullptr;  // the image's label map (indices are image-relative)
+    const int32_t *sizes = labels_all ? sizes_all + (size_t)blockIdx.y * H * W : nullptr;
     uint32_t *words = reinterpret_cast<uint32_t *>(s_gap) + (size_t)wid * 3 * Cpad;
     int *carry = s_gap + (size_t)wid * 3 * Cpad + Cpad, *ncarry = carry + Cpad;
     // 1: validity words (four independent loads in flight per lane)
     for (int k0 = 0; k0 < Cw; k0 += 4) {
         float val[4];
+        int lab[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int u = (k0 + i) * 32 + lane;
             val[i] = u < W ? line[u] : -1.f;
+            lab[i] = (labels && u < W) ? labels[(size_t)v * W + u] : CCL_KEPT;
+        }
+        if (labels) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                // lab is the pixel's tile-local root (k_ccl_totals left every such root pointing straight at its component's root)
+                if (val[i] >= 0.f && !(lab[i] & CCL_KEPT) && sizes[labels[lab[i]]] < min_size) {
+                    val[i] = -10.f;
+                    line[(k0 + i) * 32 + lane] = -10.f;
+                }
+            }
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -469,7 +486,7 @@ int gap_smem_optin(K kernel, size_t smem, size_t (&configured)[64]) {
 size_t gap_scratch_words(const Dims &d, int nimg) { return (size_t)nimg * d.Dh * ((d.Dw + 31) / 32); }
 
 // scratch: gap_scratch_words(d, nimg) words (the validity bits the row pass hands to the column pass)
-int launch_gap(const Dims &d, const svb_params &p, float *D, uint32_t *scratch, int nimg, cudaStream_t s) {
+int launch_gap(const Dims &d, const svb_params &p, float *D, uint32_t *scratch, const int32_t *labels, const int32_t *sizes, int nimg, cudaStream_t s) {
     if (nimg <= 0) return SVB_OK;
     const int W = d.Dw, H = d.Dh, Cw = (W + 31) / 32, HW = (H + 31) / 32;
     const int Cpad = (Cw + 3) & ~3;
@@ -478,7 +495,7 @@ int launch_gap(const Dims &d, const svb_params &p, float *D, uint32_t *scratch, 
         static size_t configured[64] = {};
         SVB_TRY(gap_smem_optin(k_gap_rows, smem, configured));
         dim3 grid((H + GAP_WARPS - 1) / GAP_WARPS, nimg);
-        k_gap_rows<<<grid, GAP_WARPS * 32, smem, s>>>(D, scratch, W, H, Cw, Cpad, gap_width_of(d, p), p.add_corners);
+        k_gap_rows<<<grid, GAP_WARPS * 32, smem, s>>>(D, scratch, W, H, Cw, Cpad, gap_width_of(d, p), p.add_corners, labels, sizes, ccl_min_size(d, p));
         SVB_LAUNCH_CHECK();
     }
     {

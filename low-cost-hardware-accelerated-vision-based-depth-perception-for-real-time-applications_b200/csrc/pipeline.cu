@@ -488,14 +488,23 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, 
     // needs the left and right blocks to be adjacent: true when nf == chunk, otherwise run the sides separately
     const int passes = both ? 2 : 1;
     SVB_TRY(T.mark(ST_SEGMENTS));
-    for (int s = 0; s < passes; s++)
-        SVB_TRY(launch_remove_small_segments(d, p, s ? D2 : D1, L.labels, L.sizes, L.ccl_roots, L.ccl_counts, nf, L.stream));
+    // one map to post-process and no taps: the pruning step of the speckle removal rides on the row pass of the gap interpolation
+    const bool prune_in_gap = passes == 1 && !c->tap_mode;
+    for (int s = 0; s < passes; s++) {
+        if (prune_in_gap)
+            SVB_TRY(launch_ccl_label(d, p, D1, L.labels, L.sizes, L.ccl_roots, L.ccl_counts, nf, L.stream));
+        else
+            SVB_TRY(launch_remove_small_segments(d, p, s ? D2 : D1, L.labels, L.sizes, L.ccl_roots, L.ccl_counts, nf, L.stream));
+    }
     if (c->tap_mode && nf == 1) {
         SVB_TRY(tap_store(c, "D1seg", D1, DN * 4, L.stream));
         if (both) SVB_TRY(tap_store(c, "D2seg", D2, DN * 4, L.stream));
     }
     SVB_TRY(T.mark(ST_GAP));
-    for (int s = 0; s < passes; s++) SVB_TRY(launch_gap(d, p, s ? D2 : D1, reinterpret_cast<uint32_t *>(L.sizes), nf, L.stream));  // the component sizes are dead by now
+    // (the validity bits go through Dtmp, which the tail kernels only use later)
+    for (int s = 0; s < passes; s++)
+        SVB_TRY(launch_gap(d, p, s ? D2 : D1, reinterpret_cast<uint32_t *>(L.Dtmp), prune_in_gap ? L.labels : nullptr, prune_in_gap ? L.sizes : nullptr, nf,
+                           L.stream));
     if (c->tap_mode && nf == 1) {
         SVB_TRY(tap_store(c, "D1gap", D1, DN * 4, L.stream));
         if (both) SVB_TRY(tap_store(c, "D2gap", D2, DN * 4, L.stream));
@@ -1114,7 +1123,7 @@ static int stage_inplace(svb_context *c, float *D, int which) {
     if (!D) return SVB_ERR_ARG;
     SVB_CUDA(cudaMemcpyAsync(L.Dlr, D, (size_t)d.DN * 4, cudaMemcpyHostToDevice, L.stream));
     if (which == 0) SVB_TRY(launch_remove_small_segments(d, c->p, L.Dlr, L.labels, L.sizes, L.ccl_roots, L.ccl_counts, 1, L.stream));
-    if (which == 1) SVB_TRY(launch_gap(d, c->p, L.Dlr, reinterpret_cast<uint32_t *>(L.sizes), 1, L.stream));
+    if (which == 1) SVB_TRY(launch_gap(d, c->p, L.Dlr, reinterpret_cast<uint32_t *>(L.Dtmp), nullptr, nullptr, 1, L.stream));
     if (which == 2) SVB_TRY(launch_adaptive_mean(d, c->mean_mode, L.Dlr, L.Dtmp, 1, L.stream));
     if (which == 3) SVB_TRY(launch_median(d, L.Dlr, L.Dtmp, 1, L.stream));
     SVB_CUDA(cudaMemcpyAsync(D, L.Dlr, (size_t)d.DN * 4, cudaMemcpyDeviceToHost, L.stream));

@@ -161,8 +161,10 @@ int launch_lr_check(const Dims &d, const svb_params &p, const float *D1in, const
                     cudaStream_t s);
 int launch_lr_check_rows(const Dims &d, const svb_params &p, const float *D1in, const float *D2in, float *D1out, float *D2out, int nf, int row0,
                          int row1, cudaStream_t s);
-// scratch: nimg * Dh * ceil(Dw / 32) words (row-pass validity bits for the column pass)
-int launch_gap(const Dims &d, const svb_params &p, float *D, uint32_t *scratch, int nimg, cudaStream_t s);
+// scratch: nimg * Dh * ceil(Dw / 32) words (row-pass validity bits for the column pass).  labels / sizes non-null: the row pass also does
+// the pruning step of the speckle removal (launch_ccl_label has run, launch_ccl_prune has not) on maps whose invalid pixels are all -10
+int launch_gap(const Dims &d, const svb_params &p, float *D, uint32_t *scratch, const int32_t *labels, const int32_t *sizes, int nimg, cudaStream_t s);
+constexpr int CCL_KEPT = 0x40000000;  // flag in a non-root pixel's label: its component is large enough inside its tile (pixel indices are < 2^26)
 int launch_adaptive_mean(const Dims &d, int mean_mode, float *D, float *tmp, int nimg, cudaStream_t s);
 int launch_median(const Dims &d, float *D, float *tmp, int nimg, cudaStream_t s);
 // k_ccl.cu
