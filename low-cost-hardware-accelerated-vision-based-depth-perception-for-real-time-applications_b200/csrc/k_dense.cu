@@ -35,6 +35,7 @@ struct DenseArgs {
     const uint8_t *desc_lo[2], *desc_hi[2];  // the descriptor arenas including their guard bands (range asserts of the guard build)
     unsigned bias;  // Dims::cost_bias: keeps SAD + P >= 0 in the unsigned key
     unsigned long long *evals;  // COUNT variant only: number of evaluated hypotheses (elas.cpp:759-793)
+    int owner_gen;              // generation of the owner map's entries (owner_untag); 0 = plain indices
 };
 
 __device__ __forceinline__ unsigned sad16_acc(const uint4 &a, const uint4 &b, unsigned acc) {
@@ -159,7 +160,7 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
     const int gx = a.grid_size == 1 ? uc : (int)__umulhi((unsigned)uc, a.grid_magic);  // u / grid_size by reciprocal (exact for u < 2^16)
     const int gy = a.grid_size == 1 ? v : (int)__umulhi((unsigned)v, a.grid_magic);    // u, v >= 0: equals the float floor (elas.cpp:744-745)
     const uint32_t *cell = a.grid[SIDE] + (size_t)uf * (unsigned)(a.gw * a.gh * a.gwords) + (unsigned)((gy * a.gw + gx) * a.gwords);
-    const int o = in ? __ldg(a.owner[SIDE] + fDN + (unsigned)pix) : -1;
+    const int o = in ? owner_untag(__ldg(a.owner[SIDE] + fDN + (unsigned)pix), a.owner_gen) : -1;
     SVB_GUARD_DESC(desc_at(own, rowW + uc), SIDE);
     SVB_GUARD_ASSERT(!in || (pix >= 0 && pix < a.DN));
     const uint4 c = __ldg(desc_at(own, rowW + uc));
@@ -292,7 +293,7 @@ __device__ __forceinline__ void dense_row_body(const DenseArgs &a, uint4 *s_oth,
         const bool in = u < W;
         const int uc = in ? u : W - 1;
         const int gx = a.grid_size == 1 ? uc : (int)__umulhi((unsigned)uc, a.grid_magic);
-        const int o = in ? __ldg(owner + u) : -1;
+        const int o = in ? owner_untag(__ldg(owner + u), a.owner_gen) : -1;
         const uint4 c = __ldg(own + uc);
         // elas.cpp:714 (column range) and :731-736 (texture)
         const bool active = in && o >= 0 && u >= 2 && u < W - 2 && (int)sad16(c, k128) >= a.match_texture;
@@ -412,15 +413,16 @@ __global__ void __launch_bounds__(128, 12) k_dense(const DenseArgs a) {
 
 int launch_dense(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, const int32_t *owner1, const int32_t *owner2,
                  const PlaneRec *rec1, const PlaneRec *rec2, const uint32_t *grid1, const uint32_t *grid2, float *D1, float *D2, int nf,
-                 cudaStream_t s) {
-    return launch_dense_rows(d, p, desc1, desc2, owner1, owner2, rec1, rec2, grid1, grid2, D1, D2, nf, 0, d.H, s);
+                 cudaStream_t s, int owner_gen) {
+    return launch_dense_rows(d, p, desc1, desc2, owner1, owner2, rec1, rec2, grid1, grid2, D1, D2, nf, 0, d.H, s, owner_gen);
 }
 
 int launch_dense_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, const int32_t *owner1, const int32_t *owner2,
                       const PlaneRec *rec1, const PlaneRec *rec2, const uint32_t *grid1, const uint32_t *grid2, float *D1, float *D2, int nf,
-                      int row0, int row1, cudaStream_t s) {
+                      int row0, int row1, cudaStream_t s, int owner_gen) {
     if (nf <= 0 || row1 <= row0) return SVB_OK;
     DenseArgs a;
+    a.owner_gen = owner_gen;
     a.desc[0] = desc1;
     a.desc[1] = desc2;
     a.owner[0] = owner1;

@@ -188,7 +188,7 @@ __device__ __forceinline__ int f2u_as_int_x86(float x) {
 __global__ void __launch_bounds__(128) k_raster(const int32_t *__restrict__ support_all, const int32_t *__restrict__ tri1_all,
                                                const int32_t *__restrict__ tri2_all, const int32_t *__restrict__ ntri_all,
                                                const int32_t *__restrict__ trioff_all, int32_t *__restrict__ owner1_all,
-                                               int32_t *__restrict__ owner2_all, int W, int H, int maxS, int row0, int row1, int sub, int Dw, int Dh) {
+                                               int32_t *__restrict__ owner2_all, int W, int H, int maxS, int row0, int row1, int sub, int Dw, int Dh, int tag) {
     const int f = blockIdx.z, side = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -247,13 +247,13 @@ __global__ void __launch_bounds__(128) k_raster(const int32_t *__restrict__ supp
             if (!sub) {
                 for (int v = v_lo; v < v_hi; v++) {
                     SVB_GUARD_ASSERT(u >= 0 && u < W && v >= 0 && v < H);
-                    atomicMax(owner + (size_t)v * W + u, i);
+                    atomicMax(owner + (size_t)v * W + u, tag | i);
                 }
             } else if ((u >> 1) < Dw) {
                 for (int v = (v_lo + 1) & ~1; v < v_hi; v += 2)
                     if ((v >> 1) < Dh) {
                         SVB_GUARD_ASSERT(u >= 0 && v >= 0);
-                        atomicMax(owner + (size_t)(v >> 1) * Dw + (u >> 1), i);
+                        atomicMax(owner + (size_t)(v >> 1) * Dw + (u >> 1), tag | i);
                     }
             }
         }
@@ -303,16 +303,23 @@ int launch_grid_expand(const Dims &d, const svb_params &p, const uint32_t *grid,
 }
 
 int launch_raster(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,
-                  int32_t *owner1, int32_t *owner2, int nf, int max_tri, cudaStream_t s) {
-    return launch_raster_rows(d, support, tri1, tri2, ntri, trioff, owner1, owner2, nf, max_tri, 0, d.H, s);
+                  int32_t *owner1, int32_t *owner2, int nf, int max_tri, cudaStream_t s, int gen) {
+    return launch_raster_rows(d, support, tri1, tri2, ntri, trioff, owner1, owner2, nf, max_tri, 0, d.H, s, gen);
 }
 
 int launch_raster_rows(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,
-                       int32_t *owner1, int32_t *owner2, int nf, int max_tri, int row0, int row1, cudaStream_t s) {
+                       int32_t *owner1, int32_t *owner2, int nf, int max_tri, int row0, int row1, cudaStream_t s, int gen) {
     if (nf <= 0 || row1 <= row0) return SVB_OK;
     if (max_tri > d.maxT) max_tri = d.maxT;
     cudaError_t e = cudaSuccess;
-    if (row0 == 0 && row1 == d.H) {
+    // gen > 0: the entries carry the generation in bits 24..30 (owner_tagged / owner_untag, svb_internal.h): whatever an earlier
+    // generation left in the map is smaller than any entry of this one and reads as "no triangle", so the map is not cleared
+    if (gen > 0) {
+        if (gen > OWNER_GEN_MAX || d.maxT > OWNER_INDEX_MASK) {
+            set_error("launch_raster: generation %d / %d triangles do not fit the owner encoding", gen, d.maxT);
+            return SVB_ERR_ARG;
+        }
+    } else if (row0 == 0 && row1 == d.H) {
         e = cudaMemsetAsync(owner1, 0xFF, (size_t)nf * d.DN * sizeof(int32_t), s);
         if (e == cudaSuccess) e = cudaMemsetAsync(owner2, 0xFF, (size_t)nf * d.DN * sizeof(int32_t), s);
     } else if (d.sub) {
@@ -331,7 +338,7 @@ int launch_raster_rows(const Dims &d, const int32_t *support, const int32_t *tri
     }
     if (max_tri <= 0) return SVB_OK;
     dim3 grid((max_tri + 3) / 4, 2, nf);
-    k_raster<<<grid, 128, 0, s>>>(support, tri1, tri2, ntri, trioff, owner1, owner2, d.W, d.H, d.maxS, row0, row1, d.sub, d.Dw, d.Dh);
+    k_raster<<<grid, 128, 0, s>>>(support, tri1, tri2, ntri, trioff, owner1, owner2, d.W, d.H, d.maxS, row0, row1, d.sub, d.Dw, d.Dh, gen << OWNER_GEN_SHIFT);
     SVB_LAUNCH_CHECK();
     return SVB_OK;
 }

@@ -153,6 +153,7 @@ int lane_create(svb_context *c, Lane &L) {
         SVB_TRY(dev_alloc(&L.rec[s], C * d.maxT));
         SVB_TRY(dev_alloc(&L.grid[s], C * d.gw * d.gh * d.gwords));
         SVB_TRY(dev_alloc(&L.owner[s], C * N));
+        SVB_CUDA(cudaMemset(L.owner[s], 0xFF, C * N * sizeof(int32_t)));  // generation-tagged entries (stage_b): cleared here and when the generation wraps
         SVB_TRY(host_alloc(&L.h_tri[s], C * (d.maxT + 8) * 3));
     }
     SVB_TRY(dev_alloc(&L.dcan_raw, C * d.cw * d.ch));
@@ -468,12 +469,22 @@ int stage_b(svb_context *c, Lane &L, int nf, float *out_D1, double *out_points, 
     SVB_TRY(T.mark(ST_GRID));
     SVB_TRY(launch_grid(d, p, L.support, L.nsupport, L.grid_tmp, L.grid[0], L.grid[1], nf, max_support, L.stream));
     SVB_TRY(T.mark(ST_RASTER));
-    SVB_TRY(launch_raster(d, L.support, L.tri[0], L.tri[1], L.ntri, L.trioff, L.owner[0], L.owner[1], nf, max_tri, L.stream));
+    // Outside tap mode the owner maps are not cleared per chunk: their entries carry a generation number (svb_internal.h) that moves
+    // on with every chunk of the lane; the maps are cleared when the 7-bit number wraps (and once at creation).
+    int owner_gen = 0;
+    if (!c->tap_mode) {
+        if (++L.owner_gen > OWNER_GEN_MAX) {
+            for (int sd = 0; sd < 2; sd++) SVB_CUDA(cudaMemsetAsync(L.owner[sd], 0xFF, (size_t)C * N * sizeof(int32_t), L.stream));
+            L.owner_gen = 1;
+        }
+        owner_gen = L.owner_gen;
+    }
+    SVB_TRY(launch_raster(d, L.support, L.tri[0], L.tri[1], L.ntri, L.trioff, L.owner[0], L.owner[1], nf, max_tri, L.stream, owner_gen));
     SVB_TRY(T.mark(ST_DENSE));
     float *D1raw = L.Draw, *D2raw = L.Draw + C * N;
     float *D1 = L.Dlr, *D2 = L.Dlr + C * N;
     SVB_TRY(launch_dense(d, p, L.desc[0], L.desc[1], L.owner[0], L.owner[1], L.rec[0], L.rec[1], L.grid[0], L.grid[1], D1raw, D2raw, nf,
-                         L.stream));
+                         L.stream, owner_gen));
     SVB_TRY(T.mark(ST_LR));
     const bool both = !p.postprocess_only_left;
     const bool need_d2 = both || c->tap_mode || (out_D1 == nullptr && out_points == nullptr);

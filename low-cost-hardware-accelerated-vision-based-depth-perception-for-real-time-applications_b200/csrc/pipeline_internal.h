@@ -36,6 +36,7 @@ struct Lane {
     float *Dlr = nullptr;   // [2][chunk][N]
     float *Dtmp = nullptr;  // [2][chunk][N]
     int32_t *labels = nullptr, *sizes = nullptr;  // [2][chunk][N]
+    int owner_gen = 0;  // generation of the owner maps' entries (stage_b)
     int32_t *ccl_roots = nullptr, *ccl_counts = nullptr;  // per-tile lists of tile-local roots and their lengths (k_ccl.cu)
     uint8_t *dmap = nullptr;
     // pinned host

@@ -145,17 +145,24 @@ int launch_planes(const Dims &d, const int32_t *support, const int32_t *tri1, co
 int launch_grid(const Dims &d, const svb_params &p, const int32_t *support, const int32_t *nsupport, uint32_t *tmp, uint32_t *grid1,
                 uint32_t *grid2, int nf, int max_support, cudaStream_t s);
 int launch_grid_expand(const Dims &d, const svb_params &p, const uint32_t *grid, int32_t *grid_ref, cudaStream_t s);
+// The owner map holds, per pixel, the index of the last triangle that covers it (-1: none).  gen > 0: entries are (gen << 24 | index) and
+// the map is NOT cleared -- entries of earlier generations are smaller than any of this one (atomicMax keeps the new ones) and read as
+// "none" through owner_untag; the caller clears the map before it reuses a generation number.  gen = 0: plain indices, map cleared first.
+constexpr int OWNER_GEN_SHIFT = 24, OWNER_GEN_MAX = 127, OWNER_INDEX_MASK = 0xFFFFFF;
+#ifdef __CUDACC__
+__device__ __forceinline__ int owner_untag(int raw, int gen) { return (raw >> OWNER_GEN_SHIFT) == gen ? (raw & OWNER_INDEX_MASK) : -1; }
+#endif
 int launch_raster(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,
-                  int32_t *owner1, int32_t *owner2, int nf, int max_tri, cudaStream_t s);
+                  int32_t *owner1, int32_t *owner2, int nf, int max_tri, cudaStream_t s, int gen = 0);
 int launch_raster_rows(const Dims &d, const int32_t *support, const int32_t *tri1, const int32_t *tri2, const int32_t *ntri, const int32_t *trioff,
-                       int32_t *owner1, int32_t *owner2, int nf, int max_tri, int row0, int row1, cudaStream_t s);
+                       int32_t *owner1, int32_t *owner2, int nf, int max_tri, int row0, int row1, cudaStream_t s, int gen = 0);
 // k_dense.cu
 int launch_dense(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, const int32_t *owner1, const int32_t *owner2,
                  const PlaneRec *rec1, const PlaneRec *rec2, const uint32_t *grid1, const uint32_t *grid2, float *D1, float *D2, int nf,
-                 cudaStream_t s);
+                 cudaStream_t s, int owner_gen = 0);
 int launch_dense_rows(const Dims &d, const svb_params &p, const uint8_t *desc1, const uint8_t *desc2, const int32_t *owner1, const int32_t *owner2,
                       const PlaneRec *rec1, const PlaneRec *rec2, const uint32_t *grid1, const uint32_t *grid2, float *D1, float *D2, int nf,
-                      int row0, int row1, cudaStream_t s);
+                      int row0, int row1, cudaStream_t s, int owner_gen = 0);
 // k_post.cu
 int launch_lr_check(const Dims &d, const svb_params &p, const float *D1in, const float *D2in, float *D1out, float *D2out, int nf,
                     cudaStream_t s);

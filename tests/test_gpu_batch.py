@@ -280,3 +280,27 @@ def test_bgra_batch_input_and_device_pointers(svb, golden_meta):
         assert d1 and not pts
     finally:
         ctx.close()
+
+
+def test_owner_map_generations_wrap(svb):
+    """The owner maps are not cleared per chunk: their entries carry a 7-bit generation number (svb_internal.h).  One lane is driven
+    through more than 127 chunks, so that the number wraps and the maps are cleared in between; frames that repeat an input must
+    repeat its result exactly, before and after the wrap, and differently textured frames in between must not leak into them."""
+    W, H = 333, 127
+    kinds = 3
+    n = 140
+    L = np.zeros((n, H, W), np.uint8)
+    R = np.zeros((n, H, W), np.uint8)
+    for i in range(n):
+        svb.synth_pair(500 + (i % kinds), W, H, (i % kinds) & 1, L[i], R[i])
+    p = svb.default_params(svb.PIPELINE)
+    ctx = svb.Context(p, W, H, chunk=1)  # one lane, one frame per chunk: 140 generations
+    try:
+        ctx.batch_upload(L, R)
+        ctx.batch_run(n, svb.OUT_DISPARITY)
+        want = [ctx.process(L[k], R[k])[0] for k in range(kinds)]
+        for i in range(n):
+            assert np.array_equal(ctx.batch_disparity(i), want[i % kinds]), "frame %d" % i
+        assert (want[0] >= 0).mean() > 0.5
+    finally:
+        ctx.close()
