@@ -531,7 +531,7 @@ def main():
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int32 SAD + f32 filters + f64 reprojection", "data": "synthetic",
             "config": {"workload": WORKLOAD,
-                       "frames_per_gpu": args.batch, "frames_per_launch": args.chunk, "lanes": int(os.environ.get("SVB_LANES", "6")), "single_stream": bool(args.single_stream),
+                       "frames_per_gpu": args.batch, "frames_per_launch": args.chunk, "lanes": int(os.environ.get("SVB_LANES", "8")), "single_stream": bool(args.single_stream),
                        "l2": "inputs larger than L2 (%.0f MB of images, %.0f MB of descriptors per step)" % (2 * N * args.batch / 1e6,
                                                                                                             32 * N * args.batch / 1e6),
                        "parallelism": "frame-batch data parallel x%d, no collective" % world},

@@ -704,7 +704,7 @@ svb_context *svb_create(const svb_params *params, int width, int height, int chu
         const char *fp = getenv("SVB_FUSED_POST");
         if (fp && atoi(fp) == 0) c->fused_post = false;
         const char *e = getenv("SVB_LANES");
-        const int n = e ? atoi(e) : 6;  // measured: 6 lanes hide the latency-bound stages (lattice filters, Delaunay, vertex-sort replay) better than 4: + 1 % synthetic, + 5 % kitti_mini
+        const int n = e ? atoi(e) : 8;  // measured: 8 lanes hide the latency-bound stages (lattice filters, Delaunay, vertex-sort replay) better than 4: + 2 % synthetic, + 7 % kitti_mini
         c->n_lanes = n < 1 ? 1 : (n > MAX_LANES ? MAX_LANES : n);
         if (c->chunk == 1) c->n_lanes = 1;  // single-frame contexts never pipeline
     }

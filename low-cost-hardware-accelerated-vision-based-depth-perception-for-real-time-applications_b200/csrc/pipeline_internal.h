@@ -12,7 +12,7 @@
 
 namespace svb {
 
-constexpr int MAX_LANES = 8;  // arenas in flight; the context uses n_lanes of them (default 6, SVB_LANES overrides)
+constexpr int MAX_LANES = 8;  // arenas in flight; the context uses n_lanes of them (default 8, SVB_LANES overrides)
 
 struct Lane {
     cudaStream_t own_stream = nullptr;  // created with the lane

@@ -147,7 +147,7 @@ def test_batch_is_identical_across_stream_modes_lanes_and_vertex_order(svb, gold
             ctx.close()
 
     want = run(False, {})
-    for single, env in ((False, {}), (True, {}), (False, {"SVB_LANES": "6"}), (False, {"SVB_GPU_ORDER": "0"}), (False, {"SVB_DELAUNAY_DEVICE": "0"})):
+    for single, env in ((False, {}), (True, {}), (False, {"SVB_LANES": "3"}), (False, {"SVB_GPU_ORDER": "0"}), (False, {"SVB_DELAUNAY_DEVICE": "0"})):
         got = run(single, env)
         assert all(np.array_equal(a, b) for a, b in zip(got[0], want[0])), (single, env)
         assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got[1], want[1])), (single, env)
