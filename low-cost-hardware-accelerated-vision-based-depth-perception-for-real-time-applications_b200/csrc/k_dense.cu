@@ -254,7 +254,10 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
 //    loop serves the lane's next two bits, so the trip count is the largest candidate count of a lane, not the size of the union,
 //  * visits only the mask words that have a bit in some lane's cell (a per-cell summary of non-zero words, one REDUX per pixel).
 // Arithmetic, evaluation-order semantics and the packed key are those of dense_body.
-constexpr int DR_THREADS = 256;
+#ifndef SVB_DR_THREADS
+#define SVB_DR_THREADS 256
+#endif
+constexpr int DR_THREADS = SVB_DR_THREADS;
 
 template <int SIDE, int RADIUS, bool COUNT>
 __device__ __forceinline__ void dense_row_body(const DenseArgs &a, uint4 *s_oth, uint32_t *s_cell, uint32_t *s_nz) {

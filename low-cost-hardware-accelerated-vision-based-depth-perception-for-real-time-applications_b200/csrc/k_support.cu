@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(SM_WARPS * 32) k_support_match(const uint8_t *
 // (88 % of its hypotheses are in range) and to test every hypothesis against its lane's range.  Loop body: 2 LDS.128, 16 chained
 // VABSDIFF4.ACC, 3 min/max, 2 IMAD (FMA pipe).  Forward and backward pass are two launches of the same kernel with the images'
 // roles exchanged; the forward result waits in dcan_raw.
+#ifndef SVB_MR_UNROLL_PRAGMA
+#define SVB_MR_UNROLL_PRAGMA "unroll 2"  // groups of four steps per loop trip (1 and 4 measured: see DESIGN.md)
+#endif
 constexpr int MR_MAX_THREADS = 768;  // candidates per lattice row (one CTA); 80 registers x 768 threads fit the register file
 
 __device__ __forceinline__ unsigned imad_fma_pipe(unsigned a, unsigned b, unsigned c) {
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(MR_MAX_THREADS) k_support_match_row(const uint
     }
 #define SVB_ROW_WALK(PRED)                                 \
     {                                                      \
-        _Pragma("unroll 2") for (int g = n >> 2; g > 0; g--) { \
+        _Pragma(SVB_MR_UNROLL_PRAGMA) for (int g = n >> 2; g > 0; g--) { \
             SVB_ROW_STEP(t0, b0, 0, PRED)                  \
             SVB_ROW_STEP(t1, b1, 1, PRED)                  \
             SVB_ROW_STEP(t2, b2, 2, PRED)                  \
