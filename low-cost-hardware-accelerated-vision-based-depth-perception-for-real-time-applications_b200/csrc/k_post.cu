@@ -53,7 +53,10 @@ __global__ void __launch_bounds__(256) k_lr_check(const float *__restrict__ D1in
 // first one after it.  The map is read once (row pass, all loads independent); only words with a gap are looked at again, and only
 // the gap's two end values are loaded.  The row pass leaves the validity bits of its RESULT (one word per 32 columns of a row) in a
 // scratch array, from which the column pass builds its column words by 32 x 32 bit transposes instead of reading the map again.
-constexpr int GAP_WARPS = 8;
+#ifndef SVB_GAP_WARPS
+#define SVB_GAP_WARPS 8
+#endif
+constexpr int GAP_WARPS = SVB_GAP_WARPS;
 
 __device__ __forceinline__ float gap_fill_value(float d1, float d2) {
     if (fabsf(__fsub_rn(d1, d2)) < 3.0f) return __fdiv_rn(__fadd_rn(d1, d2), 2.0f);

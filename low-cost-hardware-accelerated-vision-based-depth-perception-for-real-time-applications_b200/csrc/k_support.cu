@@ -182,7 +182,10 @@ __global__ void __launch_bounds__(SM_WARPS * 32) k_support_match(const uint8_t *
 #ifndef SVB_MR_UNROLL_PRAGMA
 #define SVB_MR_UNROLL_PRAGMA "unroll 2"  // groups of four steps per loop trip (1 and 4 measured: see DESIGN.md)
 #endif
-constexpr int MR_MAX_THREADS = 768;  // candidates per lattice row (one CTA); 80 registers x 768 threads fit the register file
+#ifndef SVB_MR_MAX_THREADS
+#define SVB_MR_MAX_THREADS 768
+#endif
+constexpr int MR_MAX_THREADS = SVB_MR_MAX_THREADS;  // candidates per lattice row (one CTA); 80 registers x 768 threads fit the register file
 
 __device__ __forceinline__ unsigned imad_fma_pipe(unsigned a, unsigned b, unsigned c) {
     unsigned r;
