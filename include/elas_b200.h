@@ -79,7 +79,7 @@ int svb_default_params(int setting, svb_params *out);
 /* Replaces `ElasGPU elas(param)` (src/parallel_includes/elas/elas_gpu.h:26-33) plus the lazy
  * ElasGPU::memInit (elas_gpu.cu:289-306): all device arenas, pinned staging buffers, streams and
  * the host Delaunay worker pool are created once, sized for `chunk` frames of width x height in
- * flight per lane.  device < 0 picks the current device. */
+ * flight per lane (chunk = 1: one lane; chunk > 1: 8 lanes, SVB_LANES in the environment overrides; roughly 1.4 GB of device memory per lane for 32 frames of 1242x375).  device < 0 picks the current device. */
 svb_context *svb_create(const svb_params *params, int width, int height, int chunk, int device);
 void svb_destroy(svb_context *ctx);
 int svb_set_mean_mode(svb_context *ctx, int mode);
@@ -158,8 +158,8 @@ int svb_stage_reproject(svb_context *ctx, const float *D, const double *Q16, con
 
 /* ---- frame-batch pipeline (BASELINE.json configs[1]: 1242x375 x 1024 frames) ------------------
  * Frames are independent: a batch is cut into chunks that flow through
- * descriptor+support (GPU) -> Delaunay (host worker pool) -> planes..reproject (GPU), with the
- * lanes overlapping one another.  Replaces the per-frame loop imageLoop()/generatePointCloud()
+ * descriptor+support+Delaunay (GPU; the host worker pool only triangulates lists the device hands back) -> planes..reproject (GPU),
+ * with the lanes overlapping one another.  Replaces the per-frame loop imageLoop()/generatePointCloud()
  * (stereo_vision.cu:645-697,574-632). */
 int svb_set_calibration(svb_context *ctx, const double *Q16, const double *XR9, const double *XT3);
 /* copy n frames (tight W*H u8 each) into the device-resident input store */
