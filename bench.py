@@ -16,7 +16,7 @@ u8 conversion + reprojectTo3D) over the batch, through the C-ABI of include/elas
              point cloud, like generatePointCloud returns), H2D and D2H copies inside the timed region
   roofline   the kernel with the largest share of the step, its algorithmic bytes over its mean
              launch duration measured with CUDA events in the timed region, against MEASURED_PEAKS.json
-  cpu_baseline  the reference's serial ELAS (oracle/_ref, Makefile flags) + a numpy restatement of projectParallel,
+  cpu_baseline  the reference's serial ELAS (oracle/_ref, Makefile flags) + the C restatement of projectParallel (oracle/project_port.c),
              frame-parallel over the host cores, on a bounded sample of the same frames
 
 torch is used for process-group plumbing only (barrier, max over ranks); every kernel is the library's own.
@@ -147,7 +147,7 @@ class ClockSampler(threading.Thread):
 
 # ---- CPU arms -------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    """One host process: the reference's serial Elas::process (+ numpy projectParallel) on its share of frames."""
+    """One host process: the reference's serial Elas::process (+ projectParallel restated in C, oracle/project_port.c) on its share of frames."""
     frames, slanted_mask, fast = args
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -243,7 +243,7 @@ def run_reference_arm(args):
         "config": {"workload": WORKLOAD, "frames_per_step": cores * per_core, "bounded_sample": sample},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference",
                          "sample": sample + "; oracle/_ref/libelas_ref_fast.so = reference serial ELAS with the reference Makefile's "
-                                            "flags (-O2 -ffast-math), one process per core, + numpy projectParallel"},
+                                            "flags (-O2 -ffast-math), one process per core, + projectParallel restated in C (oracle/project_port.c)"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         # this arm must not touch the product: true would mean libelas_b200.so got mapped into the process that timed the reference
@@ -520,7 +520,7 @@ def main():
         fps, wall = cpu_frames_per_s(per_core, cores, first_frame=0, fast=True)
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference",
                "sample": "%d frames of the same synthetic workload (%d per core), reference serial ELAS (oracle/_ref, -O2 -ffast-math = "
-                         "reference Makefile flags) + numpy projectParallel, one process per core, %.1f s wall" % (per_core * cores, per_core, wall),
+                         "reference Makefile flags) + projectParallel restated in C, one process per core, %.1f s wall" % (per_core * cores, per_core, wall),
                # the two single-process forms the reference's own binaries take (make serial=1 / make omp=1), 8 frames each
                "serial_one_core_fps": cpu_single_process(8, omp=False),
                "openmp_one_process_fps": cpu_single_process(8, omp=True),

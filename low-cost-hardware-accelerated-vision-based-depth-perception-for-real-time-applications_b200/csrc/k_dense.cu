@@ -47,6 +47,19 @@ __device__ __forceinline__ unsigned sad16_acc(const uint4 &a, const uint4 &b, un
     return acc;
 }
 
+__device__ __forceinline__ unsigned imad_fma_pipe(unsigned a, unsigned b, unsigned c) {
+    unsigned r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// 16 bytes of shared memory at a 32-bit shared-window address
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+
 // base + idx as one IMAD.WIDE (FMA pipe) instead of a 4-instruction 64-bit LEA sequence on the ALU pipe
 // guard build: a descriptor load must stay inside the arena (frames + zero-filled guard bands)
 #define SVB_GUARD_DESC(ptr, side) \
@@ -257,6 +270,9 @@ __device__ __forceinline__ void dense_body(const DenseArgs &a) {
 #ifndef SVB_DR_THREADS
 #define SVB_DR_THREADS 256
 #endif
+#ifndef SVB_DR_LEAN
+#define SVB_DR_LEAN 0  // candidate walk on bit positions inside a word (see dense_row_body)
+#endif
 constexpr int DR_THREADS = SVB_DR_THREADS;
 
 template <int SIDE, int RADIUS, bool COUNT>
@@ -292,6 +308,10 @@ __device__ __forceinline__ void dense_row_body(const DenseArgs &a, uint4 *s_oth,
     const float fv = (float)v;
     unsigned n_hyp = 0u;
     const int lane = threadIdx.x & 31;
+#if SVB_DR_LEAN
+    const unsigned s_oth32 = (unsigned)__cvta_generic_to_shared(s_oth);
+    const unsigned bias = a.bias * blockDim.z;  // x 1: a register instead of a constant-bank load in front of every trip of the candidate loop
+#endif
     for (int u = threadIdx.x; u - lane < W; u += DR_THREADS) {  // whole warps: the loops below vote
         const bool in = u < W;
         const int uc = in ? u : W - 1;
@@ -315,6 +335,9 @@ __device__ __forceinline__ void dense_row_body(const DenseArgs &a, uint4 *s_oth,
         const int dlo = SIDE ? 2 - u : u - (W - 3);
         const int dhi = SIDE ? (W - 3) - u : u - 2;
         const uint4 *po = s_oth + pad + uc;  // hypothesis d reads po[-d] (left) / po[+d] (right)
+#if SVB_DR_LEAN
+        const unsigned po32 = s_oth32 + (unsigned)((pad + uc) << 4);
+#endif
 
         // (i) grid candidates outside the band (elas.cpp:759-767 / 778-786); see grid_phase for the two mask forms
         unsigned key = 0xFFFFFFFFu;
@@ -334,6 +357,32 @@ __device__ __forceinline__ void dense_row_body(const DenseArgs &a, uint4 *s_oth,
                 mine &= ~((w == wband ? band_lo : 0u) | (w == wband + 1 ? band_hi : 0u));
             }
             if (COUNT) n_hyp += __popc(mine);
+#if SVB_DR_LEAN
+            // Inside a word only the bit position p = d - 32 w is carried: the address is the word's base column -+ p and the key
+            // (cost << 13) + p, one IMAD each (FMA pipe); the word's minimum gets its 32 w once (adding a constant below bit 13 to all
+            // keys of a word keeps their order, d < 8192).  A lane that has no candidate left gets p = -1 from bfind: the column next
+            // to the word's first one, inside the staged row's margins; its result is discarded by the predicate.  27 instead of 37
+            // instructions per trip.
+            const unsigned pw = po32 + (unsigned)(SIDE ? (w << 9) : -(w << 9));  // byte address of column uc -+ 32 w in shared memory
+            unsigned kw = 0xFFFFFFFFu;
+            while (__any_sync(0xFFFFFFFFu, mine != 0u)) {
+                const uint32_t bit0 = mine & (0u - mine);
+                mine ^= bit0;
+                const uint32_t bit1 = mine & (0u - mine);
+                mine ^= bit1;
+                unsigned p0, p1;
+                asm("bfind.u32 %0, %1;" : "=r"(p0) : "r"(bit0));
+                asm("bfind.u32 %0, %1;" : "=r"(p1) : "r"(bit1));
+                SVB_GUARD_ASSERT((w << 5) + (int)p0 >= -1 && (w << 5) + (int)p0 <= pad && (w << 5) + (int)p1 >= -1 && (w << 5) + (int)p1 <= pad);
+                const uint4 o0 = lds128(imad_fma_pipe(p0, SIDE ? 16u : 0xFFFFFFF0u, pw));
+                const uint4 o1 = lds128(imad_fma_pipe(p1, SIDE ? 16u : 0xFFFFFFF0u, pw));
+                const unsigned cand0 = imad_fma_pipe(sad16_acc(c, o0, bias), 0x2000u, p0);
+                const unsigned cand1 = imad_fma_pipe(sad16_acc(c, o1, bias), 0x2000u, p1);
+                if (bit0) kw = min(kw, cand0);
+                if (bit1) kw = min(kw, cand1);
+            }
+            if (kw != 0xFFFFFFFFu) key = min(key, kw + (unsigned)(w << 5));
+#else
             while (__any_sync(0xFFFFFFFFu, mine != 0u)) {
                 // the lane's next two candidates: both loads are in flight before either SAD chain starts (a lane that has none left
                 // re-reads the word's first column and discards the result)
@@ -351,6 +400,7 @@ __device__ __forceinline__ void dense_row_body(const DenseArgs &a, uint4 *s_oth,
                 key = min(key, bit0 ? cand0 : 0xFFFFFFFFu);
                 key = min(key, bit1 ? cand1 : 0xFFFFFFFFu);
             }
+#endif
         }
         // (ii) the plane band with the prior (elas.cpp:768-774 / 787-793)
         const int lo2 = max(dmin, dlo), hi2 = min(dmax, dhi);

@@ -178,9 +178,7 @@ __global__ void __launch_bounds__(PF_THREADS, TH == 32 ? 4 : 2) k_post_fused(con
     float *Dout = a.Dout ? a.Dout + img : nullptr;
     uint8_t *dmap = a.dmap ? a.dmap + img : nullptr;
     double *points = a.points ? a.points + img * 3 : nullptr;
-    double colterm[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) colterm[k] = __dmul_rn(a.cal.Q[4 * k + 0], (double)u);
+    const double fu = (double)u;
     const bool col_in = u >= 3 && u < W - 3;
     for (int rg = half; rg < TH / 4; rg += 2) {
         const int r0 = 8 + 4 * rg, v0 = y0 + 4 * rg;
@@ -214,7 +212,7 @@ __global__ void __launch_bounds__(PF_THREADS, TH == 32 ? 4 : 2) k_post_fused(con
                     RpPixel px;
                     const double fy = (double)v;
 #pragma unroll
-                    for (int t = 0; t < 4; t++) px.base[t] = __dadd_rn(colterm[t], __dmul_rn(a.cal.Q[4 * t + 1], fy));
+                    for (int t = 0; t < 4; t++) px.base[t] = __fma_rn(fu, a.cal.Q[4 * t + 0], __dmul_rn(fy, a.cal.Q[4 * t + 1]));  // = rp_pixel_xy
                     double out[3];
                     // float_disp: the filtered disparity itself (invalid = negative -> 0, which projects to w = 0 like the u8 path's 0)
                     rp_point_d(a.cal, px, a.float_disp ? (double)fmaxf(res[k], 0.f) : (double)q, out);

@@ -259,3 +259,31 @@ class RefProject:
         if rc != 0:
             raise RuntimeError("ref_project_parallel: cudaError %d" % rc)
         return pts
+
+
+_PORT = None
+
+
+def port_project(d, H, W, Q, XR, XT):
+    """TEST INFRASTRUCTURE ONLY: oracle/project_port.c -- the CPU restatement of `projectParallel` (stereo_vision.cu:188-212) with
+    the fused multiply-adds of the reference's own nvcc build (see the header of that file).  d: H*W float64 (the u8 map's values,
+    or the float disparity for SVB_OUT_POINTS_FLOATDISP) -> (H*W, 3) float64.  Built by oracle/Makefile (gcc, no reference source
+    needed); compiled on the spot when the library is missing."""
+    global _PORT
+    if _PORT is None:
+        path = os.path.join(HERE, "_port", "libproject_port.so")
+        if not os.path.exists(path):
+            import subprocess
+
+            subprocess.run(["make", "-C", HERE, "-s"], check=True)
+        _PORT = C.CDLL(path)
+        _PORT.port_project_parallel.restype = None
+    d = np.ascontiguousarray(d, np.float64).reshape(-1)
+    assert d.size == H * W
+    Q = np.ascontiguousarray(Q, np.float64).reshape(16)
+    XR = np.ascontiguousarray(XR, np.float64).reshape(9)
+    XT = np.ascontiguousarray(XT, np.float64).reshape(3)
+    pts = np.empty((H * W, 3), np.float64)
+    _PORT.port_project_parallel(_p(d, C.c_double), _p(pts, C.c_double), C.c_int(H), C.c_int(W), _p(XT, C.c_double), _p(XR, C.c_double),
+                                _p(Q, C.c_double))
+    return pts

@@ -96,29 +96,34 @@ def isolated_parity(ctx, ref, p, t):
 
 
 def reproject_oracle(D, Q, XR, XT):
-    """CPU restatement of generateDisparityMap's tail + projectParallel (stereo_vision.cu:324,188-212), float64."""
+    """CPU restatement of generateDisparityMap's tail + projectParallel (stereo_vision.cu:324,188-212), float64: the u8 conversion in
+    numpy, the projection by oracle/project_port.c, which fuses the multiply-adds the reference's own nvcc build fuses (pinned bit for
+    bit to the reference kernel on the GPU box, test_reproject_against_the_reference_kernel)."""
+    from oracle.ref import port_project
+
     H, W = D.shape
     d8 = np.clip(np.rint(D.astype(np.float32) * np.float32(4.0)), 0, 255).astype(np.uint8)
-    x = np.tile(np.arange(W, dtype=np.float64), H)
-    y = np.repeat(np.arange(H, dtype=np.float64), W)
-    d = d8.reshape(-1).astype(np.float64)
-    Q = np.asarray(Q, np.float64)
-    pos = [Q[j, 0] * x + Q[j, 1] * y + Q[j, 2] * d + Q[j, 3] for j in range(4)]
-    with np.errstate(divide="ignore", invalid="ignore"):
-        X, Y, Z = pos[0] / pos[3], pos[1] / pos[3], pos[2] / pos[3]
-        XR = np.asarray(XR, np.float64).reshape(3, 3)
-        XT = np.asarray(XT, np.float64).reshape(3)
-        pts = np.stack([XR[j, 0] * X + XR[j, 1] * Y + XR[j, 2] * Z + XT[j] for j in range(3)], 1)
-    return d8, pts
+    return d8, port_project(d8.astype(np.float64), H, W, Q, XR, XT)
 
 
 def reproject_float_oracle(D, Q, XR, XT):
-    """SVB_OUT_POINTS_FLOATDISP: the formula of projectParallel (stereo_vision.cu:188-212) with the filtered float disparity itself
-    (invalid pixels as 0) in place of the u8 value -- new relative to the reference, so numpy is the oracle."""
+    """SVB_OUT_POINTS_FLOATDISP: projectParallel's arithmetic (stereo_vision.cu:188-212, as above) on the filtered float disparity itself
+    (invalid pixels as 0) in place of the u8 value -- new relative to the reference, so the port is the oracle."""
+    from oracle.ref import port_project
+
     H, W = D.shape
+    d = np.maximum(D.astype(np.float32), np.float32(0)).astype(np.float64)
+    return port_project(d, H, W, Q, XR, XT)
+
+
+def reproject_numpy(d, Q, XR, XT):
+    """projectParallel's formula as written in the source (stereo_vision.cu:188-212), every product and sum rounded on its own: what
+    the kernel would compute WITHOUT nvcc's contraction.  Only a cross-check of the port (they agree to a few ulps of the larger
+    terms); d: (H, W) values that enter Q."""
+    H, W = d.shape
     x = np.tile(np.arange(W, dtype=np.float64), H)
     y = np.repeat(np.arange(H, dtype=np.float64), W)
-    d = np.maximum(D.astype(np.float32), np.float32(0)).reshape(-1).astype(np.float64)
+    d = np.asarray(d, np.float64).reshape(-1)
     Q = np.asarray(Q, np.float64)
     pos = [Q[j, 0] * x + Q[j, 1] * y + Q[j, 2] * d + Q[j, 3] for j in range(4)]
     with np.errstate(divide="ignore", invalid="ignore"):

@@ -304,9 +304,10 @@ def test_reproject_parity(svb, golden, golden_meta):
 def test_reproject_against_the_reference_kernel(svb, golden, golden_meta, kitti_gray):
     """Row 19 pinned to the reference ITSELF: `projectParallel` (stereo_vision.cu:188-212), cut out of the reference's driver and
     compiled by oracle/build_ref.sh (oracle/_ref/libproject_ref.so, reference Makefile flags = FMA contraction on), run on this
-    GPU.  Checked: (1) the product's fused u8 + reprojection kernel against it -- identical inf / NaN pattern, <= 1e-4 relative
-    (north_star; the two differ only by the reference's contracted multiply-adds, ~1e-13 near the principal point);
-    (2) the numpy restatement tests/parity.py::reproject_oracle, which the other tests use, against it as well."""
+    GPU.  Checked, BIT FOR BIT (NaNs at the same places): (1) the product's u8 + reprojection kernel, stand-alone and as the last
+    phase of the fused tail kernel, which spell out the reference build's fused multiply-adds; (2) the CPU restatement
+    oracle/project_port.c behind tests/parity.py::reproject_oracle, which the other tests use.  The formula without contraction
+    (parity.reproject_numpy) is reported next to them: it differs by rounding only (<= 1e-4 relative, north_star's bar)."""
     from oracle.ref import RefProject
 
     rp = RefProject()
@@ -314,27 +315,55 @@ def test_reproject_against_the_reference_kernel(svb, golden, golden_meta, kitti_
     Q = np.array(golden_meta["Q"])
     Qg = Q.copy()
     Qg[3, 0], Qg[3, 1], Qg[3, 3] = 1e-4, -3e-4, 0.37  # a general Q: w depends on x and y too
+    Qn = Q.copy()
+    Qn[3, 2], Qn[0, 1], Qn[1, 0], Qn[2, 2] = -Q[3, 2], 0.013, -0.021, 0.5  # negative w, every entry of the upper rows in play
+    XR, XT = np.array(golden_meta["XR"]), np.array(golden_meta["XT"])
     cases = [(golden["pipeline_0_D1"], Q, np.eye(3), np.zeros(3)),
-             (golden["pipeline_7_D1"], Q, np.array(golden_meta["XR"]), np.array(golden_meta["XT"])),
-             (golden["robotics_0_D1"], Q, np.array(golden_meta["XR"]), np.array(golden_meta["XT"])),  # invalid pixels: d8 = 0 -> w = 0
-             (golden["robotics_7_D1"], Qg, np.array(golden_meta["XR"]), np.array(golden_meta["XT"]))]
+             (golden["pipeline_7_D1"], Q, XR, XT),
+             (golden["robotics_0_D1"], Q, XR, XT),  # invalid pixels: d8 = 0 -> w = 0
+             (golden["robotics_7_D1"], Qg, XR, XT),
+             (golden["pipeline_7_D1"], Qn, XR.T.copy(), -XT)]
     H, W = cases[0][0].shape
     ctx = svb.Context(svb.default_params(svb.PIPELINE), W, H)
+
+    def same_bits(got, want, name):
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got), nan), name
+        neq = (got.view(np.uint64) != want.view(np.uint64)) & ~nan
+        assert not neq.any(), (name, int(neq.sum()), got[neq][:4], want[neq][:4])
+
     try:
         worst = 0.0
-        for D, q, XR, XT in cases:
-            dm, pts = ctx.reproject(D, q, XR, XT)
-            dm_np, pts_np = parity.reproject_oracle(D, q, XR, XT)
-            assert np.array_equal(dm, dm_np)
-            want = rp.project(dm, q, XR, XT)  # the reference kernel on the product's u8 map (= cv convertTo of the float map)
-            for got, name in ((pts, "product"), (pts_np, "numpy restatement")):
-                assert np.array_equal(np.isnan(got), np.isnan(want)), name
-                assert np.array_equal(np.isinf(got), np.isinf(want)) and np.array_equal(np.signbit(got[np.isinf(got)]), np.signbit(want[np.isinf(want)])), name
-                fin = np.isfinite(want)
-                rel = np.abs(got[fin] - want[fin]) / np.maximum(np.abs(want[fin]), 1e-300)
-                assert rel.max() <= POINT_RTOL, (name, rel.max())
-                worst = max(worst, float(rel.max()))
-        print("worst relative difference to the reference kernel: %.3g" % worst)  # contraction differences only (~1e-13)
+        for D, q, xr, xt in cases:
+            dm, pts = ctx.reproject(D, q, xr, xt)
+            dm_o, pts_o = parity.reproject_oracle(D, q, xr, xt)
+            assert np.array_equal(dm, dm_o)
+            want = rp.project(dm, q, xr, xt)  # the reference kernel on the product's u8 map (= cv convertTo of the float map)
+            same_bits(pts, want, "product (k_reproject)")
+            same_bits(pts_o, want, "oracle/project_port.c")
+            same_bits(svb.reproject_u8(dm, q, xr, xt), want, "product (k_reproject_u8)")
+            plain = parity.reproject_numpy(dm.astype(np.float64), q, xr, xt)
+            assert np.array_equal(np.isnan(plain), np.isnan(want)) and np.array_equal(np.isinf(plain), np.isinf(want))
+            fin = np.isfinite(want)
+            rel = np.abs(plain[fin] - want[fin]) / np.maximum(np.abs(want[fin]), 1e-300)
+            assert rel.max() <= POINT_RTOL
+            worst = max(worst, float(rel.max()))
+        print("uncontracted formula against the reference kernel, worst relative difference: %.3g" % worst)
+    finally:
+        ctx.close()
+    # the fused tail kernel's projection (the batch pipeline's path) on real frames, against the reference kernel run on the u8
+    # map of the same disparity
+    L = np.stack([kitti_gray["L0"], kitti_gray["L7"]])
+    R = np.stack([kitti_gray["R0"], kitti_gray["R7"]])
+    H, W = L.shape[1:]
+    ctx = svb.Context(svb.default_params(svb.PIPELINE), W, H, chunk=2)
+    try:
+        ctx.set_calibration(Qg, XR, XT)
+        ctx.batch_upload(L, R)
+        ctx.batch_run(2, svb.OUT_DISPARITY | svb.OUT_POINTS)
+        for i in range(2):
+            dm, _ = parity.reproject_oracle(ctx.batch_disparity(i), Qg, XR, XT)
+            same_bits(ctx.batch_points(i), rp.project(dm, Qg, XR, XT), "product (k_post_fused), frame %d" % i)
     finally:
         ctx.close()
 

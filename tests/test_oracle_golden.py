@@ -113,3 +113,39 @@ def test_reproject_restatement_known_point(golden_meta):
     XR, XT = np.array(golden_meta["XR"]), np.array(golden_meta["XT"])
     _, pts2 = parity.reproject_oracle(D, Q, XR, XT)
     assert np.allclose(pts2[0], XR.reshape(3, 3) @ pts[0] + XT.reshape(3), rtol=1e-13)
+
+
+def test_project_port_against_uncontracted_formula(golden, golden_meta):
+    """oracle/project_port.c (projectParallel with the reference build's fused multiply-adds) against the formula as written in the
+    source, every operation rounded on its own (numpy): identical inf / NaN pattern, differences of rounding size only; and the
+    port's fma is a true single-rounding one (a product whose low half decides the result)."""
+    from oracle.ref import port_project
+
+    Q = np.array(golden_meta["Q"])
+    Qg = Q.copy()
+    Qg[3, 0], Qg[3, 1], Qg[3, 3] = 1e-4, -3e-4, 0.37
+    XR, XT = np.array(golden_meta["XR"]), np.array(golden_meta["XT"])
+    for D, q in ((golden["pipeline_0_D1"], Q), (golden["robotics_7_D1"], Qg)):
+        d8, got = parity.reproject_oracle(D, q, XR, XT)
+        want = parity.reproject_numpy(d8.astype(np.float64), q, XR, XT)
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want))
+        fin = np.isfinite(want)
+        # scale of the terms that enter the sums: cancellation near the principal point makes the RELATIVE difference of a
+        # coordinate large-ish (1e-13), the difference against the size of the summands is a few ulps
+        scale = np.abs(want[fin]).max()
+        assert np.abs(got[fin] - want[fin]).max() <= 64 * np.finfo(np.float64).eps * scale
+        rel = np.abs(got[fin] - want[fin]) / np.maximum(np.abs(want[fin]), 1e-300)
+        assert rel.max() <= 1e-9
+    # single rounding: a = 1 + 2^-30, b = 1 - 2^-30, a * b = 1 - 2^-60 exactly: fma(a, b, -1) = -2^-60 where two roundings give 0.
+    # point[0] = fma(XR02, Z, fma(XR00, X, XR01 * Y)) + XT0 with XR00 = a, X = b, XR01 = 1, Y = -1
+    a, b = 1.0 + 2.0**-30, 1.0 - 2.0**-30
+    Qs = np.zeros((4, 4))
+    Qs[0, 3], Qs[1, 3], Qs[3, 3] = b, -1.0, 1.0
+    XRs = np.array([[a, 1.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+    pts = port_project(np.zeros((1, 1)), 1, 1, Qs, XRs, np.zeros(3))
+    assert pts[0, 0] == -(2.0**-60) and a * b - 1.0 == 0.0
+    # pos[0] = fma(d, Q02, fma(x, Q00, y * Q01)) + Q03 with d = a, Q02 = b, y * Q01 = -1 (y = 1)
+    Qs = np.zeros((4, 4))
+    Qs[0, 2], Qs[0, 1], Qs[3, 3] = b, -1.0, 1.0
+    pts = port_project(np.array([[0.0], [a]]), 2, 1, Qs, np.eye(3), np.zeros(3))
+    assert pts[1, 0] == -(2.0**-60)
