@@ -6,7 +6,7 @@
 //   - recursion with ghost ("bounding") triangles, 2- and 3-vertex base cases                (triangle.cpp:5670-5815)
 //   - hull merge: strict ccw > 0 for the lower tangent, strict incircle > 0 for edge
 //     deletion and for choosing the right candidate, horizontal-cut handle rotation          (:5362-5651)
-// Every predicate is evaluated exactly in integers: |coordinates| < 2^13 keeps orient2d below 2^28 and incircle below 2^59.
+// Every predicate is evaluated exactly in integers: x in [-8192, 16383], y in [0, 8191] keep orient2d below 2^29 and incircle below 2^60.
 //
 // Records.  Record r occupies R[8r .. 8r+7] = {nbr0, nbr1, nbr2, *, vtx0, vtx1, vtx2, *}; a handle is (8r + orientation), i.e. the
 // index of its own neighbour slot, and its apex sits four elements further.  RT = int32_t on the host, uint16_t in the device's shared
@@ -102,11 +102,11 @@ struct MeshT {
         return t << 3;
     }
 
-    // exact orientation: > 0 iff a, b, c are counter-clockwise.  |coordinate differences| < 2^14: 32-bit exact.
+    // exact orientation: > 0 iff a, b, c are counter-clockwise.  |x differences| < 2^15, |y differences| < 2^13: 32-bit exact.
     SVB_HD static int32_t ccw(Pt a, Pt b, Pt c) { return (a.x - c.x) * (b.y - c.y) - (a.y - c.y) * (b.x - c.x); }
     SVB_HD int32_t ccw(int a, int b, int c) const { return ccw(P[a], P[b], P[c]); }
     // exact in-circle: > 0 iff d lies inside the circle through a, b, c (a, b, c counter-clockwise).
-    // lifts and 2x2 minors stay below 2^29 (32-bit), their products below 2^58 (64-bit).
+    // lifts stay below 2^31 and 2x2 minors below 2^29 (32-bit), their products below 2^60 (64-bit).
     SVB_HD static int64_t incircle(Pt a, Pt b, Pt c, Pt d) {
         const int32_t adx = a.x - d.x, ady = a.y - d.y;
         const int32_t bdx = b.x - d.x, bdy = b.y - d.y;
@@ -119,7 +119,7 @@ struct MeshT {
     }
     SVB_HD int64_t incircle(int a, int b, int c, int d) const { return incircle(P[a], P[b], P[c], P[d]); }
     // The same determinant for one circle (a, b, c) and many query points: translated to a, expanded along the query's
-    // row; the three cofactors are computed once.  test(d) == incircle(a, b, c, d) exactly (|cofactors| < 2^44, terms < 2^59).
+    // row; the three cofactors are computed once.  test(d) == incircle(a, b, c, d) exactly (|cofactors| < 2^45, terms < 2^58).
     struct Circle {
         Pt a;
         int64_t bx, by, cx, cy, k0, k1, k2;

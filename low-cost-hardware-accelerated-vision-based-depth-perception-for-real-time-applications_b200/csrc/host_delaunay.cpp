@@ -14,7 +14,8 @@
 //     deletion and for choosing the right candidate, horizontal-cut handle rotation          (:5362-5651)
 //   - output = live non-ghost triangle records in creation order, corners (org, dest, apex)  (:7449-7500)
 // Unlike the reference (float coordinates + adaptive-precision floating point predicates) every predicate here
-// is evaluated exactly in 64-bit integers: |coordinates| < 2^13 keeps orient2d below 2^28 and incircle below 2^56.
+// is evaluated exactly in integers: x in [-8192, 16383] and y in [0, 8191] (what frames of up to 8192 x 8192 pixels and disparities up
+// to 4095 produce; the stage entry points reject anything else) keep orient2d below 2^29 (32 bits) and incircle below 2^61 (64 bits).
 // Triangle records are 32-byte rows {3 neighbour handles, 3 vertices} in one flat arena (no pointer pool, no per-call
 // malloc); a handle is one int (8 * record + orientation).
 //

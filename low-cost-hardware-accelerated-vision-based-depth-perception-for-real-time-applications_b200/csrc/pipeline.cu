@@ -971,8 +971,23 @@ int svb_stage_support(svb_context *c, const uint8_t *desc1, const uint8_t *desc2
     return SVB_OK;
 }
 
+// The integer predicates of the Delaunay stage (delaunay_mesh.h) are exact for x in [-8192, 16383] and y in [0, 8191] -- every list a
+// frame of up to 8192 x 8192 pixels with disparities up to 4095 can produce, corner points (u + d) included.  Lists handed to the stage
+// entry points directly are held to the same range instead of overflowing silently.
+static bool support_coordinates_in_range(const int32_t *support, int n, int right_image) {
+    for (int i = 0; i < n; i++) {
+        const long long x = right_image ? (long long)support[3 * i] - support[3 * i + 2] : support[3 * i], y = support[3 * i + 1];
+        if (x < -8192 || x > 16383 || y < 0 || y > 8191) {
+            set_error("support point %d: (%lld, %lld) outside the Delaunay stage's coordinate range (x -8192 .. 16383, y 0 .. 8191)", i, x, y);
+            return false;
+        }
+    }
+    return true;
+}
+
 int svb_stage_delaunay(const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out) {
     if (!support || !tri || n < 0 || cap < 0) return SVB_ERR_ARG;
+    if (!support_coordinates_in_range(support, n, right_image)) return SVB_ERR_ARG;
     DelaunayScratch scratch;
     if (const char *pt = getenv("SVB_DELAUNAY_PAR")) scratch.par_threads = atoi(pt);  // tests: subtrees of a large list on threads of their own
     const int m = delaunay_support(support, n, right_image, tri, cap, scratch);
@@ -983,6 +998,7 @@ int svb_stage_delaunay(const int32_t *support, int n, int right_image, int32_t *
 // The host half of the pipeline's Delaunay stage on its own (no GPU needed): `order` is what k_order.cu would deliver.
 int svb_stage_delaunay_ordered(const int32_t *support, int n, int right_image, const int32_t *order, int32_t *tri, int cap, int *n_tri_out) {
     if (!support || !order || !tri || n < 0 || cap < 0) return SVB_ERR_ARG;
+    if (!support_coordinates_in_range(support, n, right_image)) return SVB_ERR_ARG;
     DelaunayScratch scratch;
     const int m = delaunay_support_ordered(support, n, right_image ? 1 : 0, order, n, tri, cap, scratch);
     if (m < 0) {
@@ -998,6 +1014,7 @@ int svb_stage_delaunay_ordered(const int32_t *support, int n, int right_image, c
 int svb_stage_delaunay_levels(const int32_t *support, int n, int right_image, const int32_t *order, int host_levels, int32_t *tri, int cap,
                               int *n_tri_out) {
     if (!support || !order || !tri || n < 0 || cap < 0) return SVB_ERR_ARG;
+    if (!support_coordinates_in_range(support, n, right_image)) return SVB_ERR_ARG;
     DelaunayScratch scratch;
     const int m = delaunay_support_levels(support, n, right_image ? 1 : 0, order, host_levels, tri, cap, scratch);
     if (m < 0) {
@@ -1015,6 +1032,7 @@ int svb_stage_delaunay_pipeline(svb_context *c, const int32_t *support, int n, i
                                 int *used_device_order) {
     STAGE_PROLOG();
     if (!support || !tri || n < 0 || cap < 0 || n > d.maxS) return SVB_ERR_ARG;
+    if (!support_coordinates_in_range(support, n, right_image)) return SVB_ERR_ARG;
     L.h_nsupport[0] = n;
     memcpy(L.h_support, support, (size_t)n * 12);
     SVB_CUDA(cudaMemcpyAsync(L.nsupport, L.h_nsupport, 4, cudaMemcpyHostToDevice, L.stream));

@@ -180,6 +180,30 @@ def test_host_delaunay_degenerate_inputs(svb, ref):
         assert np.array_equal(svb.delaunay(s2, side), ref.delaunay(s2, side))
 
 
+def test_host_delaunay_coordinate_range(svb, ref):
+    """The stage entry points hold a list to the range the integer predicates are exact for (x -8192 .. 16383, y 0 .. 8191: what
+    frames of up to 8192 x 8192 pixels with disparities up to 4095 produce); inside it -- far outside the radix sort's fast path,
+    negative x in the right image, corner points beyond the frame -- the lists still equal the reference's."""
+    rng = np.random.default_rng(23)
+    # an 8192 x 8192 frame's extremes: right-image x down to -4095, corner points up to 8191 + 4095
+    u = rng.integers(0, 8192, 400)
+    v = rng.integers(0, 8192, 400)
+    d = rng.integers(0, 4096, 400)
+    s = np.unique(np.stack([u, v, d], 1).astype(np.int32), axis=0)
+    s = s[np.unique(s[:, :2], axis=0, return_index=True)[1]]  # one point per (u, v), as the lattice gives
+    s = np.concatenate([s, np.array([(8191 + 4095, 0, 4095), (8191 + 4000, 8191, 4000)], np.int32)])
+    for side in (0, 1):
+        assert np.array_equal(svb.delaunay(s, side), ref.delaunay(s, side))
+    for bad in ((16384, 10, 0), (10, 8192, 0), (10, -1, 0), (0, 10, 8193), (-8193, 10, 0)):
+        pts = np.concatenate([s[:10], np.array([bad], np.int32)])
+        side = 1 if bad[2] else 0
+        with pytest.raises(svb.SvbError) as e:
+            svb.delaunay(pts, side)
+        assert "coordinate range" in str(e.value)
+        with pytest.raises(svb.SvbError):
+            svb.delaunay_ordered(pts, side, np.arange(len(pts), dtype=np.int32))
+
+
 def test_synth_pair_is_deterministic_and_has_known_disparity(svb):
     L1, R1 = svb.synth_pair(3, 320, 120)
     L2, R2 = svb.synth_pair(3, 320, 120)
