@@ -99,7 +99,7 @@ def test_sv_py_style_client(tmp_path, golden, kitti_gray):
 SV_CLASS_CLIENT = r'''
 import sys
 import numpy as np
-root, yaml_path, npz_path, out_path = sys.argv[1:5]
+root, yaml_path, npz_path, out_path, lib_path = sys.argv[1:6]
 sys.path.insert(0, root)
 import __graft_entry__ as g
 g.load_package()
@@ -107,7 +107,7 @@ from elas_b200.sv import stereo_vision             # the reference's `from stere
 z = np.load(npz_path)
 H, W = z["L0"].shape
 bgr = lambda g: np.ascontiguousarray(np.stack([g, g, g], -1))   # what cv2.imread hands the reference's callers
-s = stereo_vision(width=W, height=H, objectTracking=False, graphics=False, display=False, CAMERA_CALIBRATION_YAML=yaml_path)
+s = stereo_vision(so_lib_path=lib_path, width=W, height=H, objectTracking=False, graphics=False, display=False, CAMERA_CALIBRATION_YAML=yaml_path)
 pts = np.array(s.generatePointCloud(bgr(z["L0"]), bgr(z["R0"])))
 pts7 = np.array(s.generatePointCloud(bgr(z["L7"]), bgr(z["R7"])))
 col = np.array(s.getColor())
@@ -127,8 +127,8 @@ def test_stereo_vision_class(tmp_path, golden, kitti_gray):
     out_path = tmp_path / "out.npz"
     script = tmp_path / "client.py"
     script.write_text(SV_CLASS_CLIENT)
-    r = subprocess.run([sys.executable, str(script), ROOT, str(yaml_path), os.path.join(GOLDEN, "kitti_gray.npz"), str(out_path)], capture_output=True,
-                       text=True, timeout=600)
+    r = subprocess.run([sys.executable, str(script), ROOT, str(yaml_path), os.path.join(GOLDEN, "kitti_gray.npz"), str(out_path), LIB],
+                       capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "client done" in r.stdout and "not reached" not in r.stdout and "Program exitted successfully!" in r.stdout
     z = np.load(out_path)
