@@ -121,7 +121,10 @@ int svb_stage_descriptor(svb_context *ctx, const uint8_t *I, int stride, uint8_t
  * support is cap x {u,v,d}; returns the number of support points via *n_out. */
 int svb_stage_support(svb_context *ctx, const uint8_t *desc1, const uint8_t *desc2, int16_t *dcan_raw, int16_t *dcan,
                       int32_t *support, int cap, int *n_out);
-/* Elas::computeDelaunayTriangulation (elas.cpp:442-501) -- the host stage on its own */
+/* Elas::computeDelaunayTriangulation (elas.cpp:442-501) -- the host stage on its own.  All four Delaunay entry points return
+ * SVB_ERR_ARG for a point whose x (u, or u - d for the right image) lies outside [-8192, 16383] or whose v lies outside [0, 8191]:
+ * the range the stage's integer predicates are exact for, and more than any supported frame (<= 8192 x 8192, disp_max <= 4095)
+ * produces. */
 int svb_stage_delaunay(const int32_t *support, int n, int right_image, int32_t *tri, int cap, int *n_tri_out);
 /* Elas::computeDisparityPlanes (elas.cpp:503-575): planes = m x {t1a,t1b,t1c,t2a,t2b,t2c} */
 /* The host half of the pipeline's stage: `order` = the n support indices in the order the divide-and-conquer meets them
