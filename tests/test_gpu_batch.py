@@ -211,7 +211,7 @@ def test_fused_post_chain_equals_stage_by_stage(svb, golden_meta, monkeypatch, s
 
 def test_float_disparity_point_cloud(svb, golden_meta, monkeypatch):
     """SVB_OUT_POINTS_FLOATDISP: the float disparity enters Q without the 4x u8 quantisation that clips at 63.75 px.
-    Fused and stage-by-stage kernels against the numpy formula; the u8 drop-in path is unchanged next to it."""
+    Fused and stage-by-stage kernels against the CPU restatement; the u8 drop-in path is unchanged next to it."""
     W, H, n = 640, 240, 3
     L, R = make_batch(svb, n, W, H)
     Q, XR, XT = np.array(golden_meta["Q"]), np.array(golden_meta["XR"]), np.array(golden_meta["XT"])

@@ -5,7 +5,7 @@
  * generateDisparityMap() (C++): `Elas::parameters param(Elas::MIDDLEBURY); param.postprocess_only_left = true;
    param.filter_adaptive_mean = true; ElasGPU elas(param); elas.process(...)` (stereo_vision.cu:315-321), compiled here
    with g++ against include/elas.h.
-Results are checked against the committed reference outputs (tests/golden) and the numpy restatement of
+Results are checked against the committed reference outputs (tests/golden) and the CPU restatement of
 projectParallel."""
 import ctypes
 import json
@@ -272,7 +272,7 @@ def test_cpp_elas_gpu_class(tmp_path, golden, kitti_gray):
 
 
 def test_reproject_u8_any_size(svb, golden_meta):
-    """svb_reproject_u8 (no context, any map size) against the numpy restatement of projectParallel, bit for bit."""
+    """svb_reproject_u8 (no context, any map size) against the CPU restatement of projectParallel (oracle/project_port.c), bit for bit."""
     import parity
 
     rng = np.random.default_rng(3)

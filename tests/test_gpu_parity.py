@@ -483,7 +483,7 @@ def test_reference_profile_pairs(svb, ref, name):
 def test_kitti_mini_all_21_pairs(svb, ref, kitti_gray):
     """Every stereo pair of datasets/kitti_mini (BASELINE configs[0]) through the frame-batch pipeline with the driver's preset:
     disparity bit for bit against the live oracle and against the committed digests, support point counts included; the point
-    cloud of every frame against the numpy restatement of projectParallel."""
+    cloud of every frame against the CPU restatement of projectParallel."""
     n = 21
     L = np.stack([kitti_gray["L%d" % i] for i in range(n)])
     R = np.stack([kitti_gray["R%d" % i] for i in range(n)])

@@ -97,7 +97,7 @@ def test_oracle_prior_table(ref):
 
 
 def test_reproject_restatement_known_point(golden_meta):
-    """The numpy restatement of stereo_vision.cu:188-212,324 on hand-computed points."""
+    """The CPU restatement of stereo_vision.cu:188-212,324 (u8 conversion in numpy, projection in oracle/project_port.c) on hand-computed points."""
     Q = np.array(golden_meta["Q"])
     assert abs(Q[0, 3] + 738.7995529175) < 1e-6 and abs(Q[2, 3] - 1027.855158176) < 1e-6 and abs(Q[3, 2] - 1.861616069957) < 1e-9
     D = np.full((2, 3), -10.0, np.float32)
