@@ -86,3 +86,41 @@ def test_kitti_q_is_the_surveys(svb, calib_golden, golden_meta, tmp_path):
     out = svb.stereo_rectify(svb.load_calibration(p), (1242, 375))
     assert np.allclose(out["Q"], np.array(golden_meta["Q"]), rtol=1e-13, atol=1e-13)
     assert abs(out["Q"][0, 3] + 738.7995529175) < 1e-6 and abs(out["Q"][3, 2] - 1.861616069957) < 1e-9
+
+
+def test_yaml_reader_survives_corrupt_files(svb, calib_golden, tmp_path):
+    """Truncations, byte flips, absurd dimensions: svb_calib_load_yaml returns a calibration or an error, never crashes; a matrix
+    that claims more entries than the structure holds is refused (run under ASan / UBSan as well when the reader changes)."""
+    rng = np.random.default_rng(3)
+    c = calib_golden["cases"][0]
+    p = tmp_path / "good.yml"
+    write_yaml(p, c)
+    good = p.read_bytes()
+    q = tmp_path / "fuzz.yml"
+    n_err = n_ok = 0
+    for cut in range(0, len(good), 11):
+        q.write_bytes(good[:cut])
+        try:
+            svb.load_calibration(q)
+            n_ok += 1
+        except svb.SvbError:
+            n_err += 1
+    for _ in range(300):
+        b = bytearray(good)
+        for _ in range(int(rng.integers(1, 6))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        q.write_bytes(bytes(b))
+        try:
+            svb.load_calibration(q)
+            n_ok += 1
+        except svb.SvbError:
+            n_err += 1
+    assert n_err > 20 and n_ok > 0
+    many = ", ".join(["1.0"] * 5000)
+    for text in ("%YAML:1.0\nD1: !!opencv-matrix\n   rows: 1\n   cols: 5000\n   dt: d\n   data: [ " + many + " ]\n",
+                 "%YAML:1.0\nK1: !!opencv-matrix\n   rows: 2147483647\n   cols: 2147483647\n   dt: d\n   data: [ 1 ]\n",
+                 "%YAML:1.0\nK1: !!opencv-matrix\n   rows: -3\n   cols: 3\n   dt: d\n   data: [ " + many + " ]\n",
+                 "%YAML:1.0\nT: [ " + many + " ]\n", "K1: [", "", "\x00" * 64):
+        q.write_bytes(text.encode())
+        with pytest.raises(svb.SvbError):
+            svb.load_calibration(q)
