@@ -96,54 +96,6 @@ def test_sv_py_style_client(tmp_path, golden, kitti_gray):
     assert np.array_equal(z["col"], gray_to_bgra(kitti_gray["L7"]))
 
 
-SV_CLASS_CLIENT = r'''
-import sys
-import numpy as np
-root, yaml_path, npz_path, out_path, lib_path = sys.argv[1:6]
-sys.path.insert(0, root)
-import __graft_entry__ as g
-g.load_package()
-from elas_b200.sv import stereo_vision             # the reference's `from stereo_vision.sv import stereo_vision`
-z = np.load(npz_path)
-H, W = z["L0"].shape
-bgr = lambda g: np.ascontiguousarray(np.stack([g, g, g], -1))   # what cv2.imread hands the reference's callers
-s = stereo_vision(so_lib_path=lib_path, width=W, height=H, objectTracking=False, graphics=False, display=False, CAMERA_CALIBRATION_YAML=yaml_path)
-pts = np.array(s.generatePointCloud(bgr(z["L0"]), bgr(z["R0"])))
-pts7 = np.array(s.generatePointCloud(bgr(z["L7"]), bgr(z["R7"])))
-col = np.array(s.getColor())
-np.savez(out_path, pts=pts, pts7=pts7, col=col)
-print("client done", flush=True)
-del s                                               # __del__ -> clean() -> exit(0) (sv.py:191-192)
-print("not reached")
-'''
-
-
-def test_stereo_vision_class(tmp_path, golden, kitti_gray):
-    """The package's mirror of the reference's Python plugin class (elas_b200.sv.stereo_vision = stereo_vision/sv.py:154-192) on real
-    frames: BGR images in, the aliased double3 cloud out, against the oracle; teardown through __del__ like the reference."""
-    case, _ = kitti_case()
-    yaml_path = tmp_path / "kitti.yml"
-    write_yaml(yaml_path, case)
-    out_path = tmp_path / "out.npz"
-    script = tmp_path / "client.py"
-    script.write_text(SV_CLASS_CLIENT)
-    r = subprocess.run([sys.executable, str(script), ROOT, str(yaml_path), os.path.join(GOLDEN, "kitti_gray.npz"), str(out_path), LIB],
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-2000:]
-    assert "client done" in r.stdout and "not reached" not in r.stdout and "Program exitted successfully!" in r.stdout
-    z = np.load(out_path)
-    Q = np.array(case["Q"]).reshape(4, 4)
-    XR, XT = np.array(case["XR"]), np.array(case["XT"])
-    for key, gold in (("pts", "pipeline_0_D1"), ("pts7", "pipeline_7_D1")):
-        _, want = parity.reproject_oracle(golden[gold], Q, XR, XT)
-        got = z[key]
-        fin = np.isfinite(want).all(1)
-        assert np.array_equal(np.isfinite(got).all(1), fin)
-        rel = np.abs(got[fin] - want[fin]) / np.maximum(np.abs(want[fin]), 1e-300)
-        assert rel.max() <= 1e-4  # north_star: point cloud within 1e-4 relative (Q comes from the library's own stereoRectify)
-    assert np.array_equal(z["col"], gray_to_bgra(kitti_gray["L7"]))
-
-
 def test_point_cloud_bgra_stage(svb, golden, kitti_gray, golden_meta):
     L, R = kitti_gray["L0"], kitti_gray["R0"]
     H, W = L.shape
