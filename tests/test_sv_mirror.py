@@ -18,6 +18,9 @@ REFERENCE_INIT = [("so_lib_path", None), ("width", 1242), ("height", 375), ("def
                   ("display", False), ("scale", 1), ("pc_extrapolation", 1), ("YOLO_CFG", "src/yolo/yolov4-tiny.cfg"),
                   ("YOLO_WEIGHTS", "src/yolo/yolov4-tiny.weights"), ("YOLO_CLASSES", "src/yolo/classes.txt"),
                   ("CAMERA_CALIBRATION_YAML", "data/calibration/kitti_2011_09_26.yml"), ("subsampling", False)]
+# sv.py:180: the ctypes prototype, 14 of generatePointCloud's 16 parameters
+REFERENCE_ARGTYPES = ["c_char_p", "c_char_p", "c_char_p", "c_int", "c_int", "c_bool", "c_bool", "c_bool", "c_bool", "c_int", "c_int", "c_char_p",
+                      "c_char_p", "c_char_p"]
 REFERENCE_SV = "/root/reference/stereo_vision/sv.py"
 
 
@@ -52,18 +55,7 @@ def test_signature_against_the_reference_source():
     assert [a.arg for a in fns["generatePointCloud"].args.args] == ["self", "left", "right"]
     # the ctypes prototype: 14 argument types (sv.py:180)
     proto = [n for n in ast.walk(init) if isinstance(n, ast.Assign) and isinstance(n.targets[0], ast.Attribute) and n.targets[0].attr == "argtypes"][0]
-    ref_types = [e.attr for e in proto.value.elts]
-    m = mirror()
-    import numpy as np
-
-    os.environ["SVB_CLEAN_NO_EXIT"] = "1"
-    try:
-        s = m.stereo_vision(width=32, height=16)
-        assert [t.__name__ for t in s.sv.generatePointCloud.argtypes] == ref_types
-        assert s.sv.generatePointCloud.restype._shape_ == (32 * 16, 3) and s.sv.generatePointCloud.restype._dtype_ == np.float64
-        del s
-    finally:
-        del os.environ["SVB_CLEAN_NO_EXIT"]
+    assert [e.attr for e in proto.value.elts] == REFERENCE_ARGTYPES
 
 
 CLIENT = r'''
@@ -75,6 +67,9 @@ g.load_package()
 from elas_b200.sv import stereo_vision
 W, H = 96, 64
 s = stereo_vision(width=W, height=H, objectTracking=False, CAMERA_CALIBRATION_YAML="/nonexistent/calibration.yml")
+print("argtypes", ",".join(t.__name__ for t in s.sv.generatePointCloud.argtypes), flush=True)
+rt = s.sv.generatePointCloud.restype
+print("restype", rt._dtype_, rt._shape_, flush=True)
 rng = np.random.default_rng(1)
 L = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
 pts = s.generatePointCloud(L, L)
@@ -101,6 +96,7 @@ def test_call_and_teardown_behaviour(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     out = r.stdout
     assert "sum 0.0" in out and "client done" in out and "accepted a bad image" not in out
+    assert "argtypes " + ",".join(REFERENCE_ARGTYPES) in out and "restype float64 (%d, 3)" % (96 * 64) in out  # sv.py:167,180
     assert "Program exitted successfully!" in out and "not reached" not in out
     assert len([l for l in out.splitlines() if l.startswith("(FPS=")]) == 2  # the per-call line of stereo_vision.cu:630
     # SVB_CLEAN_NO_EXIT=1: clean() returns instead of ending the process
